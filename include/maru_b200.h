@@ -1,0 +1,156 @@
+/*
+ * maru_b200.h — C ABI of the B200-native leaf evaluator for takedarts/maru.
+ *
+ * This is the drop-in boundary for ONE path of the reference: batched neural-network
+ * evaluation of MCTS leaf positions (feature planes -> trunk -> heads -> policy/value).
+ * Everything here is plain C: pointers, sizes, int return codes (0 = ok, !=0 = error,
+ * text via maru_last_error()). No torch / C++ types cross this boundary.
+ *
+ * Reference interfaces replaced (paths relative to the reference repo root):
+ *   S1  deepgo::Model::Model(std::string, int32_t gpu, bool fp16, bool deterministic)
+ *       deepgo::Model::forward(float* in, float* out, uint32_t n)
+ *       deepgo::Model::isCuda()                     src/deepgo/native/cpp/Model.h:22-41
+ *                                                   src/deepgo/native/cpp/Model.cpp:62-100
+ *   S2  deepgo::Processor::execute(float*, float*, int32_t)
+ *                                                   src/deepgo/native/cpp/Processor.h:33
+ *                                                   src/deepgo/native/cpp/Processor.cpp:36-60
+ *       deepgo::Executor::{execute,_run,_forward}   src/deepgo/native/cpp/Executor.cpp:52-189
+ *   S3  deepgo::Board::getInputs(float*, color, komi, rule, superko)
+ *                                                   src/deepgo/native/cpp/Board.cpp:494-623
+ *       deepgo::Evaluator::evaluate(Board*, color)  src/deepgo/native/cpp/Evaluator.cpp:37-84
+ *   tensor contract                                 src/deepgo/config.py:37-50
+ *
+ * Row layouts (identical to the reference):
+ *   input  row: float32[11920] = planes [33][19][19] (plane, y, x) + 7 scalars
+ *   output row: float32[2169]  = planes [6][19][19] + 3 scalars
+ */
+#ifndef MARU_B200_H
+#define MARU_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MARU_MODEL_SIZE 19            /* config.py:37  MODEL_SIZE        */
+#define MARU_MODEL_FEATURES 32        /* config.py:39  MODEL_FEATURES    */
+#define MARU_MODEL_INFOS 7            /* config.py:41  MODEL_INFOS       */
+#define MARU_MODEL_PREDICTIONS 6      /* config.py:43  MODEL_PREDICTIONS */
+#define MARU_MODEL_VALUES 3           /* config.py:45  MODEL_VALUES      */
+#define MARU_INPUT_SIZE 11920         /* config.py:48  (32+1)*361 + 7    */
+#define MARU_OUTPUT_SIZE 2169         /* config.py:50  6*361 + 3         */
+
+#define MARU_BLACK 1
+#define MARU_WHITE (-1)
+#define MARU_RULE_CH 0
+#define MARU_RULE_JP 1
+#define MARU_RULE_COM 2
+
+/* cell byte of maru_state::cells */
+#define MARU_CELL_EMPTY 0u
+#define MARU_CELL_BLACK 1u
+#define MARU_CELL_WHITE 2u
+#define MARU_CELL_COLOR_MASK 3u
+#define MARU_CELL_LADDER 4u           /* Ren::shicho of the stone's group (Board.cpp:523)        */
+#define MARU_CELL_LIB_SHIFT 3         /* bits 3..6: min(#liberties, 8) of the group (Board.cpp:524) */
+#define MARU_NONE 0xFFu               /* "no move / no ko" coordinate                              */
+
+#define MARU_STATE_HAS_MASK 1u        /* maru_state::flags: move_mask is filled                    */
+
+/*
+ * Compact board record: everything Board::getInputs reads, 448 bytes instead of 47 680.
+ * Filled from the reference Board's PUBLIC getters (getWidth/getHeight/getColor/getRenSpace/
+ * isShicho/getHistories/getKo, Board.h:47-116) — see maru_b200/dropin/state_from_board.h.
+ */
+typedef struct maru_state {
+  uint8_t cells[368];      /* y*width+x over the width x height board; [361..367] zero          */
+  uint8_t width;           /* 1..19                                                              */
+  uint8_t height;          /* 1..19                                                              */
+  int8_t  color;           /* side to move: +1 black, -1 white                                   */
+  uint8_t rule;            /* MARU_RULE_*                                                        */
+  uint8_t superko;         /* 0/1                                                                */
+  uint8_t ko_x, ko_y;      /* Board::getKo(color) (Board.cpp:213-219); MARU_NONE if none          */
+  uint8_t flags;           /* MARU_STATE_*                                                       */
+  uint8_t hist[2][3][2];   /* [0]=black,[1]=white; [i]: i-th newest non-pass move (x,y); MARU_NONE */
+  float   komi;
+  uint8_t reserved[8];
+  uint8_t move_mask[48];   /* optional: bit (y*width+x) = legal && territory==EMPTY (Evaluator.cpp:60-68) */
+} maru_state;              /* sizeof == 448 */
+
+typedef struct maru_eval maru_eval;     /* one evaluator = one GPU, one stream, one weight replica */
+typedef struct maru_queue maru_queue;   /* leaf-batch queue over >=1 evaluators (Processor mirror)  */
+
+/* flags for maru_eval_create */
+#define MARU_FLAG_NO_GRAPH 1u           /* launch kernels directly instead of CUDA graphs           */
+
+typedef struct maru_eval_info {
+  int32_t blocks, channels, attn_every, heads, head_channels, value_channels;
+  int32_t n_attn;                       /* number of attention layers                               */
+  int32_t gpu_id, max_batch, sm_count;
+  int32_t launches_per_forward;         /* kernels launched by one forward_states of <= max_batch   */
+  int32_t reserved0;
+  double  flops_per_eval;               /* algorithmic FLOPs per 19x19 position (SURVEY 8d formula)  */
+  double  flops_per_eval_executed;      /* FLOPs the kernels execute per position (padding included) */
+  uint64_t n_forward, n_positions;      /* counters since create                                    */
+  double  device_ms_last;               /* CUDA-event time of the last forward (kernels only)       */
+} maru_eval_info;
+
+/* ---- lifetime (replaces Model::Model, Model.cpp:62-80) -------------------------------------- */
+/* weights_path: a weight pack written by `python -m maru_b200.convert <file>.model`; if the path
+ * does not end in ".b200" the sidecar "<path>.b200" is opened. gpu_id >= 0 (there is no CPU path:
+ * gpu_id < 0 is an error). */
+int  maru_eval_create(const char* weights_path, int gpu_id, int max_batch, unsigned flags,
+                      maru_eval** out);
+void maru_eval_destroy(maru_eval* e);
+int  maru_eval_get_info(maru_eval* e, maru_eval_info* info);
+
+/* ---- blocking forwards on HOST buffers (replace Model::forward, Model.cpp:88-100) ------------ */
+/* in: [n][11920] fp32 rows exactly as Board::getInputs writes them; out: [n][2169] fp32. */
+int  maru_eval_forward_planes(maru_eval* e, const float* in, float* out, int n);
+/* s: [n] compact records; encoding happens on the GPU (K1). out: [n][2169] fp32. */
+int  maru_eval_forward_states(maru_eval* e, const maru_state* s, float* out, int n);
+
+/* ---- device-resident forwards (inputs/outputs already in HBM; used by bench `value`) -------- */
+int  maru_eval_forward_states_device(maru_eval* e, const maru_state* d_states, float* d_out, int n);
+int  maru_eval_forward_planes_device(maru_eval* e, const float* d_in, float* d_out, int n);
+int  maru_eval_sync(maru_eval* e);
+
+/* ---- K1 alone: compact record -> reference fp32 rows (bit-exact Board::getInputs) ----------- */
+int  maru_encode_planes(maru_eval* e, const maru_state* s, float* out_rows, int n);         /* host */
+int  maru_encode_planes_device(maru_eval* e, const maru_state* d_s, float* d_rows, int n);  /* HBM  */
+
+/* ---- debugging / parity: activations of the last forward ------------------------------------- */
+/* Copies the trunk input (bf16 NHWC, padded geometry) of the last forward as fp32 NCHW planes
+ * [n][channels_in][19][19]; used by the parity tests to prove both ingest paths are identical. */
+int  maru_eval_debug_trunk_input(maru_eval* e, float* out, int n, int channels);
+/* Pre-softmax policy logits of the last forward: [n][2][361] fp32 (north_star tolerance is on logits). */
+int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
+
+/* ---- leaf-batch queue (replaces Processor/Executor/ExecutorJob, Processor.cpp, Executor.cpp) -- */
+/* Takes ownership of nothing: evaluators must outlive the queue. batch_size = drain cap
+ * (Executor.cpp:116). One worker thread + pinned double buffers per evaluator. */
+int  maru_queue_create(maru_eval** evals, int n_evals, int batch_size, maru_queue** out);
+void maru_queue_destroy(maru_queue* q);
+/* Thread-safe, blocking; same contract as Processor::execute(float*, float*, int32_t). */
+int  maru_queue_execute(maru_queue* q, const float* in, float* out, int n);
+/* Same, compact records in (the path the substitute Evaluator uses). */
+int  maru_queue_execute_states(maru_queue* q, const maru_state* s, float* out, int n);
+
+typedef struct maru_queue_stats {
+  uint64_t jobs, positions, batches;
+  uint64_t max_batch_seen;
+  double   wait_ms_total;               /* sum over jobs of enqueue -> completion                   */
+  double   device_ms_total;             /* sum over batches of CUDA-event forward time              */
+} maru_queue_stats;
+int  maru_queue_get_stats(maru_queue* q, maru_queue_stats* st);
+
+/* ---- errors ---------------------------------------------------------------------------------- */
+const char* maru_last_error(void);      /* thread-local text of the last failing call              */
+int  maru_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARU_B200_H */

@@ -1,0 +1,226 @@
+"""Architecture specification of the network this evaluator runs, as a scriptable PyTorch module.
+
+The reference ships NO network source: `Model::Model` just `torch::jit::load`s an opaque TorchScript
+file (reference src/deepgo/native/cpp/Model.cpp:77) whose only pinned properties are
+  * input  row float32[11920] = 33 planes x 19 x 19 + 7 scalars   (src/deepgo/config.py:37-48)
+  * output row float32[2169]  = 6 planes x 19 x 19 + 3 scalars    (src/deepgo/config.py:43-50)
+  * outputs are probabilities (plane 0 is used as a prior, Evaluator.cpp:66-69, Node.cpp:114,483)
+  * README.md:5 "nested-bottleneck convolutions and multi-head attention", names b<blocks>c<channels>.
+Everything else here is BUILDER-DEFINED and is the contract between
+  - this module (exported with torch.jit.script to a `.model` the UNMODIFIED reference runtime loads),
+  - maru_b200/convert.py (folds BN, casts to bf16, writes the `.b200` weight pack), and
+  - the sm_100a kernels in maru_b200/csrc (which implement exactly this arithmetic).
+
+This file is an authoring/export tool. The evaluator never calls `MaruNet.forward`; the only thing
+that executes it is the reference runtime (oracle) via the exported TorchScript file.
+"""
+from __future__ import annotations
+
+import math
+from typing import List
+
+import torch
+from torch import nn
+
+MODEL_SIZE = 19
+CELLS = MODEL_SIZE * MODEL_SIZE
+IN_PLANES = 33
+IN_INFOS = 7
+INPUT_SIZE = IN_PLANES * CELLS + IN_INFOS      # 11920
+OUT_PLANES = 6
+OUT_VALUES = 3
+OUTPUT_SIZE = OUT_PLANES * CELLS + OUT_VALUES  # 2169
+BN_EPS = 1e-5
+
+
+class ConvBN(nn.Module):
+    def __init__(self, cin: int, cout: int, k: int):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=k // 2, bias=False)
+        self.bn = nn.BatchNorm2d(cout, eps=BN_EPS)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.bn(self.conv(x))
+
+
+class Inner(nn.Module):
+    """One residual pair of 3x3 convolutions inside the bottleneck."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.c1 = ConvBN(c, c, 3)
+        self.c2 = ConvBN(c, c, 3)
+
+    def forward(self, r: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+        s = torch.relu(self.c1(r)) * m
+        s = self.c2(s) * m
+        return torch.relu(r + s)
+
+
+class NestedBottleneck(nn.Module):
+    """C -> C/2 (1x1), two residual 3x3 pairs at C/2, C/2 -> C (1x1), outer residual."""
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.reduce = ConvBN(c, c // 2, 1)
+        self.inner0 = Inner(c // 2)
+        self.inner1 = Inner(c // 2)
+        self.expand = ConvBN(c // 2, c, 1)
+
+    def forward(self, h: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+        r = torch.relu(self.reduce(h)) * m
+        r = self.inner0(r, m)
+        r = self.inner1(r, m)
+        return torch.relu(h + self.expand(r) * m)
+
+
+class BoardAttention(nn.Module):
+    """Pre-norm multi-head self-attention over the 361 board cells; off-board keys are masked."""
+
+    def __init__(self, c: int, head_dim: int):
+        super().__init__()
+        self.heads = c // head_dim
+        self.head_dim = head_dim
+        self.norm = nn.BatchNorm2d(c, eps=BN_EPS)
+        self.qkv = nn.Conv2d(c, 3 * c, 1, bias=True)
+        self.proj = nn.Conv2d(c, c, 1, bias=True)
+
+    def forward(self, h: torch.Tensor, m: torch.Tensor) -> torch.Tensor:
+        n, c, t = h.shape[0], h.shape[1], h.shape[2] * h.shape[3]
+        qkv = self.qkv(self.norm(h)).reshape(n, 3, self.heads, self.head_dim, t)
+        q = qkv[:, 0].transpose(-1, -2)                       # [n, H, T, d]
+        k = qkv[:, 1]                                         # [n, H, d, T]
+        v = qkv[:, 2].transpose(-1, -2)                       # [n, H, T, d]
+        s = torch.matmul(q, k) * (1.0 / math.sqrt(self.head_dim))
+        key_mask = m.reshape(n, 1, 1, t)
+        s = s.masked_fill(key_mask < 0.5, float('-inf'))
+        a = torch.softmax(s, dim=-1)
+        o = torch.matmul(a, v).transpose(-1, -2).reshape(n, c, h.shape[2], h.shape[3])
+        return h + self.proj(o) * m
+
+
+class Heads(nn.Module):
+    def __init__(self, c: int, ch: int, cv: int):
+        super().__init__()
+        self.g = ConvBN(c, ch, 1)
+        self.planes = nn.Conv2d(ch, OUT_PLANES, 1, bias=True)
+        self.fc1 = nn.Linear(2 * ch, cv)
+        self.fc2 = nn.Linear(cv, OUT_VALUES)
+
+    def forward(self, h: torch.Tensor, m: torch.Tensor) -> List[torch.Tensor]:
+        n, t = h.shape[0], h.shape[2] * h.shape[3]
+        g = torch.relu(self.g(h)) * m
+        z = self.planes(g).reshape(n, 6, t)
+        mf = m.reshape(n, 1, t)
+        # planes 0,1: softmax over ON-BOARD cells (off-board exactly 0)
+        pol_logits = z[:, 0:2].masked_fill(mf < 0.5, float('-inf'))
+        pol = torch.softmax(pol_logits, dim=-1)
+        # planes 2..4: 3-way class softmax per cell; plane 5: sigmoid
+        ter = torch.softmax(z[:, 2:5], dim=1) * mf
+        val = torch.sigmoid(z[:, 5:6]) * mf
+        # value / score scalars from pooled features
+        gf = g.reshape(n, g.shape[1], t)
+        mean = gf.sum(-1) / mf.sum(-1)
+        mx = gf.max(-1)[0]
+        v = self.fc2(torch.relu(self.fc1(torch.cat([mean, mx], dim=1))))
+        scal = torch.cat([torch.sigmoid(v[:, 0:1]), v[:, 1:3]], dim=1)
+        out = torch.cat([pol, ter, val], dim=1).reshape(n, 6 * t)
+        return [torch.cat([out, scal], dim=1), z[:, 0:2]]
+
+
+class MaruNet(nn.Module):
+    """b<blocks>c<channels>: stem, `blocks` nested bottlenecks, attention after every
+    `attn_every`-th block, policy/territory/value heads. [N,11920] fp32 -> [N,2169] fp32."""
+
+    def __init__(self, blocks: int = 4, channels: int = 128, attn_every: int = 2,
+                 head_dim: int = 32, head_channels: int = 32, value_channels: int = 64):
+        super().__init__()
+        assert channels % 32 == 0 and channels % head_dim == 0
+        self.stem_conv = nn.Conv2d(IN_PLANES, channels, 3, padding=1, bias=False)
+        self.stem_info = nn.Linear(IN_INFOS, channels, bias=False)
+        self.stem_bn = nn.BatchNorm2d(channels, eps=BN_EPS)
+        self.blocks = nn.ModuleList([NestedBottleneck(channels) for _ in range(blocks)])
+        n_attn = blocks // attn_every if attn_every > 0 else 0
+        self.attn = nn.ModuleList([BoardAttention(channels, head_dim) for _ in range(n_attn)])
+        self.attn_every = attn_every
+        self.heads = Heads(channels, head_channels, value_channels)
+        # hyper-parameters travel inside the TorchScript archive's state_dict
+        self.register_buffer('arch', torch.tensor(
+            [blocks, channels, attn_every, head_dim, head_channels, value_channels, 0, 0],
+            dtype=torch.int32))
+
+    def _forward(self, x: torch.Tensor) -> List[torch.Tensor]:
+        n = x.shape[0]
+        planes = x[:, :33 * 361].reshape(n, 33, 19, 19)
+        info = x[:, 33 * 361:]
+        m = planes[:, 32:33]
+        h = self.stem_conv(planes) + self.stem_info(info).reshape(n, -1, 1, 1)
+        h = torch.relu(self.stem_bn(h)) * m
+        ai = 0
+        for i, blk in enumerate(self.blocks):
+            h = blk(h, m)
+            if self.attn_every > 0 and (i + 1) % self.attn_every == 0:
+                for j, att in enumerate(self.attn):
+                    if j == ai:
+                        h = att(h, m)
+                ai += 1
+        return self.heads(h, m)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self._forward(x)[0]
+
+    @torch.jit.export
+    def forward_with_logits(self, x: torch.Tensor) -> List[torch.Tensor]:
+        """[N,2169] outputs and the pre-softmax policy logits [N,2,361] (tolerance is on logits)."""
+        return self._forward(x)
+
+
+def randomize_(net: nn.Module, seed: int = 0) -> nn.Module:
+    """Random-init weights as SURVEY 8(d) prescribes: default conv/linear init under
+    torch.manual_seed(seed); BN running_mean~N(0,0.1), running_var~U(0.5,1.5), weight~U(0.5,1.5),
+    bias~N(0,0.1) so that BN folding is actually exercised."""
+    g = torch.Generator().manual_seed(seed + 1)
+    for mod in net.modules():
+        if isinstance(mod, nn.BatchNorm2d):
+            with torch.no_grad():
+                mod.running_mean.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+                mod.running_var.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.weight.copy_(torch.rand(mod.num_features, generator=g) + 0.5)
+                mod.bias.copy_(torch.randn(mod.num_features, generator=g) * 0.1)
+    return net
+
+
+def build(blocks: int = 4, channels: int = 128, attn_every: int = 2, head_dim: int = 32,
+          head_channels: int = 32, value_channels: int = 64, seed: int = 0) -> MaruNet:
+    torch.manual_seed(seed)
+    net = MaruNet(blocks, channels, attn_every, head_dim, head_channels, value_channels)
+    randomize_(net, seed)
+    return net.eval()
+
+
+def export(net: MaruNet, path: str) -> None:
+    """Write the TorchScript `.model` the reference runtime loads (Model.cpp:77)."""
+    torch.jit.script(net).save(path)
+
+
+def flops_per_eval(blocks: int, channels: int, attn_every: int, tokens: int = CELLS,
+                   head_channels: int = 32, value_channels: int = 64) -> float:
+    """Algorithmic FLOPs of one position (SURVEY 8d formula), T = tokens actually on the board."""
+    t, c = tokens, channels
+    stem = 2 * t * IN_PLANES * c * 9 + 2 * IN_INFOS * c
+    block = 2 * (2 * t * c * (c // 2)) + 4 * (2 * t * (c // 2) ** 2 * 9)
+    mha = 2 * t * c * 3 * c + 4 * t * t * c + 2 * t * c * c
+    n_attn = blocks // attn_every if attn_every > 0 else 0
+    heads = 2 * t * c * head_channels + 2 * t * head_channels * OUT_PLANES \
+        + 2 * (2 * head_channels) * value_channels + 2 * value_channels * OUT_VALUES
+    return float(stem + blocks * block + n_attn * mha + heads)
+
+
+CONFIGS = {
+    # BASELINE.json configs[1]: the metric's model
+    'b4c128': dict(blocks=4, channels=128, attn_every=2, head_dim=32),
+    # BASELINE.json configs[2]: "larger nested-bottleneck+attention model (~10 blocks x 256 ch)"
+    'b10c256': dict(blocks=10, channels=256, attn_every=2, head_dim=32),
+    # tiny net for fast CPU tests
+    'b2c64': dict(blocks=2, channels=64, attn_every=1, head_dim=32),
+}
