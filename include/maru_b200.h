@@ -116,17 +116,31 @@ int  maru_eval_forward_states(maru_eval* e, const maru_state* s, float* out, int
 int  maru_eval_forward_states_device(maru_eval* e, const maru_state* d_states, float* d_out, int n);
 int  maru_eval_forward_planes_device(maru_eval* e, const float* d_in, float* d_out, int n);
 int  maru_eval_sync(maru_eval* e);
+void* maru_eval_stream(maru_eval* e);   /* the evaluator's cudaStream_t (for CUDA-event timing)      */
 
 /* ---- K1 alone: compact record -> reference fp32 rows (bit-exact Board::getInputs) ----------- */
 int  maru_encode_planes(maru_eval* e, const maru_state* s, float* out_rows, int n);         /* host */
 int  maru_encode_planes_device(maru_eval* e, const maru_state* d_s, float* d_rows, int n);  /* HBM  */
 
 /* ---- debugging / parity: activations of the last forward ------------------------------------- */
-/* Copies the trunk input (bf16 NHWC, padded geometry) of the last forward as fp32 NCHW planes
- * [n][channels_in][19][19]; used by the parity tests to prove both ingest paths are identical. */
-int  maru_eval_debug_trunk_input(maru_eval* e, float* out, int n, int channels);
+/* Copies `channels` channels of an activation buffer of the last forward as fp32 [n][channels][361]
+ * (19x19 cells, halo rows dropped). which: 0 trunk input x0 (64 ch), 1 h (C), 2 r (C/2), 3 s (C/2),
+ * 4 qkv (3C), 5 attention output o (C), 6 head features g (Ch). */
+#define MARU_BUF_X0 0
+#define MARU_BUF_H 1
+#define MARU_BUF_R 2
+#define MARU_BUF_S 3
+#define MARU_BUF_QKV 4
+#define MARU_BUF_O 5
+#define MARU_BUF_G 6
+int  maru_eval_debug_planes(maru_eval* e, int which, float* out, int n, int channels);
 /* Pre-softmax policy logits of the last forward: [n][2][361] fp32 (north_star tolerance is on logits). */
 int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
+/* Debug knobs. key 0: stop the launch sequence after `value` trunk launches (<0: run everything;
+ * the heads then do not run). key 1: UMMA descriptor experiment bits (bring-up only; 0 = normal). */
+#define MARU_DBG_STOP_AFTER 0
+#define MARU_DBG_DESC_BITS 1
+int  maru_eval_debug_set(maru_eval* e, int key, int value);
 
 /* ---- leaf-batch queue (replaces Processor/Executor/ExecutorJob, Processor.cpp, Executor.cpp) -- */
 /* Takes ownership of nothing: evaluators must outlive the queue. batch_size = drain cap

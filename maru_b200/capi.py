@@ -1,0 +1,289 @@
+"""ctypes bindings of include/maru_b200.h and the host-side mirror of the reference's Python API.
+
+`Processor` mirrors reference src/deepgo/processor.py:9-39 (same constructor arguments, same
+`execute(np.float32[N,11920]) -> np.float32[N,2169]`, same FileNotFoundError), so code written
+against `deepgo.processor.Processor` runs unchanged; `execute_states` is the added compact path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+INPUT_SIZE = 11920    # reference src/deepgo/config.py:48
+OUTPUT_SIZE = 2169    # reference src/deepgo/config.py:50
+STATE_SIZE = 448      # sizeof(maru_state)
+FLAG_NO_GRAPH = 1
+
+
+class MaruB200Error(RuntimeError):
+    pass
+
+
+class EvalInfo(C.Structure):
+    _fields_ = [('blocks', C.c_int32), ('channels', C.c_int32), ('attn_every', C.c_int32),
+                ('heads', C.c_int32), ('head_channels', C.c_int32), ('value_channels', C.c_int32),
+                ('n_attn', C.c_int32), ('gpu_id', C.c_int32), ('max_batch', C.c_int32),
+                ('sm_count', C.c_int32), ('launches_per_forward', C.c_int32),
+                ('reserved0', C.c_int32), ('flops_per_eval', C.c_double),
+                ('flops_per_eval_executed', C.c_double), ('n_forward', C.c_uint64),
+                ('n_positions', C.c_uint64), ('device_ms_last', C.c_double)]
+
+
+class QueueStats(C.Structure):
+    _fields_ = [('jobs', C.c_uint64), ('positions', C.c_uint64), ('batches', C.c_uint64),
+                ('max_batch_seen', C.c_uint64), ('wait_ms_total', C.c_double),
+                ('device_ms_total', C.c_double)]
+
+
+# every symbol include/maru_b200.h declares (tests check that the library exports all of them)
+ABI_SYMBOLS = [
+    'maru_eval_create', 'maru_eval_destroy', 'maru_eval_get_info', 'maru_eval_forward_planes',
+    'maru_eval_forward_states', 'maru_eval_forward_states_device',
+    'maru_eval_forward_planes_device', 'maru_eval_sync', 'maru_eval_stream', 'maru_encode_planes',
+    'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
+    'maru_eval_debug_set',
+    'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
+    'maru_queue_get_stats', 'maru_last_error', 'maru_abi_version',
+]
+
+
+def lib_path() -> Path:
+    env = os.environ.get('MARU_B200_LIB')
+    return Path(env) if env else Path(__file__).resolve().parent / 'lib' / 'libmaru_b200.so'
+
+
+_lib = None
+
+
+def load_library():
+    """Load libmaru_b200.so (in-tree build: `make -C maru_b200/csrc`). Fails loudly if absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    p = lib_path()
+    if not p.exists():
+        raise MaruB200Error(f'{p} not found: build it with `make -C maru_b200/csrc` '
+                            '(or python -c "import __graft_entry__ as g; g.build()")')
+    lib = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+    vp, ci, cu = C.c_void_p, C.c_int, C.c_uint
+    lib.maru_eval_create.argtypes = [C.c_char_p, ci, ci, cu, C.POINTER(vp)]
+    lib.maru_eval_destroy.argtypes = [vp]
+    lib.maru_eval_destroy.restype = None
+    lib.maru_eval_get_info.argtypes = [vp, C.POINTER(EvalInfo)]
+    lib.maru_eval_forward_planes.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_forward_states.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_forward_states_device.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_forward_planes_device.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_sync.argtypes = [vp]
+    lib.maru_eval_stream.argtypes = [vp]
+    lib.maru_eval_stream.restype = vp
+    lib.maru_encode_planes.argtypes = [vp, vp, vp, ci]
+    lib.maru_encode_planes_device.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_debug_planes.argtypes = [vp, ci, vp, ci, ci]
+    lib.maru_eval_debug_set.argtypes = [vp, ci, ci]
+    lib.maru_eval_debug_policy_logits.argtypes = [vp, vp, ci]
+    lib.maru_queue_create.argtypes = [C.POINTER(vp), ci, ci, C.POINTER(vp)]
+    lib.maru_queue_destroy.argtypes = [vp]
+    lib.maru_queue_destroy.restype = None
+    lib.maru_queue_execute.argtypes = [vp, vp, vp, ci]
+    lib.maru_queue_execute_states.argtypes = [vp, vp, vp, ci]
+    lib.maru_queue_get_stats.argtypes = [vp, C.POINTER(QueueStats)]
+    lib.maru_last_error.restype = C.c_char_p
+    lib.maru_abi_version.restype = ci
+    _lib = lib
+    return lib
+
+
+def _check(lib, rc: int, what: str) -> None:
+    if rc != 0:
+        raise MaruB200Error(f'{what}: {lib.maru_last_error().decode(errors="replace")}')
+
+
+def ensure_pack(model: str | Path) -> Path:
+    """Return the `.b200` weight pack of a `.model` file, converting it if it is missing or stale."""
+    model = Path(model)
+    if model.suffix == '.b200':
+        return model
+    pack = Path(str(model) + '.b200')
+    if not pack.exists() or pack.stat().st_mtime < model.stat().st_mtime:
+        from .convert import convert  # the loader is the only torch user
+        convert(str(model), str(pack))
+    return pack
+
+
+def _rows(x: np.ndarray, width: int, dtype) -> np.ndarray:
+    x = np.ascontiguousarray(x, dtype=dtype)
+    if x.ndim == 1:
+        x = x.reshape(1, -1)
+    if x.ndim != 2 or x.shape[1] != width:
+        raise ValueError(f'expected [N,{width}] {np.dtype(dtype).name}, got {x.shape}')
+    return x
+
+
+class Evaluator:
+    """One evaluator = one GPU, one stream, one weight replica (mirrors deepgo::Model,
+    reference src/deepgo/native/cpp/Model.h:12-58)."""
+
+    def __init__(self, model: str | Path, gpu: int = 0, max_batch: int = 256, flags: int = 0):
+        if not Path(model).exists():
+            raise FileNotFoundError(f'File not found: {model}')
+        self.lib = load_library()
+        pack = ensure_pack(model)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.maru_eval_create(str(pack).encode(), gpu, max_batch, flags,
+                                                   C.byref(h)), 'maru_eval_create')
+        self.handle = h
+        self.max_batch = max_batch
+
+    def close(self) -> None:
+        if getattr(self, 'handle', None):
+            self.lib.maru_eval_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+    def info(self) -> EvalInfo:
+        inf = EvalInfo()
+        self.lib.maru_eval_get_info(self.handle, C.byref(inf))
+        return inf
+
+    def forward(self, inputs: np.ndarray) -> np.ndarray:
+        """[N,11920] fp32 reference rows -> [N,2169] fp32 (Model::forward, Model.cpp:88-100)."""
+        x = _rows(inputs, INPUT_SIZE, np.float32)
+        out = np.zeros((x.shape[0], OUTPUT_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_eval_forward_planes(self.handle, x.ctypes.data,
+                                                           out.ctypes.data, x.shape[0]),
+               'maru_eval_forward_planes')
+        return out
+
+    def forward_states(self, states: np.ndarray) -> np.ndarray:
+        """[N,448] uint8 compact records -> [N,2169] fp32; encoding runs on the GPU (K1)."""
+        s = _rows(states, STATE_SIZE, np.uint8)
+        out = np.zeros((s.shape[0], OUTPUT_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_eval_forward_states(self.handle, s.ctypes.data,
+                                                           out.ctypes.data, s.shape[0]),
+               'maru_eval_forward_states')
+        return out
+
+    def encode_planes(self, states: np.ndarray) -> np.ndarray:
+        """[N,448] compact records -> [N,11920] fp32 rows, bit-exact Board::getInputs."""
+        s = _rows(states, STATE_SIZE, np.uint8)
+        out = np.zeros((s.shape[0], INPUT_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_encode_planes(self.handle, s.ctypes.data, out.ctypes.data,
+                                                     s.shape[0]), 'maru_encode_planes')
+        return out
+
+    def debug_planes(self, which: int, n: int, channels: int) -> np.ndarray:
+        """Activation buffer `which` (MARU_BUF_*) of the last forward as fp32 [n][channels][361]."""
+        out = np.zeros((n, channels, 361), np.float32)
+        _check(self.lib, self.lib.maru_eval_debug_planes(self.handle, which, out.ctypes.data, n,
+                                                         channels), 'maru_eval_debug_planes')
+        return out
+
+    def debug_set(self, key: int, value: int) -> None:
+        _check(self.lib, self.lib.maru_eval_debug_set(self.handle, key, value),
+               'maru_eval_debug_set')
+
+    def debug_policy_logits(self, n: int) -> np.ndarray:
+        out = np.zeros((n, 2, 361), np.float32)
+        _check(self.lib, self.lib.maru_eval_debug_policy_logits(self.handle, out.ctypes.data, n),
+               'debug_policy_logits')
+        return out
+
+    # device-resident entry points (raw device pointers as ints, e.g. torch_tensor.data_ptr())
+    def forward_states_device(self, d_states: int, d_out: int, n: int) -> None:
+        _check(self.lib, self.lib.maru_eval_forward_states_device(self.handle, d_states, d_out, n),
+               'maru_eval_forward_states_device')
+
+    def forward_planes_device(self, d_in: int, d_out: int, n: int) -> None:
+        _check(self.lib, self.lib.maru_eval_forward_planes_device(self.handle, d_in, d_out, n),
+               'maru_eval_forward_planes_device')
+
+    def encode_planes_device(self, d_states: int, d_rows: int, n: int) -> None:
+        _check(self.lib, self.lib.maru_encode_planes_device(self.handle, d_states, d_rows, n),
+               'maru_encode_planes_device')
+
+    def sync(self) -> None:
+        _check(self.lib, self.lib.maru_eval_sync(self.handle), 'maru_eval_sync')
+
+    def stream(self) -> int:
+        return int(self.lib.maru_eval_stream(self.handle) or 0)
+
+
+class LeafQueue:
+    """Leaf-batch queue over one or more evaluators (maru_queue_*; mirrors deepgo::Processor +
+    Executor, reference Processor.cpp:17-60 / Executor.cpp:52-189). Thread-safe, blocking."""
+
+    def __init__(self, evaluators: Sequence[Evaluator], batch_size: int = 2048):
+        self.lib = load_library()
+        self.evaluators = list(evaluators)
+        arr = (C.c_void_p * len(self.evaluators))(*[e.handle for e in self.evaluators])
+        h = C.c_void_p()
+        _check(self.lib, self.lib.maru_queue_create(arr, len(self.evaluators), batch_size,
+                                                    C.byref(h)), 'maru_queue_create')
+        self.handle = h
+
+    def close(self) -> None:
+        if getattr(self, 'handle', None):
+            self.lib.maru_queue_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+    def execute(self, inputs: np.ndarray) -> np.ndarray:
+        x = _rows(inputs, INPUT_SIZE, np.float32)
+        out = np.zeros((x.shape[0], OUTPUT_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_queue_execute(self.handle, x.ctypes.data, out.ctypes.data,
+                                                     x.shape[0]), 'maru_queue_execute')
+        return out
+
+    def execute_states(self, states: np.ndarray) -> np.ndarray:
+        s = _rows(states, STATE_SIZE, np.uint8)
+        out = np.zeros((s.shape[0], OUTPUT_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_queue_execute_states(self.handle, s.ctypes.data,
+                                                            out.ctypes.data, s.shape[0]),
+               'maru_queue_execute_states')
+        return out
+
+    def stats(self) -> QueueStats:
+        st = QueueStats()
+        self.lib.maru_queue_get_stats(self.handle, C.byref(st))
+        return st
+
+
+class Processor:
+    """Drop-in for `deepgo.processor.Processor` (reference src/deepgo/processor.py:9-39).
+
+    Same arguments and behaviour: `gpus` lists CUDA ordinals (one evaluator per gpu x
+    threads_par_gpu, least-loaded dispatch). Differences forced by the B200-only design:
+    `gpus=[-1]` (CPU) raises instead of silently computing on the host; `fp16` is accepted and
+    ignored (the trunk always runs bf16 tensor-core math with fp32 accumulation);
+    `deterministic` is accepted (the kernels are run-to-run deterministic anyway)."""
+
+    def __init__(self, model: str | Path, gpus: List[int] = [0], batch_size: int = 2048,
+                 fp16: bool = False, deterministic: bool = False, threads_par_gpu: int = 1,
+                 max_batch: Optional[int] = None) -> None:
+        if not Path(model).exists():
+            raise FileNotFoundError(f'File not found: {model}')
+        if any(g < 0 for g in gpus):
+            raise MaruB200Error('maru_b200 has no CPU path: gpus must be CUDA ordinals >= 0')
+        mb = max_batch or min(batch_size, 2048)
+        self.evaluators = [Evaluator(model, g, mb) for g in gpus for _ in range(threads_par_gpu)]
+        self.queue = LeafQueue(self.evaluators, batch_size)
+
+    def execute(self, inputs: np.ndarray) -> np.ndarray:
+        return self.queue.execute(inputs)
+
+    def execute_states(self, states: np.ndarray) -> np.ndarray:
+        return self.queue.execute_states(states)
+
+    def close(self) -> None:
+        self.queue.close()
+        for e in self.evaluators:
+            e.close()

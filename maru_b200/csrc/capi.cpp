@@ -1,0 +1,189 @@
+// capi.cpp — extern "C" surface of libmaru_b200.so (declared in include/maru_b200.h).
+#include <cstring>
+#include <new>
+
+#include "engine.h"
+
+using maru::Engine;
+
+static Engine* E(maru_eval* e) { return reinterpret_cast<Engine*>(e); }
+
+#define CKC(expr)                                                               \
+  do {                                                                          \
+    cudaError_t _e = (expr);                                                    \
+    if (_e != cudaSuccess) {                                                    \
+      maru::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));      \
+      return 1;                                                                 \
+    }                                                                           \
+  } while (0)
+
+extern "C" {
+
+int maru_abi_version(void) { return 1; }
+
+const char* maru_last_error(void) { return maru::g_last_error.c_str(); }
+
+int maru_eval_create(const char* weights_path, int gpu_id, int max_batch, unsigned flags,
+                     maru_eval** out) {
+  if (weights_path == nullptr || out == nullptr) {
+    maru::set_error("maru_eval_create: null argument");
+    return 1;
+  }
+  *out = nullptr;
+  Engine* e = new (std::nothrow) Engine();
+  if (e == nullptr) {
+    maru::set_error("out of memory");
+    return 1;
+  }
+  if (e->init(weights_path, gpu_id, max_batch, flags)) {
+    const std::string keep = maru::g_last_error;
+    delete e;
+    maru::set_error(keep);
+    return 1;
+  }
+  *out = reinterpret_cast<maru_eval*>(e);
+  return 0;
+}
+
+void maru_eval_destroy(maru_eval* e) { delete E(e); }
+
+int maru_eval_get_info(maru_eval* ev, maru_eval_info* info) {
+  if (ev == nullptr || info == nullptr) return 1;
+  Engine* e = E(ev);
+  std::memset(info, 0, sizeof(*info));
+  info->blocks = e->blocks;
+  info->channels = e->C;
+  info->attn_every = e->attn_every;
+  info->heads = e->C / e->head_dim;
+  info->head_channels = e->Ch;
+  info->value_channels = e->Cv;
+  info->n_attn = e->n_attn;
+  info->gpu_id = e->gpu_id;
+  info->max_batch = e->max_batch;
+  info->sm_count = e->sm_count;
+  info->launches_per_forward = e->launches_per_forward;
+  info->flops_per_eval = e->flops_alg;
+  info->flops_per_eval_executed = e->flops_exec;
+  info->n_forward = e->n_forward;
+  info->n_positions = e->n_positions;
+  info->device_ms_last = e->device_ms_last;
+  return 0;
+}
+
+int maru_eval_forward_planes(maru_eval* e, const float* in, float* out, int n) {
+  if (e == nullptr || in == nullptr || out == nullptr || n < 0) {
+    maru::set_error("maru_eval_forward_planes: bad argument");
+    return 1;
+  }
+  return E(e)->forward_host(maru::KIND_PLANES, in, out, n);
+}
+
+int maru_eval_forward_states(maru_eval* e, const maru_state* s, float* out, int n) {
+  if (e == nullptr || s == nullptr || out == nullptr || n < 0) {
+    maru::set_error("maru_eval_forward_states: bad argument");
+    return 1;
+  }
+  return E(e)->forward_host(maru::KIND_STATES, s, out, n);
+}
+
+int maru_eval_forward_states_device(maru_eval* ev, const maru_state* d_states, float* d_out, int n) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  for (int off = 0; off < n; off += e->max_batch) {
+    const int m = n - off < e->max_batch ? n - off : e->max_batch;
+    if (e->forward_device(maru::KIND_STATES, d_states + off, d_out + (size_t)off * maru::OUT_ROW, m))
+      return 1;
+  }
+  return 0;
+}
+
+int maru_eval_forward_planes_device(maru_eval* ev, const float* d_in, float* d_out, int n) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  for (int off = 0; off < n; off += e->max_batch) {
+    const int m = n - off < e->max_batch ? n - off : e->max_batch;
+    if (e->forward_device(maru::KIND_PLANES, d_in + (size_t)off * maru::IN_ROW,
+                          d_out + (size_t)off * maru::OUT_ROW, m))
+      return 1;
+  }
+  return 0;
+}
+
+int maru_eval_sync(maru_eval* ev) {
+  Engine* e = E(ev);
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+void* maru_eval_stream(maru_eval* ev) { return ev ? (void*)E(ev)->stream : nullptr; }
+
+int maru_encode_planes(maru_eval* e, const maru_state* s, float* out_rows, int n) {
+  if (e == nullptr || s == nullptr || out_rows == nullptr || n < 0) {
+    maru::set_error("maru_encode_planes: bad argument");
+    return 1;
+  }
+  return E(e)->encode_rows_host(s, out_rows, n);
+}
+
+int maru_encode_planes_device(maru_eval* ev, const maru_state* d_s, float* d_rows, int n) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(maru::launch_encode_rows(d_s, d_rows, n, nullptr, e->stream));
+  return 0;
+}
+
+int maru_eval_debug_planes(maru_eval* ev, int which, float* out, int n, int channels) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  const __nv_bfloat16* bufs[7] = {e->x0, e->h, e->r, e->s, e->qkv, e->o, e->g};
+  const int chans[7] = {maru::STEM_CIN, e->C, e->C / 2, e->C / 2, 3 * e->C, e->C, e->Ch};
+  if (which < 0 || which > 6 || bufs[which] == nullptr || n > e->max_batch || channels > chans[which]) {
+    maru::set_error("maru_eval_debug_planes: bad argument");
+    return 1;
+  }
+  CKC(cudaSetDevice(e->gpu_id));
+  float* d = nullptr;
+  const size_t bytes = (size_t)n * channels * maru::CELLS * 4;
+  CKC(cudaMalloc(&d, bytes));
+  cudaError_t le = maru::launch_planes_to_nchw(bufs[which], e->rows_alloc, channels, d, n, e->stream);
+  if (le == cudaSuccess) le = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, e->stream);
+  if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
+  cudaFree(d);
+  CKC(le);
+  return 0;
+}
+
+int maru_eval_debug_set(maru_eval* ev, int key, int value) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(cudaStreamSynchronize(e->stream));
+  e->clear_graphs();
+  if (key == MARU_DBG_STOP_AFTER) e->dbg_stop_after = value;
+  else if (key == MARU_DBG_DESC_BITS) e->dbg_desc = value;
+  else {
+    maru::set_error("maru_eval_debug_set: unknown key");
+    return 1;
+  }
+  return 0;
+}
+
+int maru_eval_debug_policy_logits(maru_eval* ev, float* out, int n) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (n > e->max_batch) {
+    maru::set_error("maru_eval_debug_policy_logits: n > max_batch");
+    return 1;
+  }
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(cudaMemcpyAsync(out, e->d_logits, (size_t)n * 2 * maru::CELLS * 4, cudaMemcpyDeviceToHost,
+                      e->stream));
+  CKC(cudaStreamSynchronize(e->stream));
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,539 @@
+// engine.cu — the evaluator behind the C ABI (include/maru_b200.h): weight pack -> device buffers,
+// activation planes, the launch sequence of one forward, CUDA-graph capture per batch bucket,
+// pinned staging and the blocking / device-resident entry points.
+//
+// Mirrors deepgo::Model (reference src/deepgo/native/cpp/Model.cpp:62-100): construct from a file +
+// gpu id, forward(float* in, float* out, n) on host buffers.  There is NO CPU path: gpu_id < 0, a
+// missing device or a failed launch is an error code, never a fallback.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+
+namespace maru {
+
+thread_local std::string g_last_error;
+void set_error(const std::string& s) { g_last_error = s; }
+
+#define CK(expr)                                                                         \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                     \
+      return 1;                                                                          \
+    }                                                                                    \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------
+// weight pack (written by maru_b200/convert.py)
+// ------------------------------------------------------------------------------------------
+#pragma pack(push, 1)
+struct PackHeader {
+  char magic[8];  // "MARUB200"
+  uint32_t version;
+  uint32_t n_tensors;
+  int32_t arch[8];  // blocks, channels, attn_every, head_dim, head_channels, value_channels, 0, 0
+};
+struct PackEntry {
+  char name[48];
+  uint32_t dtype;  // 0 = f32, 1 = bf16
+  uint32_t ndim;
+  uint32_t dims[4];
+  uint64_t offset;  // from file start
+  uint64_t nbytes;
+};
+#pragma pack(pop)
+
+struct Pack {
+  std::vector<uint8_t> data;
+  PackHeader hdr;
+  std::map<std::string, PackEntry> entries;
+  const PackEntry* find(const std::string& name) const {
+    auto it = entries.find(name);
+    return it == entries.end() ? nullptr : &it->second;
+  }
+};
+
+static int load_pack(const std::string& path_in, Pack& pk) {
+  std::string path = path_in;
+  const std::string ext = ".b200";
+  if (path.size() < ext.size() || path.compare(path.size() - ext.size(), ext.size(), ext) != 0)
+    path += ext;
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) {
+    set_error("cannot open weight pack '" + path + "' (run: python -m maru_b200.convert <file>.model)");
+    return 1;
+  }
+  fseek(f, 0, SEEK_END);
+  const long sz = ftell(f);
+  fseek(f, 0, SEEK_SET);
+  pk.data.resize(sz);
+  const size_t rd = fread(pk.data.data(), 1, sz, f);
+  fclose(f);
+  if ((long)rd != sz || sz < (long)sizeof(PackHeader)) {
+    set_error("short read on weight pack '" + path + "'");
+    return 1;
+  }
+  memcpy(&pk.hdr, pk.data.data(), sizeof(PackHeader));
+  if (memcmp(pk.hdr.magic, "MARUB200", 8) != 0 || pk.hdr.version != 1) {
+    set_error("'" + path + "' is not a MARUB200 v1 weight pack");
+    return 1;
+  }
+  const size_t table = sizeof(PackHeader) + (size_t)pk.hdr.n_tensors * sizeof(PackEntry);
+  if ((size_t)sz < table) {
+    set_error("corrupt weight pack table");
+    return 1;
+  }
+  for (uint32_t i = 0; i < pk.hdr.n_tensors; i++) {
+    PackEntry e;
+    memcpy(&e, pk.data.data() + sizeof(PackHeader) + (size_t)i * sizeof(PackEntry), sizeof(PackEntry));
+    e.name[47] = 0;
+    if (e.offset + e.nbytes > (uint64_t)sz) {
+      set_error(std::string("corrupt weight pack entry ") + e.name);
+      return 1;
+    }
+    pk.entries[e.name] = e;
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+static int choose_nt(int cin, int cout, int taps) {
+  const int cands[3] = {128, 64, 32};
+  for (int nt : cands) {
+    if (cout % nt != 0) continue;
+    // keep in sync with MARU_CONV_CASES (conv_gemm.cu)
+    const bool ok =
+        (taps == 9 && ((cin == 64 && (nt == 128 || nt == 64)) || (cin == 32 && nt == 32) ||
+                       (cin == 128 && nt == 64))) ||
+        (taps == 1 && ((cin == 256 && (nt == 128 || nt == 32)) ||
+                       (cin == 128 && (nt == 128 || nt == 64 || nt == 32)) ||
+                       (cin == 64 && (nt == 128 || nt == 64 || nt == 32)) ||
+                       (cin == 32 && (nt == 64 || nt == 32))));
+    if (!ok) continue;
+    if (taps == 9 && cin == 64 && nt == 128 && cout != 128) continue;
+    return nt;
+  }
+  return 0;
+}
+
+int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int cout, int taps,
+                        ConvLayer& L) {
+  const PackEntry* w = pk.find(name + ".w");
+  const PackEntry* b = pk.find(name + ".b");
+  if (!w || !b) {
+    set_error("weight pack lacks tensor " + name);
+    return 1;
+  }
+  if (w->dtype != 1 || w->ndim != 3 || (int)w->dims[0] != taps || (int)w->dims[1] != cout ||
+      (int)w->dims[2] != cin || b->dtype != 0 || (int)b->dims[0] != cout) {
+    set_error("weight pack tensor " + name + " has unexpected shape");
+    return 1;
+  }
+  L.cin = cin;
+  L.cout = cout;
+  L.taps = taps;
+  L.nt = choose_nt(cin, cout, taps);
+  if (L.nt == 0) {
+    char msg[160];
+    snprintf(msg, sizeof msg, "no conv_gemm instantiation for %s (cin=%d cout=%d taps=%d)",
+             name.c_str(), cin, cout, taps);
+    set_error(msg);
+    return 1;
+  }
+  // [tap][cout][cin] -> UMMA K-major SWIZZLE_NONE image [tap][cin/8][cout][8]
+  const uint16_t* src = reinterpret_cast<const uint16_t*>(pk.data.data() + w->offset);
+  std::vector<uint16_t> img((size_t)taps * cin * cout);
+  const int kch = cin / 8;
+  for (int t = 0; t < taps; t++)
+    for (int c8 = 0; c8 < kch; c8++)
+      for (int co = 0; co < cout; co++)
+        for (int e = 0; e < 8; e++)
+          img[(((size_t)t * kch + c8) * cout + co) * 8 + e] =
+              src[((size_t)t * cout + co) * cin + c8 * 8 + e];
+  CK(cudaMalloc(&L.w, img.size() * 2));
+  CK(cudaMemcpy(L.w, img.data(), img.size() * 2, cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&L.b, (size_t)cout * 4));
+  CK(cudaMemcpy(L.b, pk.data.data() + b->offset, (size_t)cout * 4, cudaMemcpyHostToDevice));
+  allocs.push_back(L.w);
+  allocs.push_back(L.b);
+  return 0;
+}
+
+int Engine::upload_f32(const Pack& pk, const std::string& name, size_t count, float** dst) {
+  const PackEntry* e = pk.find(name);
+  if (!e || e->dtype != 0 || e->nbytes != count * 4) {
+    set_error("weight pack lacks f32 tensor " + name);
+    return 1;
+  }
+  CK(cudaMalloc(dst, count * 4));
+  CK(cudaMemcpy(*dst, pk.data.data() + e->offset, count * 4, cudaMemcpyHostToDevice));
+  allocs.push_back(*dst);
+  return 0;
+}
+
+int Engine::alloc_planes(int channels, __nv_bfloat16** p) {
+  const size_t bytes = (size_t)(channels / 8) * rows_alloc * 16;
+  CK(cudaMalloc(p, bytes));
+  CK(cudaMemset(*p, 0, bytes));
+  allocs.push_back(*p);
+  return 0;
+}
+
+int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned flags_) {
+  if (gpu < 0) {
+    set_error("maru_b200 has no CPU path: gpu_id must be >= 0");
+    return 1;
+  }
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (gpu >= ndev) {
+    set_error("Specified GPU device is not available.");  // same text as Model.cpp:30
+    return 1;
+  }
+  gpu_id = gpu;
+  max_batch = max_batch_ > 0 ? max_batch_ : 256;
+  flags = flags_;
+  CK(cudaSetDevice(gpu_id));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, gpu_id));
+  if (prop.major != 10) {
+    set_error(std::string("maru_b200 kernels are sm_100a only; device is ") + prop.name);
+    return 1;
+  }
+  sm_count = prop.multiProcessorCount;
+  CK(configure_conv_gemm());
+  CK(configure_attention());
+  CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+  CK(cudaEventCreate(&ev0));
+  CK(cudaEventCreate(&ev1));
+
+  Pack pk;
+  if (load_pack(weights_path, pk)) return 1;
+  blocks = pk.hdr.arch[0];
+  C = pk.hdr.arch[1];
+  attn_every = pk.hdr.arch[2];
+  head_dim = pk.hdr.arch[3];
+  Ch = pk.hdr.arch[4];
+  Cv = pk.hdr.arch[5];
+  if (C % 64 != 0 || C > 256 || (head_dim != 32 && head_dim != 64) || Ch != 32 || Cv > 128) {
+    set_error("unsupported architecture in weight pack");
+    return 1;
+  }
+  n_attn = attn_every > 0 ? blocks / attn_every : 0;
+  rows_alloc = rows_alloc_for(max_batch);
+
+  if (upload_conv(pk, "stem", STEM_CIN, C, 9, stem)) return 1;
+  blk.resize(blocks);
+  for (int i = 0; i < blocks; i++) {
+    const std::string b = "blk" + std::to_string(i);
+    if (upload_conv(pk, b + ".reduce", C, C / 2, 1, blk[i].reduce)) return 1;
+    for (int j = 0; j < 2; j++) {
+      const std::string in = b + ".in" + std::to_string(j);
+      if (upload_conv(pk, in + ".c1", C / 2, C / 2, 9, blk[i].c[2 * j])) return 1;
+      if (upload_conv(pk, in + ".c2", C / 2, C / 2, 9, blk[i].c[2 * j + 1])) return 1;
+    }
+    if (upload_conv(pk, b + ".expand", C / 2, C, 1, blk[i].expand)) return 1;
+  }
+  att.resize(n_attn);
+  for (int i = 0; i < n_attn; i++) {
+    const std::string a = "att" + std::to_string(i);
+    if (upload_conv(pk, a + ".qkv", C, 3 * C, 1, att[i].qkv)) return 1;
+    if (upload_conv(pk, a + ".proj", C, C, 1, att[i].proj)) return 1;
+  }
+  if (upload_conv(pk, "head.g", C, Ch, 1, headg)) return 1;
+  if (upload_f32(pk, "head.planes.w", 6 * Ch, &w_planes)) return 1;
+  if (upload_f32(pk, "head.planes.b", 6, &b_planes)) return 1;
+  if (upload_f32(pk, "head.fc1.w", (size_t)Cv * 2 * Ch, &w_fc1)) return 1;
+  if (upload_f32(pk, "head.fc1.b", Cv, &b_fc1)) return 1;
+  if (upload_f32(pk, "head.fc2.w", 3 * Cv, &w_fc2)) return 1;
+  if (upload_f32(pk, "head.fc2.b", 3, &b_fc2)) return 1;
+
+  if (alloc_planes(STEM_CIN, &x0)) return 1;
+  if (alloc_planes(C, &h)) return 1;
+  if (alloc_planes(C / 2, &r)) return 1;
+  if (alloc_planes(C / 2, &s)) return 1;
+  if (n_attn > 0) {
+    if (alloc_planes(3 * C, &qkv)) return 1;
+    if (alloc_planes(C, &o)) return 1;
+  }
+  if (alloc_planes(Ch, &g)) return 1;
+  CK(cudaMalloc(&mask, (size_t)rows_alloc));
+  CK(cudaMemset(mask, 0, (size_t)rows_alloc));
+  allocs.push_back(mask);
+  CK(cudaMalloc(&d_n, 64));
+  allocs.push_back(d_n);
+  CK(cudaMalloc(&d_logits, (size_t)max_batch * 2 * CELLS * 4));
+  allocs.push_back(d_logits);
+  CK(cudaMallocHost(&h_n, 64));
+  for (int i = 0; i < 3; i++) {
+    Slot& sl = slot[i];
+    CK(cudaMalloc(&sl.d_rows, (size_t)max_batch * IN_ROW * 4));
+    CK(cudaMalloc(&sl.d_states, (size_t)max_batch * sizeof(maru_state)));
+    CK(cudaMalloc(&sl.d_out, (size_t)max_batch * OUT_ROW * 4));
+    CK(cudaMallocHost(&sl.h_rows, (size_t)max_batch * IN_ROW * 4));
+    CK(cudaMallocHost(&sl.h_states, (size_t)max_batch * sizeof(maru_state)));
+    CK(cudaMallocHost(&sl.h_out, (size_t)max_batch * OUT_ROW * 4));
+    CK(cudaEventCreateWithFlags(&sl.done, cudaEventDisableTiming));
+    CK(cudaEventCreate(&sl.t0));
+    CK(cudaEventCreate(&sl.t1));
+  }
+
+  // FLOP accounting: algorithmic at T = 361 tokens, executed at 400 padded rows
+  {
+    const double T = CELLS, Tp = POS_ROWS;
+    const double c = C;
+    flops_alg = 2 * T * IN_PLANES * c * 9 + 2.0 * IN_INFOS * c;
+    flops_alg += blocks * (2 * (2 * T * c * (c / 2)) + 4 * (2 * T * (c / 2) * (c / 2) * 9));
+    flops_alg += n_attn * (2 * T * c * 3 * c + 4 * T * T * c + 2 * T * c * c);
+    flops_alg += 2 * T * c * Ch + 2 * T * Ch * 6 + 2.0 * (2 * Ch) * Cv + 2.0 * Cv * 3;
+    flops_exec = 2 * Tp * STEM_CIN * c * 9;
+    flops_exec += blocks * (2 * (2 * Tp * c * (c / 2)) + 4 * (2 * Tp * (c / 2) * (c / 2) * 9));
+    flops_exec += n_attn * (2 * Tp * c * 3 * c + 4 * Tp * Tp * c + 2 * Tp * c * c);
+    flops_exec += 2 * Tp * c * Ch + 2 * T * Ch * 6 + 2.0 * (2 * Ch) * Cv + 2.0 * Cv * 3;
+  }
+  launches_per_forward = 1 + 1 + blocks * 6 + n_attn * 3 + 2;
+  CK(cudaDeviceSynchronize());
+  return 0;
+}
+
+Engine::~Engine() {
+  if (gpu_id >= 0) cudaSetDevice(gpu_id);
+  if (stream) cudaStreamSynchronize(stream);
+  for (auto& kv : graphs)
+    if (kv.second) cudaGraphExecDestroy(kv.second);
+  for (void* p : allocs) cudaFree(p);
+  for (int i = 0; i < 3; i++) {
+    Slot& sl = slot[i];
+    if (sl.d_rows) cudaFree(sl.d_rows);
+    if (sl.d_states) cudaFree(sl.d_states);
+    if (sl.d_out) cudaFree(sl.d_out);
+    if (sl.h_rows) cudaFreeHost(sl.h_rows);
+    if (sl.h_states) cudaFreeHost(sl.h_states);
+    if (sl.h_out) cudaFreeHost(sl.h_out);
+    if (sl.done) cudaEventDestroy(sl.done);
+    if (sl.t0) cudaEventDestroy(sl.t0);
+    if (sl.t1) cudaEventDestroy(sl.t1);
+  }
+  if (h_n) cudaFreeHost(h_n);
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
+  if (stream) cudaStreamDestroy(stream);
+}
+
+// ------------------------------------------------------------------------------------------
+// the launch sequence of one forward (trunk input planes + mask already written)
+// ------------------------------------------------------------------------------------------
+int Engine::conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res,
+                 __nv_bfloat16* out, int relu, int n, const int* n_dev, cudaStream_t st) {
+  ConvParams p;
+  p.in = in;
+  p.in_chunk0 = 0;
+  p.w = L.w;
+  p.bias = L.b;
+  p.res = res;
+  p.res_chunk0 = 0;
+  p.out = out;
+  p.out_chunk0 = 0;
+  p.mask = mask;
+  p.rows_alloc = rows_alloc;
+  p.m_rows = total_rows(n);
+  p.cout_total = L.cout;
+  p.relu = relu;
+  p.n_dev = n_dev;
+  p.dbg = dbg_desc;
+  if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
+  launches_done++;
+  CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
+  return 0;
+}
+
+void Engine::clear_graphs() {
+  for (auto& kv : graphs)
+    if (kv.second) cudaGraphExecDestroy(kv.second);
+  graphs.clear();
+}
+
+int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st) {
+  launches_done = 0;
+  if (conv(stem, x0, nullptr, h, 1, n, n_dev, st)) return 1;
+  int ai = 0;
+  for (int i = 0; i < blocks; i++) {
+    Block& B = blk[i];
+    if (conv(B.reduce, h, nullptr, r, 1, n, n_dev, st)) return 1;
+    for (int j = 0; j < 2; j++) {
+      if (conv(B.c[2 * j], r, nullptr, s, 1, n, n_dev, st)) return 1;
+      if (conv(B.c[2 * j + 1], s, r, r, 1, n, n_dev, st)) return 1;  // r = relu(r + conv(s)), in place
+    }
+    if (conv(B.expand, r, h, h, 1, n, n_dev, st)) return 1;          // h = relu(h + conv(r)), in place
+    if (attn_every > 0 && (i + 1) % attn_every == 0 && ai < n_attn) {
+      Attn& A = att[ai++];
+      if (conv(A.qkv, h, nullptr, qkv, 0, n, n_dev, st)) return 1;
+      AttnParams ap;
+      ap.qkv = qkv;
+      ap.out = o;
+      ap.mask = mask;
+      ap.rows_alloc = rows_alloc;
+      ap.n = n;
+      ap.channels = C;
+      ap.head_dim = head_dim;
+      ap.n_dev = n_dev;
+      if (!(dbg_stop_after >= 0 && launches_done >= dbg_stop_after)) {
+        launches_done++;
+        CK(launch_attention(ap, st));
+      }
+      if (conv(A.proj, o, h, h, 0, n, n_dev, st)) return 1;           // h = h + proj(o), in place
+    }
+  }
+  if (conv(headg, h, nullptr, g, 1, n, n_dev, st)) return 1;
+  HeadParams hp;
+  hp.g = g;
+  hp.mask = mask;
+  hp.w_planes = w_planes;
+  hp.b_planes = b_planes;
+  hp.w_fc1 = w_fc1;
+  hp.b_fc1 = b_fc1;
+  hp.w_fc2 = w_fc2;
+  hp.b_fc2 = b_fc2;
+  hp.out = d_out;
+  hp.logits = d_logits;
+  hp.rows_alloc = rows_alloc;
+  hp.n = n;
+  hp.ch = Ch;
+  hp.cv = Cv;
+  hp.n_dev = n_dev;
+  if (dbg_stop_after >= 0) return 0;
+  CK(launch_heads(hp, st));
+  return 0;
+}
+
+int Engine::launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev,
+                       cudaStream_t st) {
+  if (kind == KIND_STATES) {
+    CK(launch_encode_trunk(static_cast<const maru_state*>(d_in), x0, mask, rows_alloc, n, n_dev, st));
+  } else {
+    CK(launch_ingest_rows(static_cast<const float*>(d_in), x0, mask, rows_alloc, n, n_dev, st));
+  }
+  return launch_trunk(n, n_dev, d_out, st);
+}
+
+static int bucket_for(int n, int max_batch) {
+  int b = 1;
+  while (b < n) b <<= 1;
+  return b > max_batch ? max_batch : b;
+}
+
+// Enqueue one forward of n <= max_batch positions on `stream` (no host sync).
+int Engine::forward_device(int kind, const void* d_in, float* d_out, int n) {
+  if (n <= 0) return 0;
+  if (n > max_batch) {
+    set_error("batch larger than max_batch");
+    return 1;
+  }
+  if (flags & MARU_FLAG_NO_GRAPH) {
+    if (launch_all(kind, d_in, d_out, n, nullptr, stream)) return 1;
+  } else {
+    // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
+    const int bucket = bucket_for(n, max_batch);
+    GraphKey key{kind, bucket, d_in, d_out};
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      cudaGraph_t gr = nullptr;
+      cudaGraphExec_t ex = nullptr;
+      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = launch_all(kind, d_in, d_out, bucket, d_n, stream);
+      cudaError_t ce = cudaStreamEndCapture(stream, &gr);
+      if (rc) return 1;
+      CK(ce);
+      CK(cudaGraphInstantiate(&ex, gr, 0));
+      cudaGraphDestroy(gr);
+      it = graphs.emplace(key, ex).first;
+    }
+    // h_n is a ring of 16 pinned ints so that back-to-back async forwards do not race on it
+    int* hn = h_n + (n_seq++ & 15);
+    *hn = n;
+    CK(cudaMemcpyAsync(d_n, hn, sizeof(int), cudaMemcpyHostToDevice, stream));
+    CK(cudaGraphLaunch(it->second, stream));
+  }
+  n_forward++;
+  n_positions += n;
+  return 0;
+}
+
+// Blocking forward on host buffers: H2D, kernels, D2H (Model::forward, Model.cpp:88-100).
+// `in` / `out` may be pageable (the reference passes stack arrays, Evaluator.cpp:48-49).
+int Engine::forward_host(int kind, const void* in, float* out, int n) {
+  std::lock_guard<std::mutex> lock(mu);
+  CK(cudaSetDevice(gpu_id));
+  const size_t in_row = kind == KIND_STATES ? sizeof(maru_state) : (size_t)IN_ROW * 4;
+  for (int off = 0; off < n; off += max_batch) {
+    const int m = (n - off < max_batch) ? n - off : max_batch;
+    Slot& sl = slot[2];
+    void* d_in = kind == KIND_STATES ? (void*)sl.d_states : (void*)sl.d_rows;
+    CK(cudaMemcpyAsync(d_in, static_cast<const uint8_t*>(in) + (size_t)off * in_row, (size_t)m * in_row,
+                       cudaMemcpyHostToDevice, stream));
+    CK(cudaEventRecord(sl.t0, stream));
+    if (forward_device(kind, d_in, sl.d_out, m)) return 1;
+    CK(cudaEventRecord(sl.t1, stream));
+    CK(cudaMemcpyAsync(out + (size_t)off * OUT_ROW, sl.d_out, (size_t)m * OUT_ROW * 4,
+                       cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sl.t0, sl.t1);
+    device_ms_last = ms;
+  }
+  return 0;
+}
+
+int Engine::enqueue_slot(int kind, int slot_idx, int n) {
+  std::lock_guard<std::mutex> lock(mu);
+  CK(cudaSetDevice(gpu_id));
+  Slot& sl = slot[slot_idx];
+  const size_t in_row = kind == KIND_STATES ? sizeof(maru_state) : (size_t)IN_ROW * 4;
+  void* d_in = kind == KIND_STATES ? (void*)sl.d_states : (void*)sl.d_rows;
+  const void* h_in = kind == KIND_STATES ? (const void*)sl.h_states : (const void*)sl.h_rows;
+  CK(cudaMemcpyAsync(d_in, h_in, (size_t)n * in_row, cudaMemcpyHostToDevice, stream));
+  CK(cudaEventRecord(sl.t0, stream));
+  if (forward_device(kind, d_in, sl.d_out, n)) return 1;
+  CK(cudaEventRecord(sl.t1, stream));
+  CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)n * OUT_ROW * 4, cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(sl.done, stream));
+  return 0;
+}
+
+int Engine::wait_slot(int slot_idx, float* device_ms) {
+  Slot& sl = slot[slot_idx];
+  CK(cudaEventSynchronize(sl.done));
+  if (device_ms) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, sl.t0, sl.t1);
+    *device_ms = ms;
+  }
+  return 0;
+}
+
+// K1 alone on host buffers: records -> reference rows (bit-exact Board::getInputs)
+int Engine::encode_rows_host(const maru_state* st, float* out_rows, int n) {
+  std::lock_guard<std::mutex> lock(mu);
+  CK(cudaSetDevice(gpu_id));
+  for (int off = 0; off < n; off += max_batch) {
+    const int m = (n - off < max_batch) ? n - off : max_batch;
+    Slot& sl = slot[2];
+    CK(cudaMemcpyAsync(sl.d_states, st + off, (size_t)m * sizeof(maru_state), cudaMemcpyHostToDevice,
+                       stream));
+    CK(launch_encode_rows(sl.d_states, sl.d_rows, m, nullptr, stream));
+    CK(cudaMemcpyAsync(out_rows + (size_t)off * IN_ROW, sl.d_rows, (size_t)m * IN_ROW * 4,
+                       cudaMemcpyDeviceToHost, stream));
+    CK(cudaStreamSynchronize(stream));
+  }
+  return 0;
+}
+
+}  // namespace maru

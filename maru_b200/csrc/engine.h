@@ -1,0 +1,110 @@
+// engine.h — internal C++ face of the evaluator (one GPU, one stream, one weight replica).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <vector>
+
+#include "kernels.h"
+
+namespace maru {
+
+extern thread_local std::string g_last_error;
+void set_error(const std::string& s);
+
+struct Pack;
+
+struct ConvLayer {
+  int cin = 0, cout = 0, taps = 0, nt = 0;
+  __nv_bfloat16* w = nullptr;
+  float* b = nullptr;
+};
+struct Block {
+  ConvLayer reduce, c[4], expand;
+};
+struct Attn {
+  ConvLayer qkv, proj;
+};
+
+enum { KIND_PLANES = 0, KIND_STATES = 1 };
+
+// device + pinned staging for one in-flight batch (the queue double-buffers over two of these)
+struct Slot {
+  float* d_rows = nullptr;
+  maru_state* d_states = nullptr;
+  float* d_out = nullptr;
+  float* h_rows = nullptr;
+  maru_state* h_states = nullptr;
+  float* h_out = nullptr;
+  cudaEvent_t done = nullptr;              // D2H of the batch finished
+  cudaEvent_t t0 = nullptr, t1 = nullptr;  // kernel span of the batch (timing events)
+};
+
+struct GraphKey {
+  int kind, bucket;
+  const void* in;
+  const void* out;
+  bool operator<(const GraphKey& o) const {
+    return std::tie(kind, bucket, in, out) < std::tie(o.kind, o.bucket, o.in, o.out);
+  }
+};
+
+struct Engine {
+  int gpu_id = -1, max_batch = 0, sm_count = 0, rows_alloc = 0;
+  unsigned flags = 0;
+  int blocks = 0, C = 0, attn_every = 0, head_dim = 0, Ch = 0, Cv = 0, n_attn = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::mutex mu;  // serialises the blocking entry points (a Model is single-threaded, Executor.cpp:172)
+
+  ConvLayer stem, headg;
+  std::vector<Block> blk;
+  std::vector<Attn> att;
+  float *w_planes = nullptr, *b_planes = nullptr, *w_fc1 = nullptr, *b_fc1 = nullptr,
+        *w_fc2 = nullptr, *b_fc2 = nullptr;
+
+  __nv_bfloat16 *x0 = nullptr, *h = nullptr, *r = nullptr, *s = nullptr, *qkv = nullptr,
+                *o = nullptr, *g = nullptr;
+  uint8_t* mask = nullptr;
+  int* d_n = nullptr;
+  int* h_n = nullptr;
+  unsigned n_seq = 0;
+  float* d_logits = nullptr;
+  Slot slot[3];  // 0,1: leaf-queue double buffer; 2: direct blocking calls
+  std::vector<void*> allocs;
+  std::map<GraphKey, cudaGraphExec_t> graphs;
+
+  int dbg_stop_after = -1;  // debug: stop the launch sequence after this many trunk launches
+  int dbg_desc = 0;         // debug: UMMA descriptor experiment bits
+  int launches_done = 0;
+  void clear_graphs();
+
+  double flops_alg = 0, flops_exec = 0;
+  int launches_per_forward = 0;
+  uint64_t n_forward = 0, n_positions = 0;
+  double device_ms_last = 0;
+
+  int init(const char* weights_path, int gpu, int max_batch, unsigned flags);
+  ~Engine();
+
+  int upload_conv(const Pack& pk, const std::string& name, int cin, int cout, int taps, ConvLayer& L);
+  int upload_f32(const Pack& pk, const std::string& name, size_t count, float** dst);
+  int alloc_planes(int channels, __nv_bfloat16** p);
+
+  int conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
+           int relu, int n, const int* n_dev, cudaStream_t st);
+  int launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st);
+  int launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev, cudaStream_t st);
+  int forward_device(int kind, const void* d_in, float* d_out, int n);  // async on `stream`
+  int forward_host(int kind, const void* in, float* out, int n);        // blocking, host buffers
+  // leaf-queue pipeline: inputs already gathered in slot.h_*; enqueue H2D + forward + D2H (async)
+  int enqueue_slot(int kind, int slot_idx, int n);
+  int wait_slot(int slot_idx, float* device_ms);
+  int encode_rows_host(const maru_state* s, float* out_rows, int n);
+};
+
+}  // namespace maru

@@ -1,0 +1,95 @@
+// kernels.h — launcher interface of the sm_100a kernels (internal to libmaru_b200.so).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "maru_b200.h"
+
+namespace maru {
+
+// Chunk-planar activation tensors:  [C/8][rows_alloc][8] bf16.  Row r of the padded-flat geometry
+// lives at plane row GUARD_ROWS + r; the GUARD_ROWS rows in front of every plane stay zero so that
+// the 3x3 slab of the first tile can be fetched without bounds logic.
+constexpr int GUARD_ROWS = 32;
+inline int rows_alloc_for(int max_batch) {
+  const int m = total_rows(max_batch);
+  return GUARD_ROWS + ((m + TILE_M - 1) / TILE_M) * TILE_M + 32;
+}
+
+struct ConvParams {
+  const __nv_bfloat16* in;   // input planes
+  int in_chunk0;             // first input plane (channel/8)
+  const __nv_bfloat16* w;    // [taps][cin/8][cout_total][8]  (UMMA K-major SWIZZLE_NONE image)
+  const float* bias;         // [cout_total]
+  const __nv_bfloat16* res;  // optional residual planes (may alias out)
+  int res_chunk0;
+  __nv_bfloat16* out;
+  int out_chunk0;
+  const uint8_t* mask;       // [m_rows] 1 = on-board cell
+  int rows_alloc;            // plane stride in rows (same for in/res/out)
+  int m_rows;                // total_rows(n)
+  int cout_total;
+  int relu;
+  const int* n_dev;          // optional: number of positions read on the device (graph replay with
+                             // a smaller batch than the one captured); overrides m_rows
+  int dbg;                   // bring-up: bit0 swap LBO/SBO of A, bit1 swap LBO/SBO of B
+};
+
+cudaError_t configure_conv_gemm();
+cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,
+                             cudaStream_t stream);
+
+// ---- K1: feature encoding (encode.cu) ------------------------------------------------------
+// compact records -> reference fp32 rows [n][11920]   (bit-exact Board::getInputs)
+// All launchers take `n` (grid sizing) and an optional device pointer `n_dev` holding the live
+// number of positions (<= n), so that one captured CUDA graph serves every batch size of a bucket.
+cudaError_t launch_encode_rows(const maru_state* states, float* rows, int n, const int* n_dev,
+                               cudaStream_t stream);
+// compact records -> trunk input planes (STEM_CIN channels) + board mask
+cudaError_t launch_encode_trunk(const maru_state* states, __nv_bfloat16* x0, uint8_t* mask,
+                                int rows_alloc, int n, const int* n_dev, cudaStream_t stream);
+// reference fp32 rows -> trunk input planes + board mask
+cudaError_t launch_ingest_rows(const float* rows, __nv_bfloat16* x0, uint8_t* mask, int rows_alloc,
+                               int n, const int* n_dev, cudaStream_t stream);
+// trunk input planes -> fp32 [n][channels][361] (debug / parity)
+cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, float* out,
+                                  int n, cudaStream_t stream);
+
+// ---- K4: attention core (attention.cu) -------------------------------------------------------
+struct AttnParams {
+  const __nv_bfloat16* qkv;  // planes: q [0,C), k [C,2C), v [2C,3C); q pre-scaled by log2(e)/sqrt(d)
+  __nv_bfloat16* out;        // planes [0,C)
+  const uint8_t* mask;
+  int rows_alloc;
+  int n;                     // positions
+  int channels;              // C
+  int head_dim;              // 32 or 64
+  const int* n_dev;
+};
+cudaError_t configure_attention();
+cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
+
+// ---- K5: heads (heads.cu) --------------------------------------------------------------------
+struct HeadParams {
+  const __nv_bfloat16* g;    // planes [0,Ch): relu(bn(conv1x1(h))) * mask
+  const uint8_t* mask;
+  const float* w_planes;     // [6][Ch]
+  const float* b_planes;     // [6]
+  const float* w_fc1;        // [Cv][2*Ch]
+  const float* b_fc1;        // [Cv]
+  const float* w_fc2;        // [3][Cv]
+  const float* b_fc2;        // [3]
+  float* out;                // [n][2169]
+  float* logits;             // optional [n][2][361] pre-softmax policy logits
+  int rows_alloc;
+  int n;
+  int ch;                    // head channels (32)
+  int cv;                    // value channels (<= 128)
+  const int* n_dev;
+};
+cudaError_t launch_heads(const HeadParams& p, cudaStream_t stream);
+
+}  // namespace maru

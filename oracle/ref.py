@@ -294,3 +294,30 @@ def make_positions(n: int, size: int | Tuple[int, int] = 19, seed: int = 0, komi
         states[i] = b.get_state(color, k, rule, superko, with_mask)
         meta.append(dict(w=w, h=h, moves=moves, color=color, komi=k, rule=rule, superko=superko))
     return rows, states, meta
+
+
+def ko_positions(size: int | Tuple[int, int] = 9, komi: float = 7.5):
+    """Forced cases the random playouts rarely hit: a ko just created (plane 31 + scalar 4, incl. the
+    reference's un-centred ko plane on small boards, Board.cpp:587-593), for both colours and a few
+    translations, each followed by a pass variant (ko cleared, pass absent from history)."""
+    w, h = (size, size) if isinstance(size, int) else size
+    rows, states, meta = [], [], []
+    for (dx, dy) in [(0, 0), (w - 4, 0), (0, h - 3), (w - 4, h - 3), ((w - 4) // 2, (h - 3) // 2)]:
+        for first in (BLACK, WHITE):
+            b = RefBoard(w, h)
+            a, o = first, -first
+            for (x, y) in [(1, 0), (0, 1), (1, 2)]:
+                assert b.play(dx + x, dy + y, a) >= 0
+            for (x, y) in [(2, 0), (3, 1), (2, 2), (1, 1)]:
+                assert b.play(dx + x, dy + y, o) >= 0
+            assert b.play(dx + 2, dy + 1, a) == 1          # captures (1,1): ko for `o`
+            assert b.get_ko(o) == (dx + 1, dy + 1)
+            for color in (o, a):
+                rows.append(b.get_inputs(color, komi, RULE_CH, False))
+                states.append(b.get_state(color, komi, RULE_CH, False, True))
+                meta.append(dict(w=w, h=h, ko=(dx + 1, dy + 1), color=color, case='ko'))
+            b.play(-1, -1, o)                               # pass clears the ko
+            rows.append(b.get_inputs(a, komi, RULE_JP, True))
+            states.append(b.get_state(a, komi, RULE_JP, True, True))
+            meta.append(dict(w=w, h=h, color=a, case='ko-then-pass'))
+    return np.stack(rows), np.stack(states), meta

@@ -1,0 +1,65 @@
+"""GPU: every activation buffer of the trunk, stage by stage, against the torch port of the packed
+network (oracle/net_port.py, bf16 storage emulated). Localises a wrong kernel; on a stem mismatch
+it also probes the UMMA descriptor variants so one GPU run tells which encoding is right."""
+import numpy as np
+import pytest
+
+from conftest import load_positions
+
+pytestmark = pytest.mark.gpu
+
+BUF_CH = {1: 'C', 2: 'C/2', 3: 'C/2', 4: '3C', 5: 'C', 6: 'Ch'}
+
+
+def run_stages(ev, arch, T, rows, upto=None):
+    from oracle import net_port
+    C, Ch = arch[1], arch[4]
+    chans = {1: C, 2: C // 2, 3: C // 2, 4: 3 * C, 5: C, 6: Ch}
+    stages, out, logits = net_port.staged_forward(arch, T, rows, emulate_bf16=True)
+    report = []
+    n = len(rows)
+    for k, (name, buf, want) in enumerate(stages):
+        if upto is not None and k >= upto:
+            break
+        ev.debug_set(0, k + 1)
+        ev.forward(rows)
+        got = ev.debug_planes(buf, n, chans[buf])
+        want = want.reshape(n, chans[buf], 361).numpy()
+        err = np.abs(got - want).max()
+        scale = np.abs(want).max() + 1e-6
+        report.append((name, float(err), float(scale)))
+    ev.debug_set(0, -1)
+    return report, out, logits
+
+
+@pytest.mark.parametrize('name', ['b2c64', 'b4c128'])
+def test_every_stage_matches_port(built_lib, model_dir, name):
+    import maru_b200
+    from oracle import net_port
+    path = model_dir(name)
+    arch, T = net_port.read_pack(str(path) + '.b200')
+    rows = np.concatenate([load_positions('19')[0][:5], load_positions('9')[0][:3],
+                           load_positions('9x13')[0][24:27]])
+    ev = maru_b200.Evaluator(path, gpu=0, max_batch=16, flags=1)
+    try:
+        report, out, logits = run_stages(ev, arch, T, rows, upto=1)
+        if report[0][1] > 0.05 * report[0][2]:
+            # bring-up aid: which LBO/SBO reading of the SWIZZLE_NONE descriptor does the HW use?
+            probe = {}
+            for bits in (1, 2, 3):
+                ev.debug_set(1, bits)
+                probe[bits] = run_stages(ev, arch, T, rows, upto=1)[0][0][1]
+            ev.debug_set(1, 0)
+            pytest.fail(f'stem mismatch err={report[0]} ; descriptor probe (bit0 swap A, bit1 swap B): {probe}')
+        report, out, logits = run_stages(ev, arch, T, rows)
+        lines = [f'{n:18s} err={e:.4f} scale={s:.3f}' for n, e, s in report]
+        print('\n'.join(lines))
+        bad = [(n, e, s) for n, e, s in report if e > 0.02 * s + 0.02]
+        assert not bad, 'stage mismatch: ' + str(bad) + '\n' + '\n'.join(lines)
+        got = ev.forward(rows)
+        glog = ev.debug_policy_logits(len(rows))
+        mask = rows[:, 32 * 361:33 * 361] > 0
+        assert np.abs(glog - logits)[np.repeat(mask[:, None], 2, 1)].max() < 2e-2
+        assert np.abs(got - out).max() < 1e-2
+    finally:
+        ev.close()

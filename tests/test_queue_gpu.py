@@ -1,0 +1,45 @@
+"""GPU: the leaf-batch queue (Processor/Executor mirror): many threads submitting n=1 jobs like
+Evaluator.cpp:52 does, mixed job sizes and kinds, results identical to a direct forward."""
+import threading
+
+import numpy as np
+import pytest
+
+from conftest import load_positions
+
+pytestmark = pytest.mark.gpu
+
+
+def test_queue_matches_direct_and_batches(built_lib, model_dir):
+    import maru_b200
+    path = model_dir('b2c64')
+    rows, states = load_positions('19')
+    rows = np.concatenate([rows, load_positions('9')[0]])
+    states = np.concatenate([states, load_positions('9')[1]])
+    direct = maru_b200.Evaluator(path, gpu=0, max_batch=64)
+    want = direct.forward(rows)
+    direct.close()
+    proc = maru_b200.Processor(path, gpus=[0], batch_size=32, threads_par_gpu=2)
+    try:
+        # Processor.execute with N rows (processor.py:34-39)
+        assert np.array_equal(proc.execute(rows), want)
+        assert np.array_equal(proc.execute_states(states), want)
+        # 16 "search threads" each submitting single positions (Evaluator.cpp:52)
+        got = np.zeros_like(want)
+        def worker(tid):
+            for i in range(tid, len(rows), 16):
+                if i % 2:
+                    got[i] = proc.execute(rows[i:i + 1])[0]
+                else:
+                    got[i] = proc.execute_states(states[i:i + 1])[0]
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(16)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert np.array_equal(got, want)
+        st = proc.queue.stats()
+        assert st.positions >= 3 * len(rows) and st.batches >= 3
+        # a job larger than the cap is never split across batches but still runs (Executor.cpp:116)
+        big = proc.execute(np.concatenate([rows, rows]))
+        assert np.array_equal(big[:len(rows)], want)
+    finally:
+        proc.close()
