@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py — NN evals/sec of the leaf-evaluation hot path (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run)
+  python bench.py --impl reference ...                     (the reference's own CPU path, oracle/_ref)
+
+One "step" = one pass of the hot path over one batch: `--batch` (256) synthetic 19x19 positions
+through K1 encode -> trunk -> heads of the b4c128-shape random-init network (BASELINE.json
+configs[1]).  Rank r runs its own evaluator on cuda:r over its own positions (positions are
+independent: weak scaling, no data-path collective; NCCL only reduces the timing).
+  value        : evals/s with the compact records already resident in HBM (CUDA-event timed on the
+                 evaluator's stream, L2 flushed between steps, max over ranks)
+  e2e          : the same metric through the blocking C-ABI call with HOST buffers
+                 (maru_eval_forward_states: pinned records H2D + kernels + outputs D2H per step)
+  roofline     : dominant kernel (3x3 implicit-GEMM conv) algorithmic FLOPs / CUDA-event duration,
+                 against the measured bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline : the reference runtime (deepgo::Processor on libtorch CPU) on a bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'nn_evals_per_sec'
+UNIT = 'evals/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--model', default='b4c128')
+    ap.add_argument('--batch', type=int, default=256)
+    ap.add_argument('--board', type=int, default=19)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def base_config(args, world: int) -> dict:
+    """Workload description shared verbatim by both arms."""
+    return dict(workload=f'{args.model} random-init (seed 0), {args.board}x{args.board} leaf evaluation, '
+                         f'batch {args.batch} per GPU (BASELINE.json configs[1])',
+                model=args.model, board=args.board, batch_per_gpu=args.batch,
+                parallelism=f'replica x{world}')
+
+
+def model_files(name: str):
+    """Random-init weights of the named architecture (seed 0): TorchScript .model + .b200 pack."""
+    from maru_b200 import convert, netspec
+    d = Path(os.environ.get('MARU_BENCH_DIR', '/tmp/maru_b200_bench'))
+    d.mkdir(parents=True, exist_ok=True)
+    path = d / f'{name}-seed0.model'
+    if not path.exists():
+        tmp = d / f'.{name}-{os.getpid()}.model'
+        netspec.export(netspec.build(**netspec.CONFIGS[name], seed=0), str(tmp))
+        os.replace(tmp, path)
+    pack = Path(str(path) + '.b200')
+    if not pack.exists():
+        tmp = d / f'.{name}-{os.getpid()}.b200'
+        convert.convert(str(path), str(tmp))
+        os.replace(tmp, pack)
+    return path, pack
+
+
+def load_peaks():
+    p = ROOT / 'MEASURED_PEAKS.json'
+    if p.exists():
+        d = json.loads(p.read_text())
+        return dict(bf16_burst=d.get('bf16_tflops', 1590.0), bf16_sustained=d.get('bf16_tflops_sustained', 1400.0),
+                    hbm=d.get('hbm_gbs', 6650.0), source='measured')
+    return dict(bf16_burst=1590.0, bf16_sustained=1400.0, hbm=6650.0, source='fallback')
+
+
+class ClockSampler:
+    QUERY = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu: int):
+        self.gpu, self.samples, self.stop = gpu, [], threading.Event()
+        self.th = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        while not self.stop.is_set():
+            try:
+                out = subprocess.run(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.QUERY}',
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(',')])
+            except Exception:
+                pass
+            self.stop.wait(0.1)
+
+    def __enter__(self):
+        self.th.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop.set()
+        self.th.join(timeout=6)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for nm, v in zip(names, s[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=mx or None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_evals_per_sec(model_path: Path, rows: np.ndarray, budget_s: float = 20.0):
+    """The reference's own path on the host cores: deepgo::Processor::execute -> Executor ->
+    Model::forward (libtorch CPU fp32), built unmodified into oracle/_ref."""
+    import torch
+    from oracle import ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    proc = ref.RefProcessor(str(model_path), gpus=[-1], batch_size=len(rows))
+    n = min(len(rows), 32)
+    t0 = time.perf_counter()
+    proc.execute(rows[:n])                                     # warm-up + cost estimate
+    per_row = (time.perf_counter() - t0) / n
+    n = int(max(16, min(len(rows), budget_s / 2 / max(per_row, 1e-6))))
+    reps = 2
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        proc.execute(rows[:n])
+    dt = time.perf_counter() - t0
+    proc.close()
+    return n * reps / dt, n, reps, torch.get_num_threads()
+
+
+def rows_from_states(states: np.ndarray) -> np.ndarray:
+    """CPU oracle (oracle/features.c) expansion of compact records to reference rows — used only to
+    feed the reference arm / cpu_baseline leg."""
+    import ctypes as C
+    so = ROOT / 'oracle' / '_build' / 'liboracle_features.so'
+    if not so.exists():
+        subprocess.check_call(['make', '-C', str(ROOT / 'oracle'), 'features'], stdout=subprocess.DEVNULL)
+    lib = C.CDLL(str(so))
+    out = np.zeros((len(states), 11920), np.float32)
+    lib.oracle_get_inputs_batch(states.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), len(states))
+    return out
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from maru_b200 import synth
+    model_path, _ = model_files(args.model)
+    states = synth.random_states(args.batch, args.board, seed=1234)
+    rows = rows_from_states(states)
+    import torch
+    from oracle import ref
+    torch.set_num_threads(os.cpu_count() or 1)
+    proc = ref.RefProcessor(str(model_path), gpus=[-1], batch_size=args.batch)
+    t0 = time.perf_counter()
+    proc.execute(rows[:16])
+    per_row = (time.perf_counter() - t0) / 16
+    total = args.steps + args.warmup
+    sample = int(max(8, min(args.batch, 150.0 / total / max(per_row, 1e-6))))
+    for _ in range(args.warmup):
+        proc.execute(rows[:sample])
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        proc.execute(rows[:sample])
+    dt = time.perf_counter() - t0
+    value = sample * args.steps / dt
+    line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True,
+                scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                config=base_config(args, args.gpus),
+                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind='reference',
+                                  sample=f'{sample} of the {args.batch} positions per step through '
+                                         'deepgo::Processor::execute (libtorch CPU fp32, oracle/_ref)'),
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def run_b200(args):
+    import torch
+    import maru_b200
+    from maru_b200 import synth
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local)
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+
+    if rank == 0:
+        model_path, pack = model_files(args.model)
+    if dist is not None:
+        dist.barrier()
+    model_path, pack = model_files(args.model)
+
+    B = args.batch
+    ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=B)
+    info = ev.info()
+    stream = torch.cuda.ExternalStream(ev.stream(), device=dev)
+    states = synth.random_states(B, args.board, seed=1234 + rank)
+    d_states = torch.from_numpy(states).to(dev)
+    d_out = torch.empty((B, maru_b200.OUTPUT_SIZE), dtype=torch.float32, device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # 256 MiB > 126 MB L2
+    h_states = torch.from_numpy(states).pin_memory()
+    h_out = torch.empty((B, maru_b200.OUTPUT_SIZE), dtype=torch.float32).pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---------------- value: device-resident, CUDA events on the evaluator's stream -------------
+    for _ in range(max(args.warmup, 3)):
+        ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), B)
+    ev.sync()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    sync_all()
+    with ClockSampler(local) as clocks:
+        t_wall0 = time.perf_counter()
+        for i in range(args.steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()                                         # evict L2 between timed steps
+                starts[i].record(stream)
+            ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), B)
+            with torch.cuda.stream(stream):
+                stops[i].record(stream)
+        sync_all()
+        t_wall = time.perf_counter() - t_wall0
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    dev_ms = float(sum(step_ms))
+    clock = clocks.summary()
+
+    # ---------------- e2e: blocking C-ABI call on host buffers -----------------------------------
+    lib = ev.lib
+    for _ in range(3):
+        lib.maru_eval_forward_states(ev.handle, h_states.data_ptr(), h_out.data_ptr(), B)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc = lib.maru_eval_forward_states(ev.handle, h_states.data_ptr(), h_out.data_ptr(), B)
+        assert rc == 0
+    sync_all()
+    e2e_s = time.perf_counter() - t0
+    # reference-shaped rows in (47 680 B/position), same call the substitute deepgo::Model makes
+    d_rows = torch.empty((B, maru_b200.INPUT_SIZE), dtype=torch.float32, device=dev)
+    ev.encode_planes_device(d_states.data_ptr(), d_rows.data_ptr(), B)
+    ev.sync()
+    h_rows = d_rows.cpu().pin_memory()
+    for _ in range(3):
+        lib.maru_eval_forward_planes(ev.handle, h_rows.data_ptr(), h_out.data_ptr(), B)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc = lib.maru_eval_forward_planes(ev.handle, h_rows.data_ptr(), h_out.data_ptr(), B)
+        assert rc == 0
+    sync_all()
+    e2e_planes_s = time.perf_counter() - t0
+
+    # ---------------- per-launch profile (roofline of the dominant kernel) -----------------------
+    prof = {}
+    for rep in range(max(3, min(args.steps, 10))):
+        with torch.cuda.stream(stream):
+            flush.zero_()
+        for l in ev.profile_states_device(d_states.data_ptr(), d_out.data_ptr(), B):
+            key = (l['kind'], l['cin'], l['cout'], l['taps'])
+            a = prof.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, name=l['name']))
+            if rep > 0:                                            # first rep = warm-up
+                a['ms'] += l['ms']; a['flops'] += l['flops']; a['bytes'] += l['bytes']; a['launches'] += 1
+
+    # ---------------- reduce over ranks ----------------------------------------------------------
+    t = torch.tensor([dev_ms, e2e_s, e2e_planes_s, t_wall], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s, e2e_planes_s, t_wall = [float(x) for x in t.tolist()]
+    total = world * B * args.steps
+    value = total / (dev_ms / 1e3)
+
+    if rank == 0:
+        peaks = load_peaks()
+        kinds = {0: 'encode', 1: 'conv3x3', 2: 'conv1x1', 3: 'attention', 4: 'heads'}
+        table = []
+        tot_ms = sum(a['ms'] for a in prof.values()) or 1.0
+        for key, a in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
+            if a['launches'] == 0:
+                continue
+            table.append(dict(kernel=f"{kinds[key[0]]} {key[1]}->{key[2]}", example=a['name'],
+                              launches_per_step=a['launches'] // max(1, (max(3, min(args.steps, 10)) - 1)),
+                              us_per_launch=a['ms'] / a['launches'] * 1e3, share=a['ms'] / tot_ms,
+                              tflops=a['flops'] / (a['ms'] / 1e3) / 1e12 if a['flops'] else None,
+                              gbs=a['bytes'] / (a['ms'] / 1e3) / 1e9))
+        dom_key = max((k for k in prof if k[0] == 1 and prof[k]['launches']), key=lambda k: prof[k]['ms'])
+        dom = prof[dom_key]
+        achieved = dom['flops'] / (dom['ms'] / 1e3) / 1e12
+        roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16_burst'], unit='TFLOP/s',
+                        frac=achieved / peaks['bf16_burst'], traffic=None,
+                        kernel=f'conv_gemm 3x3 {dom_key[1]}->{dom_key[2]} ({dom["launches"]} timed launches)',
+                        peak_source=peaks['source'] + ' (burst, kernel timed alone)',
+                        flops_per_launch=dom['flops'] / dom['launches'],
+                        us_per_launch=dom['ms'] / dom['launches'] * 1e3,
+                        whole_net_tflops=value * info.flops_per_eval / 1e12,
+                        whole_net_frac_of_sustained=value * info.flops_per_eval / 1e12 / peaks['bf16_sustained'])
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                rows = h_rows.numpy()
+                v, n, reps, cores = cpu_reference_evals_per_sec(model_path, rows)
+                cpu = dict(value=v, unit=UNIT, cores=cores, kind='reference',
+                           sample=f'{reps} x {n} of the step\'s {B} positions through '
+                                  'deepgo::Processor::execute (libtorch CPU fp32, oracle/_ref)')
+            except Exception as exc:  # the oracle always exists; report instead of hiding
+                cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind='reference',
+                           sample=f'failed: {exc}')
+        line = dict(
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+            ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
+            dtype='bf16', data='synthetic', impl='b200',
+            config=dict(base_config(args, world), l2='flushed between steps (256 MiB write)',
+                        launches_per_step=info.launches_per_forward, flops_per_eval=info.flops_per_eval,
+                        flops_per_eval_executed=info.flops_per_eval_executed),
+            e2e=dict(value=total / e2e_s, unit=UNIT, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
+                     d2h_bytes_per_step=B * maru_b200.OUTPUT_SIZE * 4,
+                     api='maru_eval_forward_states (blocking, pinned host buffers)',
+                     planes=dict(value=total / e2e_planes_s, h2d_bytes_per_step=B * maru_b200.INPUT_SIZE * 4,
+                                 api='maru_eval_forward_planes (reference Model::forward contract)')),
+            gpu_launches=info.launches_per_forward * args.steps,
+            clocks=clock, roofline=roofline, cpu_baseline=cpu, kernels=table,
+            wall_ms_per_step=t_wall / args.steps * 1e3)
+        print(json.dumps(line), flush=True)
+    ev.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == '__main__':
+    main()

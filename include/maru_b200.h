@@ -142,6 +142,21 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 #define MARU_DBG_DESC_BITS 1
 int  maru_eval_debug_set(maru_eval* e, int key, int value);
 
+/* ---- per-launch timing (roofline evidence) --------------------------------------------------- */
+/* Runs ONE forward of n positions (device-resident compact records) WITHOUT a CUDA graph, with a
+ * CUDA event pair around every kernel launch on the evaluator's stream, and reports each launch.
+ * flops / bytes are the ALGORITHMIC figures of that launch at T = 361 tokens per position
+ * (DESIGN.md "Kernels"); kind: 0 encode, 1 conv3x3, 2 conv1x1, 3 attention core, 4 heads. */
+typedef struct maru_launch_time {
+  char   name[32];
+  int32_t kind, cin, cout, taps;
+  float  ms;
+  double flops;
+  double bytes;
+} maru_launch_time;
+int  maru_eval_profile_states(maru_eval* e, const maru_state* d_states, float* d_out, int n,
+                              maru_launch_time* out, int max_launches, int* n_launches);
+
 /* ---- leaf-batch queue (replaces Processor/Executor/ExecutorJob, Processor.cpp, Executor.cpp) -- */
 /* Takes ownership of nothing: evaluators must outlive the queue. batch_size = drain cap
  * (Executor.cpp:116). One worker thread + pinned double buffers per evaluator. */

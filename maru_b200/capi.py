@@ -33,6 +33,12 @@ class EvalInfo(C.Structure):
                 ('n_positions', C.c_uint64), ('device_ms_last', C.c_double)]
 
 
+class LaunchTime(C.Structure):
+    _fields_ = [('name', C.c_char * 32), ('kind', C.c_int32), ('cin', C.c_int32),
+                ('cout', C.c_int32), ('taps', C.c_int32), ('ms', C.c_float),
+                ('flops', C.c_double), ('bytes', C.c_double)]
+
+
 class QueueStats(C.Structure):
     _fields_ = [('jobs', C.c_uint64), ('positions', C.c_uint64), ('batches', C.c_uint64),
                 ('max_batch_seen', C.c_uint64), ('wait_ms_total', C.c_double),
@@ -45,7 +51,7 @@ ABI_SYMBOLS = [
     'maru_eval_forward_states', 'maru_eval_forward_states_device',
     'maru_eval_forward_planes_device', 'maru_eval_sync', 'maru_eval_stream', 'maru_encode_planes',
     'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
-    'maru_eval_debug_set',
+    'maru_eval_debug_set', 'maru_eval_profile_states',
     'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
     'maru_queue_get_stats', 'maru_last_error', 'maru_abi_version',
 ]
@@ -85,6 +91,8 @@ def load_library():
     lib.maru_encode_planes_device.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_debug_planes.argtypes = [vp, ci, vp, ci, ci]
     lib.maru_eval_debug_set.argtypes = [vp, ci, ci]
+    lib.maru_eval_profile_states.argtypes = [vp, vp, vp, ci, C.POINTER(LaunchTime), ci,
+                                             C.POINTER(ci)]
     lib.maru_eval_debug_policy_logits.argtypes = [vp, vp, ci]
     lib.maru_queue_create.argtypes = [C.POINTER(vp), ci, ci, C.POINTER(vp)]
     lib.maru_queue_destroy.argtypes = [vp]
@@ -207,6 +215,16 @@ class Evaluator:
     def encode_planes_device(self, d_states: int, d_rows: int, n: int) -> None:
         _check(self.lib, self.lib.maru_encode_planes_device(self.handle, d_states, d_rows, n),
                'maru_encode_planes_device')
+
+    def profile_states_device(self, d_states: int, d_out: int, n: int):
+        """One un-graphed forward with a CUDA-event pair around every launch -> list of dicts."""
+        arr = (LaunchTime * 256)()
+        cnt = C.c_int(0)
+        _check(self.lib, self.lib.maru_eval_profile_states(self.handle, d_states, d_out, n, arr, 256,
+                                                           C.byref(cnt)), 'maru_eval_profile_states')
+        return [dict(name=arr[i].name.decode(), kind=arr[i].kind, cin=arr[i].cin, cout=arr[i].cout,
+                     taps=arr[i].taps, ms=arr[i].ms, flops=arr[i].flops, bytes=arr[i].bytes)
+                for i in range(min(cnt.value, 256))]
 
     def sync(self) -> None:
         _check(self.lib, self.lib.maru_eval_sync(self.handle), 'maru_eval_sync')

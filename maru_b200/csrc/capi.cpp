@@ -157,6 +157,15 @@ int maru_eval_debug_planes(maru_eval* ev, int which, float* out, int n, int chan
   return 0;
 }
 
+int maru_eval_profile_states(maru_eval* ev, const maru_state* d_states, float* d_out, int n,
+                             maru_launch_time* out, int max_launches, int* n_launches) {
+  if (ev == nullptr || out == nullptr || n_launches == nullptr) {
+    maru::set_error("maru_eval_profile_states: null argument");
+    return 1;
+  }
+  return E(ev)->profile_states(d_states, d_out, n, out, max_launches, n_launches);
+}
+
 int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);

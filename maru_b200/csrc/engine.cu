@@ -137,6 +137,7 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
     set_error("weight pack tensor " + name + " has unexpected shape");
     return 1;
   }
+  L.name = name;
   L.cin = cin;
   L.cout = cout;
   L.taps = taps;
@@ -351,7 +352,62 @@ int Engine::conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat1
   p.dbg = dbg_desc;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
   launches_done++;
+  {
+    // algorithmic figures at T = 361 on-board tokens per position (stem: 33 planes + 7 infos)
+    const double T = (double)CELLS * n;
+    const double cin_alg = (L.name == "stem") ? IN_PLANES : L.cin;
+    double fl = 2.0 * T * cin_alg * L.cout * L.taps;
+    if (L.name == "stem") fl += 2.0 * IN_INFOS * L.cout * n;
+    const double by = T * (cin_alg + L.cout + (res ? L.cout : 0)) * 2.0 + (double)L.taps * L.cin * L.cout * 2.0;
+    prof_begin(L.name.c_str(), L.taps == 9 ? 1 : 2, L.cin, L.cout, L.taps, fl, by, st);
+  }
   CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
+  prof_end(st);
+  return 0;
+}
+
+void Engine::prof_begin(const char* name, int kind, int cin, int cout, int taps, double flops,
+                        double bytes, cudaStream_t st) {
+  if (prof == nullptr) return;
+  maru_launch_time t;
+  memset(&t, 0, sizeof t);
+  snprintf(t.name, sizeof t.name, "%s", name);
+  t.kind = kind;
+  t.cin = cin;
+  t.cout = cout;
+  t.taps = taps;
+  t.flops = flops;
+  t.bytes = bytes;
+  prof->push_back(t);
+  while ((int)prof_ev.size() < 2 * (int)prof->size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    prof_ev.push_back(e);
+  }
+  cudaEventRecord(prof_ev[2 * (prof->size() - 1)], st);
+}
+void Engine::prof_end(cudaStream_t st) {
+  if (prof == nullptr) return;
+  cudaEventRecord(prof_ev[2 * (prof->size() - 1) + 1], st);
+}
+
+int Engine::profile_states(const maru_state* d_states, float* d_out, int n, maru_launch_time* out,
+                           int max, int* count) {
+  std::lock_guard<std::mutex> lock(mu);
+  CK(cudaSetDevice(gpu_id));
+  if (n <= 0 || n > max_batch) {
+    set_error("maru_eval_profile_states: n out of range");
+    return 1;
+  }
+  std::vector<maru_launch_time> rec;
+  prof = &rec;
+  const int rc = launch_all(KIND_STATES, d_states, d_out, n, nullptr, stream);
+  prof = nullptr;
+  if (rc) return 1;
+  CK(cudaStreamSynchronize(stream));
+  for (size_t i = 0; i < rec.size(); i++) cudaEventElapsedTime(&rec[i].ms, prof_ev[2 * i], prof_ev[2 * i + 1]);
+  *count = (int)rec.size();
+  for (int i = 0; i < (int)rec.size() && i < max; i++) out[i] = rec[i];
   return 0;
 }
 
@@ -387,7 +443,11 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
       ap.n_dev = n_dev;
       if (!(dbg_stop_after >= 0 && launches_done >= dbg_stop_after)) {
         launches_done++;
+        const double T = CELLS;
+        prof_begin(("att" + std::to_string(ai - 1) + ".core").c_str(), 3, C, C, 0,
+                   4.0 * T * T * C * n, T * 4.0 * C * 2.0 * n, st);
         CK(launch_attention(ap, st));
+        prof_end(st);
       }
       if (conv(A.proj, o, h, h, 0, n, n_dev, st)) return 1;           // h = h + proj(o), in place
     }
@@ -410,16 +470,25 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
   hp.cv = Cv;
   hp.n_dev = n_dev;
   if (dbg_stop_after >= 0) return 0;
+  prof_begin("heads", 4, Ch, 6, 0, (2.0 * CELLS * Ch * 6 + 2.0 * 2 * Ch * Cv + 2.0 * Cv * 3) * n,
+             ((double)CELLS * Ch * 2 + OUT_ROW * 4.0) * n, st);
   CK(launch_heads(hp, st));
+  prof_end(st);
   return 0;
 }
 
 int Engine::launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev,
                        cudaStream_t st) {
   if (kind == KIND_STATES) {
+    prof_begin("encode", 0, 0, IN_PLANES, 0, 0.0,
+               ((double)sizeof(maru_state) + (double)CELLS * IN_PLANES * 2.0) * n, st);
     CK(launch_encode_trunk(static_cast<const maru_state*>(d_in), x0, mask, rows_alloc, n, n_dev, st));
+    prof_end(st);
   } else {
+    prof_begin("ingest", 0, 0, IN_PLANES, 0, 0.0, ((double)IN_ROW * 4.0 + (double)CELLS * IN_PLANES * 2.0) * n,
+               st);
     CK(launch_ingest_rows(static_cast<const float*>(d_in), x0, mask, rows_alloc, n, n_dev, st));
+    prof_end(st);
   }
   return launch_trunk(n, n_dev, d_out, st);
 }

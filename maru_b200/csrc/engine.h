@@ -19,6 +19,7 @@ void set_error(const std::string& s);
 struct Pack;
 
 struct ConvLayer {
+  std::string name;
   int cin = 0, cout = 0, taps = 0, nt = 0;
   __nv_bfloat16* w = nullptr;
   float* b = nullptr;
@@ -82,6 +83,16 @@ struct Engine {
   int dbg_desc = 0;         // debug: UMMA descriptor experiment bits
   int launches_done = 0;
   void clear_graphs();
+
+  // per-launch profiling (maru_eval_profile_states): when prof != nullptr every launch is bracketed
+  std::vector<maru_launch_time>* prof = nullptr;
+  std::vector<cudaEvent_t> prof_ev;
+  int prof_n = 0;
+  void prof_begin(const char* name, int kind, int cin, int cout, int taps, double flops, double bytes,
+                  cudaStream_t st);
+  void prof_end(cudaStream_t st);
+  int profile_states(const maru_state* d_states, float* d_out, int n, maru_launch_time* out, int max,
+                     int* count);
 
   double flops_alg = 0, flops_exec = 0;
   int launches_per_forward = 0;
