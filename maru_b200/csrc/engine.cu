@@ -349,7 +349,6 @@ int Engine::conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat1
   p.cout_total = L.cout;
   p.relu = relu;
   p.n_dev = n_dev;
-  p.dbg = dbg_desc;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
   launches_done++;
   {

@@ -33,9 +33,9 @@ struct ConvParams {
   int m_rows;                // total_rows(n)
   int cout_total;
   int relu;
+  int stages;                // pipeline depth (filled by the launcher from the smem budget)
   const int* n_dev;          // optional: number of positions read on the device (graph replay with
                              // a smaller batch than the one captured); overrides m_rows
-  int dbg;                   // bring-up: bit0 swap LBO/SBO of A, bit1 swap LBO/SBO of B
 };
 
 cudaError_t configure_conv_gemm();
