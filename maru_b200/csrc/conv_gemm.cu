@@ -16,14 +16,17 @@
 //   * the epilogue (one TMEM lane = one row per thread) reads residuals and writes outputs as
 //     16-byte row-consecutive accesses: a warp store is one contiguous 512-byte segment.
 //
-// Roles (192 threads, persistent over M tiles of 128 rows, 1 CTA per SM):
-//   warp 0   : producer  — weights once, then per tile one input slab (+ the residual tile, so the
-//              epilogue never waits on a global load) into an mbarrier ring of STAGES stages
-//   warp 1   : TMEM alloc + elected-lane tcgen05.mma issue, accumulators double-buffered in TMEM
-//   warps 2-5: epilogue  — tcgen05.ld, bias/residual/ReLU/mask, bf16 pack, global store
+// Roles (320 threads, persistent over M tiles of 128 rows, 1 CTA per SM):
+//   warp 0   : producer  — weights once, then per tile one input slab + mask (+ the residual tile)
+//              into an mbarrier ring of up to 4 stages: the epilogue never waits on a global load
+//   warp 1   : TMEM alloc + elected-lane tcgen05.mma issue (bias and residual are MMAs too),
+//              accumulators double-buffered in TMEM
+//   warps 2-9: epilogue  — tcgen05.ld, bf16 pack, packed ReLU, mask select, 16-byte stores
 #include "kernels.h"
 
 namespace maru {
+
+constexpr int CONV_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
 
 template <int CIN, int NT, int TAPS>
 struct ConvCfg {
@@ -31,40 +34,53 @@ struct ConvCfg {
   static constexpr int SLAB_ROWS = TILE_M + 2 * LEAD;          // 176 or 128 (multiple of 8)
   static constexpr int KCH = CIN / 8;                          // 16-byte channel chunks
   static constexpr int W_BYTES = TAPS * CIN * NT * 2;
+  static constexpr int ONES_BYTES = 2 * TILE_M * 16;           // A operand of the bias MMA  (K = 16)
+  static constexpr int BIASB_BYTES = 2 * NT * 16;              // B operand of the bias MMA
+  static constexpr int IDENT_BYTES = NT * NT * 2;              // B operand of the residual MMAs
   static constexpr int SLAB_BYTES = SLAB_ROWS * CIN * 2;
   static constexpr int RES_BYTES = TILE_M * NT * 2;            // residual tile [NT/8][128][16 B]
+  static constexpr int MASK_BYTES = TILE_M;                    // board mask of the tile's rows
   static constexpr int MAX_STAGES = 4;
-  static constexpr int BIAS_BYTES = NT * 4;
   static constexpr int BAR_BYTES = 128;
-  static constexpr int FIXED_BYTES = W_BYTES + BIAS_BYTES + BAR_BYTES + 16;
   static constexpr int SMEM_LIMIT = 232448;                    // 227 KB per CTA
-  // a stage = input slab (+ residual tile when the layer has one); as many stages as fit, <= 4
-  static int stage_bytes(bool has_res) { return SLAB_BYTES + (has_res ? RES_BYTES : 0); }
+  static int fixed_bytes(bool has_res) {
+    return W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + 16 + (has_res ? IDENT_BYTES : 0);
+  }
+  // a stage = input slab + mask (+ residual tile when the layer has one); as many as fit, <= 4
+  static int stage_bytes(bool has_res) { return SLAB_BYTES + MASK_BYTES + (has_res ? RES_BYTES : 0); }
   static int stages(bool has_res) {
-    int n = (SMEM_LIMIT - FIXED_BYTES) / stage_bytes(has_res);
+    int n = (SMEM_LIMIT - fixed_bytes(has_res)) / stage_bytes(has_res);
     return n > MAX_STAGES ? MAX_STAGES : n;
   }
-  static int smem_bytes(bool has_res) { return FIXED_BYTES + stages(has_res) * stage_bytes(has_res); }
+  static int smem_bytes(bool has_res) { return fixed_bytes(has_res) + stages(has_res) * stage_bytes(has_res); }
   static constexpr int TMEM_COLS = (2 * NT <= 32) ? 32 : (2 * NT <= 64) ? 64 : (2 * NT <= 128) ? 128
                                    : (2 * NT <= 256) ? 256 : 512;
-  static_assert(CIN % 16 == 0 && NT % 16 == 0 && NT >= 16 && NT <= 256, "UMMA shape");
+  static_assert(CIN % 16 == 0 && NT % 32 == 0 && NT >= 32 && NT <= 256, "UMMA shape");
   static_assert(TAPS == 1 || LEAD >= HALO, "slab lead must cover the 3x3 halo");
-  static_assert(FIXED_BYTES + SLAB_BYTES + RES_BYTES <= SMEM_LIMIT, "one stage must fit in 227 KB");
+  static_assert(W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + 16 + SLAB_BYTES + MASK_BYTES <= SMEM_LIMIT,
+                "one stage must fit");
 };
 
+// Epilogue work is pushed onto the (otherwise ~70 % idle) tensor pipe:
+//   * bias     : D  = ones[128 x 16] . biasB[NT x 16]^T   (bias split into bf16 hi + lo, K cols 0/1)
+//   * residual : D += res[128 x NT]  . I[NT x NT]^T       (bf16 x 1.0 is exact in the fp32 accumulator)
+//   * conv     : D += sum_t slab_t[128 x CIN] . W_t[NT x CIN]^T
+// so that the 8 epilogue warps only do  tcgen05.ld -> cvt.bf16x2 -> max.bf16x2 -> mask select -> st.
 template <int CIN, int NT, int TAPS>
-__global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
+__global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvParams p) {
   using Cfg = ConvCfg<CIN, NT, TAPS>;
   extern __shared__ __align__(128) uint8_t smem[];
   constexpr int MAXS = Cfg::MAX_STAGES;
   const bool has_res = p.res != nullptr;
   const int STAGES = p.stages;
-  const int STAGE_BYTES = Cfg::SLAB_BYTES + (has_res ? Cfg::RES_BYTES : 0);
+  const int STAGE_BYTES = Cfg::SLAB_BYTES + Cfg::MASK_BYTES + (has_res ? Cfg::RES_BYTES : 0);
   uint8_t* s_w = smem;
-  float* s_bias = reinterpret_cast<float*>(smem + Cfg::W_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::W_BYTES + Cfg::BIAS_BYTES);
-  uint8_t* s_stage = smem + Cfg::W_BYTES + Cfg::BIAS_BYTES + Cfg::BAR_BYTES + 16;
-  uint64_t* full = bars;                   // [MAXS] input slab (+ residual tile) landed
+  uint8_t* s_ones = s_w + Cfg::W_BYTES;
+  uint8_t* s_biasb = s_ones + Cfg::ONES_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_biasb + Cfg::BIASB_BYTES);
+  uint8_t* s_ident = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES + 16;
+  uint8_t* s_stage = s_ident + (has_res ? Cfg::IDENT_BYTES : 0);
+  uint64_t* full = bars;                   // [MAXS] input slab + mask (+ residual tile) landed
   uint64_t* empty = bars + MAXS;           // [MAXS] stage reusable
   uint64_t* tfull = bars + 2 * MAXS;       // [2] accumulator ready
   uint64_t* tempty = tfull + 2;            // [2] accumulator drained
@@ -78,14 +94,15 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
   const int n_tiles = (m_rows + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < STAGES; i++) {
+    for (int i = 0; i < MAXS; i++) {
       mbar_init(&full[i], 1);
-      // the MMA commit frees the slab; with a residual the 4 epilogue warps must also be done
-      mbar_init(&empty[i], has_res ? 5 : 1);
+      // a stage is free once the MMA commit retired (slab, residual) and the 8 epilogue warps are
+      // done with its mask
+      mbar_init(&empty[i], 9);
     }
     for (int i = 0; i < 2; i++) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
+      mbar_init(&tempty[i], 8);
     }
     mbar_init(wbar, 1);
     fence_mbar_init();
@@ -95,7 +112,31 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
     tmem_relinquish();
   }
   if (warp >= 2) {
-    for (int i = threadIdx.x - 64; i < NT; i += 128) s_bias[i] = p.bias[group * NT + i];
+    // constant MMA operands, K-major SWIZZLE_NONE images: [k-chunk][row][8 bf16]
+    const int t = threadIdx.x - 64;
+    for (int i = t; i < 2 * TILE_M; i += 256) {               // ones: (1, 1, 0, ...) in chunk 0
+      const uint32_t w0 = (i < TILE_M) ? 0x3F803F80u : 0u;
+      *reinterpret_cast<uint4*>(s_ones + i * 16) = make_uint4(w0, 0u, 0u, 0u);
+    }
+    for (int i = t; i < 2 * NT; i += 256) {                   // bias: (hi, lo, 0, ...) in chunk 0
+      uint32_t w0 = 0u;
+      if (i < NT) {
+        const float bv = p.bias[group * NT + i];
+        const __nv_bfloat16 hi = __float2bfloat16_rn(bv);
+        const __nv_bfloat16 lo = __float2bfloat16_rn(bv - __bfloat162float(hi));
+        w0 = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+      }
+      *reinterpret_cast<uint4*>(s_biasb + i * 16) = make_uint4(w0, 0u, 0u, 0u);
+    }
+    if (has_res) {
+      for (int i = t; i < (NT / 8) * NT; i += 256) {          // identity: [k-chunk c][row n]
+        const int c = i / NT, n = i - c * NT;
+        uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if ((n >> 3) == c) w[(n & 7) >> 1] = (n & 1) ? 0x3F800000u : 0x00003F80u;
+        *reinterpret_cast<uint4*>(s_ident + i * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+    fence_async_smem();                                       // generic stores -> visible to UMMA
   }
   tc_fence_before();
   __syncthreads();
@@ -121,7 +162,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(&empty[stage], phase ^ 1);
       if (elect_one()) {
-        mbar_expect_tx(&full[stage], Cfg::SLAB_BYTES + (has_res ? Cfg::RES_BYTES : 0));
+        mbar_expect_tx(&full[stage], STAGE_BYTES);
         const size_t row0 = (size_t)GUARD_ROWS + (size_t)tile * TILE_M;
         uint8_t* dst = s_stage + stage * STAGE_BYTES;
 #pragma unroll 1
@@ -129,12 +170,14 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
           const __nv_bfloat16* src = p.in + ((size_t)(p.in_chunk0 + c) * p.rows_alloc + row0 - Cfg::LEAD) * 8;
           bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, &full[stage]);
         }
+        bulk_load_1d(dst + Cfg::SLAB_BYTES, p.mask + (size_t)tile * TILE_M, Cfg::MASK_BYTES, &full[stage]);
         if (has_res) {
 #pragma unroll 1
           for (int c = 0; c < NT / 8; c++) {
             const __nv_bfloat16* src =
                 p.res + ((size_t)(p.res_chunk0 + group * (NT / 8) + c) * p.rows_alloc + row0) * 8;
-            bulk_load_1d(dst + Cfg::SLAB_BYTES + c * TILE_M * 16, src, TILE_M * 16, &full[stage]);
+            bulk_load_1d(dst + Cfg::SLAB_BYTES + Cfg::MASK_BYTES + c * TILE_M * 16, src, TILE_M * 16,
+                         &full[stage]);
           }
         }
       }
@@ -147,10 +190,15 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
   } else if (warp == 1) {
     // =========================== MMA issuer ===========================
     constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, NT, 0, 0);
-    // descriptors differ only in the 14-bit start-address field: precompute the rest once
-    const uint64_t a_hi = umma_desc(0, Cfg::SLAB_ROWS * 16, 128);
-    const uint64_t b_hi = umma_desc(0, NT * 16, 128);
-    const uint32_t w_addr = smem_u32(s_w);
+    // descriptors differ only in the 14-bit start-address field (smem < 256 KB: no carry)
+    const uint64_t a_d = umma_desc(0, Cfg::SLAB_ROWS * 16, 128);   // slab:      LBO = slab plane
+    const uint64_t r_d = umma_desc(0, TILE_M * 16, 128);           // res, ones: LBO = 128 rows
+    const uint64_t b_d = umma_desc(0, NT * 16, 128);               // W, biasB, I: LBO = NT rows
+    const uint32_t a_hi = (uint32_t)(a_d >> 32), r_hi = (uint32_t)(r_d >> 32), b_hi = (uint32_t)(b_d >> 32);
+    const uint32_t w_lo = (uint32_t)b_d + (smem_u32(s_w) >> 4);
+    const uint32_t ones_lo = (uint32_t)r_d + (smem_u32(s_ones) >> 4);
+    const uint32_t biasb_lo = (uint32_t)b_d + (smem_u32(s_biasb) >> 4);
+    const uint32_t ident_lo = (uint32_t)b_d + (smem_u32(s_ident) >> 4);
     mbar_wait(wbar, 0);
     int stage = 0;
     uint32_t phase = 0;
@@ -162,11 +210,16 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
       mbar_wait(&full[stage], phase);
       tc_fence_after();
       if (elect_one()) {
-        // smem addresses are < 256 KB, so (addr >> 4) never carries out of the 14-bit field:
-        // per-MMA descriptor = base + compile-time constant (one uniform add)
-        const uint64_t a_base = a_hi + (smem_u32(s_stage + stage * STAGE_BYTES) >> 4);
-        const uint64_t b_base = b_hi + (w_addr >> 4);
+        const uint32_t st_addr = smem_u32(s_stage + stage * STAGE_BYTES);
+        const uint32_t a_lo = (uint32_t)a_d + (st_addr >> 4);
+        const uint32_t res_lo = (uint32_t)r_d + ((st_addr + Cfg::SLAB_BYTES + Cfg::MASK_BYTES) >> 4);
         const uint32_t d_tmem = tmem_base + acc * NT;
+        umma_bf16_lohi<0>(d_tmem, ones_lo, r_hi, biasb_lo, b_hi, idesc);           // D = bias
+        if (has_res) {
+#pragma unroll
+          for (int j = 0; j < NT / 16; j++)                                         // D += residual
+            umma_bf16_lohi<1>(d_tmem, res_lo + 2 * j * TILE_M, r_hi, ident_lo + 2 * j * NT, b_hi, idesc);
+        }
 #pragma unroll
         for (int t = 0; t < TAPS; t++) {
           const int off = (TAPS == 9) ? ((t / 3 - 1) * PITCH + (t % 3 - 1)) : 0;
@@ -174,10 +227,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
           for (int j = 0; j < CIN / 16; j++) {
             const uint32_t a16 = (2 * j) * Cfg::SLAB_ROWS + Cfg::LEAD + off;   // in 16-byte units
             const uint32_t b16 = (t * Cfg::KCH + 2 * j) * NT;
-            umma_bf16(d_tmem, a_base + a16, b_base + b16, idesc, (t | j) != 0);
+            umma_bf16_lohi<1>(d_tmem, a_lo + a16, a_hi, w_lo + b16, b_hi, idesc);
           }
         }
-        umma_commit(&empty[stage]);  // slab reusable once these MMAs retire
+        umma_commit(&empty[stage]);  // slab / residual reusable once these MMAs retire
         umma_commit(&tfull[acc]);    // accumulator complete
       }
       __syncwarp();
@@ -187,8 +240,10 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
       }
     }
   } else {
-    // =========================== epilogue ===========================
-    const int lg = warp & 3;  // TMEM lane group this warp may access
+    // =========================== epilogue (8 warps) ===========================
+    constexpr int CW = NT / 2;               // columns per warp
+    const int lg = warp & 3;                 // TMEM lane group this warp may access
+    const int half = (warp - 2) >> 2;        // which half of the NT columns
     int it = 0;
     int stage = 0;
     uint32_t phase = 0;
@@ -198,43 +253,48 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
       const int trow = lg * 32 + lane;
       const int row = tile * TILE_M + trow;
       const bool valid = row < m_rows;
-      const uint8_t mk = valid ? p.mask[row] : (uint8_t)0;   // issued before the wait: latency hidden
       const size_t grow = (size_t)GUARD_ROWS + row;
-      const uint8_t* s_res = s_stage + stage * STAGE_BYTES + Cfg::SLAB_BYTES;
-      if (has_res) mbar_wait(&full[stage], phase);           // residual tile landed with the slab
+      const uint8_t* s_mask = s_stage + stage * STAGE_BYTES + Cfg::SLAB_BYTES;
+      mbar_wait(&full[stage], phase);                        // mask landed with the slab
+      const bool on = valid && (s_mask[trow] != 0);
       mbar_wait(&tfull[acc], acc_phase);
       tc_fence_after();
-      const bool on = mk != 0;
-#pragma unroll 1
-      for (int c0 = 0; c0 < NT; c0 += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + c0, v);
+      const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + half * CW;
+      const int chunk0 = p.out_chunk0 + group * (NT / 8) + half * (CW / 8);
+      __nv_bfloat16* out_row = p.out + ((size_t)chunk0 * p.rows_alloc + grow) * 8;
+      if constexpr (CW == 16) {
+        uint32_t v[16];
+        tmem_ld16(t_addr, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const int lchunk = c0 / 8 + q;                      // chunk within this group's NT channels
-          float x[8];
+        for (int q = 0; q < 2; q++) {
+          uint32_t o[4];
 #pragma unroll
-          for (int e = 0; e < 8; e++) x[e] = __uint_as_float(v[q * 8 + e]) + s_bias[c0 + q * 8 + e];
-          if (has_res) {
-            const uint4 r = *reinterpret_cast<const uint4*>(s_res + (lchunk * TILE_M + trow) * 16);
-            x[0] += bf16_lo(r.x); x[1] += bf16_hi(r.x);
-            x[2] += bf16_lo(r.y); x[3] += bf16_hi(r.y);
-            x[4] += bf16_lo(r.z); x[5] += bf16_hi(r.z);
-            x[6] += bf16_lo(r.w); x[7] += bf16_hi(r.w);
+          for (int e = 0; e < 4; e++) {
+            uint32_t pk = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+            if (p.relu) pk = relu_bf16x2(pk);
+            o[e] = on ? pk : 0u;
           }
-          if (p.relu) {
+          if (valid) *reinterpret_cast<uint4*>(out_row + (size_t)q * p.rows_alloc * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < CW; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + c0, v);
+          tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 8; e++) x[e] = fmaxf(x[e], 0.0f);
-          }
-          uint4 o;
-          o.x = on ? pack_bf16x2(x[0], x[1]) : 0u;
-          o.y = on ? pack_bf16x2(x[2], x[3]) : 0u;
-          o.z = on ? pack_bf16x2(x[4], x[5]) : 0u;
-          o.w = on ? pack_bf16x2(x[6], x[7]) : 0u;
-          if (valid) {
-            const int chunk = p.out_chunk0 + group * (NT / 8) + lchunk;
-            *reinterpret_cast<uint4*>(p.out + ((size_t)chunk * p.rows_alloc + grow) * 8) = o;
+          for (int q = 0; q < 4; q++) {
+            uint32_t o[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              uint32_t pk = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+              if (p.relu) pk = relu_bf16x2(pk);
+              o[e] = on ? pk : 0u;
+            }
+            if (valid)
+              *reinterpret_cast<uint4*>(out_row + (size_t)(c0 / 8 + q) * p.rows_alloc * 8) =
+                  make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
       }
@@ -242,7 +302,7 @@ __global__ void __launch_bounds__(192, 1) conv_gemm_kernel(const ConvParams p) {
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&tempty[acc]);
-        if (has_res) mbar_arrive(&empty[stage]);
+        mbar_arrive(&empty[stage]);
       }
       if (++stage == STAGES) {
         stage = 0;
@@ -272,13 +332,14 @@ static cudaError_t launch_cfg(ConvParams p, int sm_count, cudaStream_t stream) {
   using Cfg = ConvCfg<CIN, NT, TAPS>;
   const bool has_res = p.res != nullptr;
   p.stages = Cfg::stages(has_res);
+  if (p.stages < 1) return cudaErrorInvalidConfiguration;   // e.g. stem shape with a residual
   const int groups = p.cout_total / NT;
   const int n_tiles = (p.m_rows + TILE_M - 1) / TILE_M;
   int gx = sm_count / groups;
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
   dim3 grid(gx, groups, 1);
-  conv_gemm_kernel<CIN, NT, TAPS><<<grid, 192, Cfg::smem_bytes(has_res), stream>>>(p);
+  conv_gemm_kernel<CIN, NT, TAPS><<<grid, CONV_THREADS, Cfg::smem_bytes(has_res), stream>>>(p);
   return cudaGetLastError();
 }
 
