@@ -288,8 +288,6 @@ def run_b200(args):
     # ---------------- per-launch profile (roofline of the dominant kernel) -----------------------
     prof = {}
     for rep in range(max(3, min(args.steps, 10))):
-        with torch.cuda.stream(stream):
-            flush.zero_()
         for l in ev.profile_states_device(d_states.data_ptr(), d_out.data_ptr(), B):
             key = (l['kind'], l['cin'], l['cout'], l['taps'])
             a = prof.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, name=l['name']))

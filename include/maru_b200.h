@@ -137,14 +137,16 @@ int  maru_eval_debug_planes(maru_eval* e, int which, float* out, int n, int chan
 /* Pre-softmax policy logits of the last forward: [n][2][361] fp32 (north_star tolerance is on logits). */
 int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 /* Debug knobs. key 0: stop the launch sequence after `value` trunk launches (<0: run everything;
- * the heads then do not run). key 1: UMMA descriptor experiment bits (bring-up only; 0 = normal). */
+ * the heads then do not run). key 1: bit0 = disable programmatic dependent launch (A/B timing), bit2 = use the legacy
+ * mma.sync attention kernel instead of the tcgen05 one (A/B). */
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
 int  maru_eval_debug_set(maru_eval* e, int key, int value);
 
 /* ---- per-launch timing (roofline evidence) --------------------------------------------------- */
-/* Runs ONE forward of n positions (device-resident compact records) WITHOUT a CUDA graph, with a
- * CUDA event pair around every kernel launch on the evaluator's stream, and reports each launch.
+/* Per-launch timing of the forward of n positions (device-resident compact records): after one
+ * plain forward, every launch of the sequence is issued 10 times back to back inside one CUDA event
+ * pair on the evaluator's stream; ms = that span / 10 (event overhead amortised, launch gaps kept).
  * flops / bytes are the ALGORITHMIC figures of that launch at T = 361 tokens per position
  * (DESIGN.md "Kernels"); kind: 0 encode, 1 conv3x3, 2 conv1x1, 3 attention core, 4 heads. */
 typedef struct maru_launch_time {

@@ -53,6 +53,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
   uint8_t* s_mask = s_v + DCH * PLANE_BYTES;       // [400]
   uint64_t* bar = reinterpret_cast<uint64_t*>(s_mask + 512);
 
+  pdl_launch_dependents();
   const int heads = p.channels / D;
   const int pos = blockIdx.x / heads;
   const int head = blockIdx.x - pos * heads;
@@ -68,6 +69,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
     fence_mbar_init();
   }
   __syncthreads();
+  pdl_wait();
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar, 2 * DCH * PLANE_BYTES);
     for (int c = 0; c < DCH; c++) {
@@ -197,12 +199,302 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
   }
 }
 
+// =============================================================================================
+// v2: tcgen05 / TMEM attention for head_dim 32.
+//
+// One CTA = (position, head), two CTAs co-resident per SM (256 TMEM columns and ~103 KB smem each)
+// so that one CTA's MMAs overlap the other's exponentials.  Per 128-query tile and per key part
+// (400 padded keys = 144 + 128 + 128):
+//     S  = Q K^T          tcgen05.mma  M=128, N=part, K=32   (Q, K: K-major chunk-planar images)
+//     P  = exp2(S - c_i)  4 softmax warps, one TMEM lane (= query row) per thread, bf16 to smem
+//     O += P [V | 1]      tcgen05.mma  M=128, N=48,   K=part (V read as an MN-major B operand; the
+//                         extra "ones" column, zero for masked keys, yields the row sums l_i)
+// c_i = min(|q_i| * max_j |k_j|, 96) >= max_j S_ij (Cauchy-Schwarz) replaces the running row max:
+// softmax is shift invariant, p <= 1 cannot overflow, and because V rows and the ones column of
+// off-board keys are zero the key mask costs nothing in the inner loop and the key parts are
+// independent (no online rescaling of O).  Final O_i / l_i in the epilogue.
+// Query tiles start at rows 0, 128, 256 and 272; in the last one only rows 384..399 are new.
+// =============================================================================================
+constexpr int A2_SM_WARPS = 8;              // warps 0..7 softmax/epilogue: lane group = w & 3, column half = w >> 2
+constexpr int A2_WARPS = A2_SM_WARPS + 1;   // warp 8: control (bulk loads + MMA issue)
+constexpr int A2_THREADS = A2_WARPS * 32;
+constexpr int A2_D = 32, A2_DCH = 4;
+constexpr int A2_PLANE = POS_ROWS * 16;     // 6400 B: one 8-channel plane of one position
+constexpr int A2_K_BYTES = A2_DCH * A2_PLANE;
+constexpr int A2_V_BYTES = (A2_DCH + 1) * A2_PLANE;   // + ones plane; the 6th plane aliases P (unused cols)
+constexpr int A2_PMAX = 144;
+constexpr int A2_P_BYTES = (A2_PMAX / 8) * TILE_M * 16;
+constexpr int A2_Q_BYTES = A2_DCH * TILE_M * 16;
+constexpr int A2_SMEM = A2_K_BYTES + A2_V_BYTES + A2_P_BYTES + 2 * A2_Q_BYTES + 512 + 256 + 128;
+constexpr int A2_TMEM_COLS = 256;
+constexpr int A2_O_COL = 160;
+constexpr int A2_NV = 48;                   // V columns (32) + ones + padding to a multiple of 16
+
+// 16 S columns -> 16 probabilities -> two 16-byte P chunks of this row
+__device__ __forceinline__ void exp_store16(const uint32_t* v, float c, uint8_t* s_p, int chunk, int trow) {
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++)
+      o[e] = pack_bf16x2(ex2_approx(__uint_as_float(v[h * 8 + 2 * e]) - c),
+                         ex2_approx(__uint_as_float(v[h * 8 + 2 * e + 1]) - c));
+    *reinterpret_cast<uint4*>(s_p + ((chunk + h) * TILE_M + trow) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+// columns [C0, C0 + CN) of the S part: 32 columns in flight per tcgen05.wait::ld
+template <int C0, int CN>
+__device__ __forceinline__ void softmax_cols(uint32_t t_s, float c, uint8_t* s_p, int trow) {
+#pragma unroll
+  for (int c0 = 0; c0 + 32 <= CN; c0 += 32) {
+    uint32_t v[32];
+    tmem_ld32(t_s + C0 + c0, v);
+    tmem_ld_wait();
+    exp_store16(v, c, s_p, (C0 + c0) / 8, trow);
+    exp_store16(v + 16, c, s_p, (C0 + c0) / 8 + 2, trow);
+  }
+  if (CN % 32) {
+    uint32_t v[16];
+    tmem_ld16(t_s + C0 + CN - 16, v);
+    tmem_ld_wait();
+    exp_store16(v, c, s_p, (C0 + CN - 16) / 8, trow);
+  }
+}
+
+__global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint8_t* s_k = smem;
+  uint8_t* s_v = s_k + A2_K_BYTES;
+  uint8_t* s_p = s_v + A2_V_BYTES;
+  uint8_t* s_q = s_p + A2_P_BYTES;                       // two Q tile buffers
+  uint8_t* s_mask = s_q + 2 * A2_Q_BYTES;                // [400] (+pad)
+  float* s_red = reinterpret_cast<float*>(s_mask + 512); // [8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 512 + 256);
+  uint64_t* kv_full = bars;
+  uint64_t* q_full = bars + 1;      // [2]
+  uint64_t* s_full = bars + 3;
+  uint64_t* p_full = bars + 4;
+  uint64_t* o_full = bars + 5;
+  uint64_t* o_empty = bars + 6;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  pdl_launch_dependents();
+  const int heads = p.channels / A2_D;
+  const int pos = blockIdx.x / heads;
+  const int head = blockIdx.x - pos * heads;
+  if (pos >= ((p.n_dev != nullptr) ? *p.n_dev : p.n)) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const size_t prow0 = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS;
+  const int cch = p.channels / 8;
+  const int q_chunk0 = head * A2_DCH, k_chunk0 = cch + head * A2_DCH, v_chunk0 = 2 * cch + head * A2_DCH;
+  constexpr int N_TILES = 4;
+
+  if (threadIdx.x == 0) {
+    mbar_init(kv_full, 1);
+    mbar_init(&q_full[0], 1);
+    mbar_init(&q_full[1], 1);
+    mbar_init(s_full, 1);
+    mbar_init(p_full, A2_SM_WARPS);
+    mbar_init(o_full, 1);
+    mbar_init(o_empty, A2_SM_WARPS);
+    fence_mbar_init();
+  }
+  if (warp == A2_SM_WARPS) {
+    tmem_alloc(tmem_slot, A2_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // qkv and mask are written by the previous kernels
+
+  if (warp == A2_SM_WARPS) {
+    // =========================== control warp: bulk loads + MMA issue ===========================
+    auto load_q = [&](int tile, int buf) {
+      const int r0 = (tile == 3) ? 272 : tile * TILE_M;
+      mbar_expect_tx(&q_full[buf], A2_Q_BYTES);
+      for (int c = 0; c < A2_DCH; c++)
+        bulk_load_1d(s_q + buf * A2_Q_BYTES + c * TILE_M * 16,
+                     p.qkv + ((size_t)(q_chunk0 + c) * p.rows_alloc + prow0 + r0) * 8, TILE_M * 16, &q_full[buf]);
+    };
+    if (elect_one()) {
+      mbar_expect_tx(kv_full, A2_K_BYTES + A2_DCH * A2_PLANE);
+      for (int c = 0; c < A2_DCH; c++) {
+        bulk_load_1d(s_k + c * A2_PLANE, p.qkv + ((size_t)(k_chunk0 + c) * p.rows_alloc + prow0) * 8, A2_PLANE, kv_full);
+        bulk_load_1d(s_v + c * A2_PLANE, p.qkv + ((size_t)(v_chunk0 + c) * p.rows_alloc + prow0) * 8, A2_PLANE, kv_full);
+      }
+      load_q(0, 0);
+    }
+    __syncwarp();
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(TILE_M, A2_NV, 0, 1);   // B = V is MN-major
+    const uint64_t q_d = umma_desc(0, TILE_M * 16, 128);      // Q, P tiles: K-major, LBO = 128 rows
+    const uint64_t k_d = umma_desc(0, A2_PLANE, 128);         // K image:    K-major, LBO = plane
+    // V image read transposed (MN-major): SBO = distance between 8-channel planes (N direction),
+    // LBO = distance between 8-key groups (K direction)
+    const uint64_t v_d = umma_desc(0, 128, A2_PLANE);
+    const uint32_t q_hi = (uint32_t)(q_d >> 32), k_hi = (uint32_t)(k_d >> 32), v_hi = (uint32_t)(v_d >> 32);
+    const uint32_t k_lo = (uint32_t)k_d + (smem_u32(s_k) >> 4);
+    const uint32_t v_lo = (uint32_t)v_d + (smem_u32(s_v) >> 4);
+    const uint32_t p_lo = (uint32_t)q_d + (smem_u32(s_p) >> 4);
+    const uint32_t t_s = tmem_base, t_o = tmem_base + A2_O_COL;
+    mbar_wait(kv_full, 0);
+    uint32_t ph_p = 0, ph_oe = 0;
+    for (int tile = 0; tile < N_TILES; tile++) {
+      const int buf = tile & 1;
+      // the other Q buffer was last read by tile-1, whose MMAs completed before its last p_full
+      if (tile + 1 < N_TILES && elect_one()) load_q(tile + 1, buf ^ 1);
+      __syncwarp();
+      mbar_wait(&q_full[buf], (tile >> 1) & 1);
+      tc_fence_after();
+      const uint32_t qt_lo = (uint32_t)q_d + (smem_u32(s_q + buf * A2_Q_BYTES) >> 4);
+#pragma unroll
+      for (int part = 0; part < 3; part++) {
+        const int key0 = part == 0 ? 0 : (part == 1 ? 144 : 272);
+        const int pn = part == 0 ? 144 : 128;
+        if (elect_one()) {
+          // S = Q K^T over this key part (2 k16 steps)
+          const uint32_t idesc_qk = umma_idesc_bf16(TILE_M, pn, 0, 0);
+          umma_bf16_lohi<0>(t_s, qt_lo, q_hi, k_lo + key0, k_hi, idesc_qk);
+          umma_bf16_lohi<1>(t_s, qt_lo + 2 * TILE_M, q_hi, k_lo + key0 + 2 * POS_ROWS, k_hi, idesc_qk);
+          umma_commit(s_full);
+        }
+        __syncwarp();
+        mbar_wait(p_full, ph_p);           // softmax done: S consumed, P written (and fenced)
+        ph_p ^= 1;
+        if (part == 0 && tile > 0) {       // previous tile's O has been read by the epilogue
+          mbar_wait(o_empty, ph_oe);
+          ph_oe ^= 1;
+        }
+        tc_fence_after();
+        if (elect_one()) {
+          for (int j = 0; j < pn / 16; j++) {
+            const uint32_t a = p_lo + 2 * j * TILE_M;
+            const uint32_t b = v_lo + key0 + 16 * j;
+            if (part == 0 && j == 0) umma_bf16_lohi<0>(t_o, a, q_hi, b, v_hi, idesc_pv);
+            else umma_bf16_lohi<1>(t_o, a, q_hi, b, v_hi, idesc_pv);
+          }
+          if (part == 2) umma_commit(o_full);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // =========================== softmax + epilogue warps ===========================
+    const int lg = warp & 3, half = warp >> 2;
+    const int trow = lg * 32 + lane;                        // TMEM lane = row within the tile
+    const int st = threadIdx.x;                             // 0..255
+    for (int r = st; r < POS_ROWS; r += 256) s_mask[r] = p.mask[(size_t)pos * POS_ROWS + r];
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    // ones plane of V: 1.0 for on-board keys, 0 otherwise (row sums + key mask in one column)
+    for (int r = st; r < POS_ROWS; r += 256)
+      *reinterpret_cast<uint4*>(s_v + A2_DCH * A2_PLANE + r * 16) =
+          make_uint4(s_mask[r] ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    mbar_wait(kv_full, 0);
+    // max_j |k_j|^2
+    float mk = 0.0f;
+    for (int r = st; r < POS_ROWS; r += 256) {
+      float ss = 0.0f;
+#pragma unroll
+      for (int c = 0; c < A2_DCH; c++) {
+        const uint4 u = *reinterpret_cast<const uint4*>(s_k + c * A2_PLANE + r * 16);
+        const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                            bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+        for (int e = 0; e < 8; e++) ss = fmaf(f[e], f[e], ss);
+      }
+      mk = fmaxf(mk, ss);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mk = fmaxf(mk, __shfl_xor_sync(0xffffffffu, mk, o));
+    if (lane == 0) s_red[warp] = mk;
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    float maxk2 = s_red[0];
+#pragma unroll
+    for (int w = 1; w < A2_SM_WARPS; w++) maxk2 = fmaxf(maxk2, s_red[w]);
+    const uint32_t t_lane = tmem_base + ((uint32_t)(lg * 32) << 16);
+    uint32_t ph_s = 0, ph_o = 0;
+    for (int tile = 0; tile < N_TILES; tile++) {
+      const int buf = tile & 1;
+      const int r0 = (tile == 3) ? 272 : tile * TILE_M;
+      const int row = r0 + trow;
+      const bool active = (tile < 3) || (lg == 3);          // tile 3: only rows 384..399 are new
+      float c = 0.0f;
+      if (active) {
+        mbar_wait(&q_full[buf], (tile >> 1) & 1);
+        float ss = 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < A2_DCH; ch++) {
+          const uint4 u = *reinterpret_cast<const uint4*>(s_q + buf * A2_Q_BYTES + (ch * TILE_M + trow) * 16);
+          const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                              bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+          for (int e = 0; e < 8; e++) ss = fmaf(f[e], f[e], ss);
+        }
+        c = fminf(sqrtf(ss * maxk2) * 1.0001f + 1e-3f, 96.0f);
+      }
+#pragma unroll
+      for (int part = 0; part < 3; part++) {
+        mbar_wait(s_full, ph_s);
+        ph_s ^= 1;
+        tc_fence_after();
+        if (active) {
+          if (part == 0) {
+            if (half == 0) softmax_cols<0, 80>(t_lane, c, s_p, trow);
+            else softmax_cols<80, 64>(t_lane, c, s_p, trow);
+          } else {
+            if (half == 0) softmax_cols<0, 64>(t_lane, c, s_p, trow);
+            else softmax_cols<64, 64>(t_lane, c, s_p, trow);
+          }
+        }
+        fence_async_smem();     // P (and, first time, the ones plane) visible to the async proxy
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+      }
+      // ---- epilogue of the tile: O / l, query mask, store (each half-warp owns 16 channels)
+      mbar_wait(o_full, ph_o);
+      ph_o ^= 1;
+      tc_fence_after();
+      uint32_t o[16];
+      tmem_ld16(t_lane + A2_O_COL + half * 16, o);
+      const uint32_t lbits = tmem_ld1(t_lane + A2_O_COL + 32);
+      tmem_ld_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(o_empty);
+      const bool write = (tile < 3) ? true : (row >= 384);
+      if (write) {
+        const bool on = s_mask[row] != 0;
+        const float inv = on ? 1.0f / __uint_as_float(lbits) : 0.0f;
+#pragma unroll
+        for (int ch = 0; ch < 2; ch++) {
+          uint4 w;
+          w.x = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 0]) * inv, __uint_as_float(o[ch * 8 + 1]) * inv) : 0u;
+          w.y = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 2]) * inv, __uint_as_float(o[ch * 8 + 3]) * inv) : 0u;
+          w.z = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 4]) * inv, __uint_as_float(o[ch * 8 + 5]) * inv) : 0u;
+          w.w = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 6]) * inv, __uint_as_float(o[ch * 8 + 7]) * inv) : 0u;
+          *reinterpret_cast<uint4*>(p.out + ((size_t)(q_chunk0 + half * 2 + ch) * p.rows_alloc + prow0 + row) * 8) = w;
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == A2_SM_WARPS) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, A2_TMEM_COLS);
+  }
+}
+
 template <int D>
 static constexpr int attn_smem_bytes() { return 2 * (D / 8) * POS_ROWS * 16 + 512 + 16; }
 
 cudaError_t configure_attention() {
   cudaError_t e = cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        attn_smem_bytes<32>());
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
   if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               attn_smem_bytes<64>());
@@ -211,10 +503,15 @@ cudaError_t configure_attention() {
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   const int heads = p.channels / p.head_dim;
-  if (p.head_dim == 32) {
-    attention_kernel<32><<<p.n * heads, ATT_THREADS, attn_smem_bytes<32>(), stream>>>(p);
+  if (p.head_dim == 32 && !(p.dbg & 2)) {  // dbg bit1: legacy mma.sync kernel (A/B)
+    return launch_kernel(attention_tc_kernel, dim3(p.n * heads), dim3(A2_THREADS), A2_SMEM, stream,
+                         p.pdl != 0, p);
+  } else if (p.head_dim == 32) {
+    return launch_kernel(attention_kernel<32>, dim3(p.n * heads), dim3(ATT_THREADS), attn_smem_bytes<32>(),
+                         stream, p.pdl != 0, p);
   } else if (p.head_dim == 64) {
-    attention_kernel<64><<<p.n * heads, ATT_THREADS, attn_smem_bytes<64>(), stream>>>(p);
+    return launch_kernel(attention_kernel<64>, dim3(p.n * heads), dim3(ATT_THREADS), attn_smem_bytes<64>(),
+                         stream, p.pdl != 0, p);
   } else {
     return cudaErrorInvalidValue;
   }

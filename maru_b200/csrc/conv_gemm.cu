@@ -87,6 +87,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   uint64_t* wbar = tempty + 2;             // weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
+  pdl_launch_dependents();                      // let the next layer's CTAs start their prologue
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int group = blockIdx.y;                 // output-channel group of NT channels
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       }
     }
     __syncwarp();
+    pdl_wait();   // everything below reads what the previous kernel wrote (activations, mask)
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -339,8 +341,8 @@ static cudaError_t launch_cfg(ConvParams p, int sm_count, cudaStream_t stream) {
   if (gx < 1) gx = 1;
   if (gx > n_tiles) gx = n_tiles;
   dim3 grid(gx, groups, 1);
-  conv_gemm_kernel<CIN, NT, TAPS><<<grid, CONV_THREADS, Cfg::smem_bytes(has_res), stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(conv_gemm_kernel<CIN, NT, TAPS>, grid, dim3(CONV_THREADS), Cfg::smem_bytes(has_res),
+                       stream, p.pdl != 0, p);
 }
 
 // (cin, channels per tile, taps) instantiated for C = 64 / 128 / 256 networks

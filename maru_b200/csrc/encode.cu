@@ -181,6 +181,7 @@ __global__ void __launch_bounds__(416) encode_trunk_kernel(const maru_state* __r
   __shared__ __align__(16) maru_state s_state;
   __shared__ StateView s_view;
   __shared__ __nv_bfloat16 s_info[9];
+  pdl_launch_dependents();
   if (n_dev != nullptr) n = *n_dev;
   const int pos = blockIdx.x;
   if (pos >= n) {
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(416) ingest_rows_kernel(const float* __restric
                                                           uint8_t* __restrict__ mask, int rows_alloc,
                                                           int n, const int* __restrict__ n_dev) {
   __shared__ __nv_bfloat16 s_info[9];
+  pdl_launch_dependents();
   if (n_dev != nullptr) n = *n_dev;
   const int pos = blockIdx.x;
   if (pos >= n) {

@@ -80,7 +80,7 @@ struct Engine {
   std::map<GraphKey, cudaGraphExec_t> graphs;
 
   int dbg_stop_after = -1;  // debug: stop the launch sequence after this many trunk launches
-  int dbg_desc = 0;         // debug: UMMA descriptor experiment bits
+  int dbg_desc = 0;         // debug: bit0 = disable programmatic dependent launch
   int launches_done = 0;
   void clear_graphs();
 
@@ -88,6 +88,7 @@ struct Engine {
   std::vector<maru_launch_time>* prof = nullptr;
   std::vector<cudaEvent_t> prof_ev;
   int prof_n = 0;
+  int prof_reps = 1;        // each launch is repeated back to back this many times inside its event pair
   void prof_begin(const char* name, int kind, int cin, int cout, int taps, double flops, double bytes,
                   cudaStream_t st);
   void prof_end(cudaStream_t st);

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   __shared__ float s_hid[HEAD_MAX_CV];
   __shared__ float s_stat[4];
 
+  pdl_launch_dependents();
   const int pos = blockIdx.x;
   if (pos >= ((p.n_dev != nullptr) ? *p.n_dev : p.n)) return;
   const int tid = threadIdx.x;
@@ -47,6 +48,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
 
   for (int i = tid; i < 6 * ch; i += HEAD_THREADS) s_wp[i / ch][i % ch] = p.w_planes[i];
   if (tid < 6) s_bp[tid] = p.b_planes[tid];
+  pdl_wait();   // g and mask come from the previous kernels
   for (int r = tid; r < POS_ROWS; r += HEAD_THREADS) s_mask[r] = p.mask[(size_t)pos * POS_ROWS + r];
   // g tile: [ch/8 planes][400 rows][8] -> smem fp32 [row][ch]; 16-byte row-consecutive loads
   const int n_chunks = ch / 8;
@@ -200,8 +202,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
 cudaError_t launch_heads(const HeadParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   if (p.ch > HEAD_MAX_CH || p.ch % 8 != 0 || p.cv > HEAD_MAX_CV) return cudaErrorInvalidValue;
-  heads_kernel<<<p.n, HEAD_THREADS, 0, stream>>>(p);
-  return cudaGetLastError();
+  return launch_kernel(heads_kernel, dim3(p.n), dim3(HEAD_THREADS), 0, stream, p.pdl != 0, p);
 }
 
 }  // namespace maru

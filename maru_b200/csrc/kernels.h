@@ -34,6 +34,7 @@ struct ConvParams {
   int cout_total;
   int relu;
   int stages;                // pipeline depth (filled by the launcher from the smem budget)
+  int pdl;                   // launch with programmatic dependent launch (see common.cuh)
   const int* n_dev;          // optional: number of positions read on the device (graph replay with
                              // a smaller batch than the one captured); overrides m_rows
 };
@@ -68,6 +69,8 @@ struct AttnParams {
   int channels;              // C
   int head_dim;              // 32 or 64
   const int* n_dev;
+  int pdl;
+  int dbg;                   // bit0: swap LBO/SBO of the MN-major V descriptor, bit1: legacy mma.sync kernel
 };
 cudaError_t configure_attention();
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
@@ -89,6 +92,7 @@ struct HeadParams {
   int ch;                    // head channels (32)
   int cv;                    // value channels (<= 128)
   const int* n_dev;
+  int pdl;
 };
 cudaError_t launch_heads(const HeadParams& p, cudaStream_t stream);
 

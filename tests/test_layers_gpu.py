@@ -52,6 +52,16 @@ def test_every_stage_matches_port(built_lib, model_dir, name):
             ev.debug_set(1, 0)
             pytest.fail(f'stem mismatch err={report[0]} ; descriptor probe (bit0 swap A, bit1 swap B): {probe}')
         report, out, logits = run_stages(ev, arch, T, rows)
+        core = [r for r in report if r[0].endswith('.core')]
+        if core and core[0][1] > 0.05 * core[0][2] + 0.02:
+            # bring-up aid for the tcgen05 attention: which reading of the MN-major V descriptor?
+            probe = {}
+            for bits in (4,):
+                ev.debug_set(1, bits)
+                rep2 = run_stages(ev, arch, T, rows)[0]
+                probe[bits] = [r for r in rep2 if r[0].endswith('.core')][0]
+            ev.debug_set(1, 0)
+            pytest.fail(f'attention core mismatch {core[0]}; probe (4: legacy mma.sync kernel): {probe}')
         lines = [f'{n:18s} err={e:.4f} scale={s:.3f}' for n, e, s in report]
         print('\n'.join(lines))
         bad = [(n, e, s) for n, e, s in report if e > 0.02 * s + 0.02]
