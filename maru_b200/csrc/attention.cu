@@ -202,32 +202,37 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 // =============================================================================================
 // v2: tcgen05 / TMEM attention for head_dim 32.
 //
-// One CTA = (position, head), two CTAs co-resident per SM (256 TMEM columns and ~103 KB smem each)
-// so that one CTA's MMAs overlap the other's exponentials.  Per 128-query tile and per key part
-// (400 padded keys = 144 + 128 + 128):
-//     S  = Q K^T          tcgen05.mma  M=128, N=part, K=32   (Q, K: K-major chunk-planar images)
-//     P  = exp2(S - c_i)  4 softmax warps, one TMEM lane (= query row) per thread, bf16 to smem
-//     O += P [V | 1]      tcgen05.mma  M=128, N=48,   K=part (V read as an MN-major B operand; the
+// One CTA = (position, head), two CTAs co-resident per SM (256 TMEM columns, ~113 KB smem each).
+// The 4 query tiles x 5 key parts (400 padded keys = 5 x 80) form one linear sequence of 20 steps:
+//     S  = Q K^T          tcgen05.mma  M=128, N=80, K=32    (Q, K: K-major chunk-planar images)
+//     P  = exp2(S - c_i)  one TMEM lane (= query row) per thread, bf16 to shared memory
+//     O += P [V | 1]      tcgen05.mma  M=128, N=48, K=80    (V read as an MN-major B operand; the
 //                         extra "ones" column, zero for masked keys, yields the row sums l_i)
+// S, P and O are double buffered (TMEM: 2x80 + 2x48 columns): two softmax warp groups alternate
+// steps, the control warp keeps the tensor pipe two steps ahead, and the O / l epilogue of a tile
+// runs while the next tile is already in flight.
 // c_i = min(|q_i| * max_j |k_j|, 96) >= max_j S_ij (Cauchy-Schwarz) replaces the running row max:
 // softmax is shift invariant, p <= 1 cannot overflow, and because V rows and the ones column of
-// off-board keys are zero the key mask costs nothing in the inner loop and the key parts are
-// independent (no online rescaling of O).  Final O_i / l_i in the epilogue.
+// off-board keys are zero, the key mask costs nothing in the inner loop and the key parts are
+// independent (no online rescaling of O).
 // Query tiles start at rows 0, 128, 256 and 272; in the last one only rows 384..399 are new.
 // =============================================================================================
-constexpr int A2_SM_WARPS = 8;              // warps 0..7 softmax/epilogue: lane group = w & 3, column half = w >> 2
+constexpr int A2_SM_WARPS = 8;              // warps 0..7 softmax/epilogue: lane group = w & 3, group = w >> 2
 constexpr int A2_WARPS = A2_SM_WARPS + 1;   // warp 8: control (bulk loads + MMA issue)
 constexpr int A2_THREADS = A2_WARPS * 32;
 constexpr int A2_D = 32, A2_DCH = 4;
 constexpr int A2_PLANE = POS_ROWS * 16;     // 6400 B: one 8-channel plane of one position
 constexpr int A2_K_BYTES = A2_DCH * A2_PLANE;
 constexpr int A2_V_BYTES = (A2_DCH + 1) * A2_PLANE;   // + ones plane; the 6th plane aliases P (unused cols)
-constexpr int A2_PMAX = 144;
-constexpr int A2_P_BYTES = (A2_PMAX / 8) * TILE_M * 16;
+constexpr int A2_PN = 80;                   // keys per step
+constexpr int A2_NP = POS_ROWS / A2_PN;     // 5 parts
+constexpr int A2_NT = 4;                    // query tiles
+constexpr int A2_STEPS = A2_NT * A2_NP;
+constexpr int A2_P_BYTES = (A2_PN / 8) * TILE_M * 16; // 20 480 per buffer
 constexpr int A2_Q_BYTES = A2_DCH * TILE_M * 16;
-constexpr int A2_SMEM = A2_K_BYTES + A2_V_BYTES + A2_P_BYTES + 2 * A2_Q_BYTES + 512 + 256 + 128;
+constexpr int A2_SMEM = A2_K_BYTES + A2_V_BYTES + 2 * A2_P_BYTES + 2 * A2_Q_BYTES + 416 + 32 + 112;
 constexpr int A2_TMEM_COLS = 256;
-constexpr int A2_O_COL = 160;
+constexpr int A2_O_COL = 2 * A2_PN;         // O buffers at columns 160 and 208
 constexpr int A2_NV = 48;                   // V columns (32) + ones + padding to a multiple of 16
 
 // 16 S columns -> 16 probabilities -> two 16-byte P chunks of this row
@@ -242,41 +247,23 @@ __device__ __forceinline__ void exp_store16(const uint32_t* v, float c, uint8_t*
     *reinterpret_cast<uint4*>(s_p + ((chunk + h) * TILE_M + trow) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
-// columns [C0, C0 + CN) of the S part: 32 columns in flight per tcgen05.wait::ld
-template <int C0, int CN>
-__device__ __forceinline__ void softmax_cols(uint32_t t_s, float c, uint8_t* s_p, int trow) {
-#pragma unroll
-  for (int c0 = 0; c0 + 32 <= CN; c0 += 32) {
-    uint32_t v[32];
-    tmem_ld32(t_s + C0 + c0, v);
-    tmem_ld_wait();
-    exp_store16(v, c, s_p, (C0 + c0) / 8, trow);
-    exp_store16(v + 16, c, s_p, (C0 + c0) / 8 + 2, trow);
-  }
-  if (CN % 32) {
-    uint32_t v[16];
-    tmem_ld16(t_s + C0 + CN - 16, v);
-    tmem_ld_wait();
-    exp_store16(v, c, s_p, (C0 + CN - 16) / 8, trow);
-  }
-}
 
 __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnParams p) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint8_t* s_k = smem;
   uint8_t* s_v = s_k + A2_K_BYTES;
-  uint8_t* s_p = s_v + A2_V_BYTES;
-  uint8_t* s_q = s_p + A2_P_BYTES;                       // two Q tile buffers
-  uint8_t* s_mask = s_q + 2 * A2_Q_BYTES;                // [400] (+pad)
-  float* s_red = reinterpret_cast<float*>(s_mask + 512); // [8]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 512 + 256);
+  uint8_t* s_p = s_v + A2_V_BYTES;                       // two P buffers
+  uint8_t* s_q = s_p + 2 * A2_P_BYTES;                   // two Q tile buffers
+  uint8_t* s_mask = s_q + 2 * A2_Q_BYTES;                // [400] (+pad to 416)
+  float* s_red = reinterpret_cast<float*>(s_mask + 416); // [8]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_mask + 416 + 32);
   uint64_t* kv_full = bars;
   uint64_t* q_full = bars + 1;      // [2]
-  uint64_t* s_full = bars + 3;
-  uint64_t* p_full = bars + 4;
-  uint64_t* o_full = bars + 5;
-  uint64_t* o_empty = bars + 6;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* s_full = bars + 3;      // [2]
+  uint64_t* p_full = bars + 5;      // [2]
+  uint64_t* o_full = bars + 7;      // [2]
+  uint64_t* o_empty = bars + 9;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   pdl_launch_dependents();
   const int heads = p.channels / A2_D;
@@ -287,16 +274,16 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
   const size_t prow0 = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS;
   const int cch = p.channels / 8;
   const int q_chunk0 = head * A2_DCH, k_chunk0 = cch + head * A2_DCH, v_chunk0 = 2 * cch + head * A2_DCH;
-  constexpr int N_TILES = 4;
 
   if (threadIdx.x == 0) {
     mbar_init(kv_full, 1);
-    mbar_init(&q_full[0], 1);
-    mbar_init(&q_full[1], 1);
-    mbar_init(s_full, 1);
-    mbar_init(p_full, A2_SM_WARPS);
-    mbar_init(o_full, 1);
-    mbar_init(o_empty, A2_SM_WARPS);
+    for (int i = 0; i < 2; i++) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_empty[i], A2_SM_WARPS);
+    }
     fence_mbar_init();
   }
   if (warp == A2_SM_WARPS) {
@@ -311,7 +298,8 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
 
   if (warp == A2_SM_WARPS) {
     // =========================== control warp: bulk loads + MMA issue ===========================
-    auto load_q = [&](int tile, int buf) {
+    auto load_q = [&](int tile) {
+      const int buf = tile & 1;
       const int r0 = (tile == 3) ? 272 : tile * TILE_M;
       mbar_expect_tx(&q_full[buf], A2_Q_BYTES);
       for (int c = 0; c < A2_DCH; c++)
@@ -324,9 +312,11 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         bulk_load_1d(s_k + c * A2_PLANE, p.qkv + ((size_t)(k_chunk0 + c) * p.rows_alloc + prow0) * 8, A2_PLANE, kv_full);
         bulk_load_1d(s_v + c * A2_PLANE, p.qkv + ((size_t)(v_chunk0 + c) * p.rows_alloc + prow0) * 8, A2_PLANE, kv_full);
       }
-      load_q(0, 0);
+      load_q(0);
+      load_q(1);
     }
     __syncwarp();
+    constexpr uint32_t idesc_qk = umma_idesc_bf16(TILE_M, A2_PN, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(TILE_M, A2_NV, 0, 1);   // B = V is MN-major
     const uint64_t q_d = umma_desc(0, TILE_M * 16, 128);      // Q, P tiles: K-major, LBO = 128 rows
     const uint64_t k_d = umma_desc(0, A2_PLANE, 128);         // K image:    K-major, LBO = plane
@@ -337,51 +327,53 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     const uint32_t k_lo = (uint32_t)k_d + (smem_u32(s_k) >> 4);
     const uint32_t v_lo = (uint32_t)v_d + (smem_u32(s_v) >> 4);
     const uint32_t p_lo = (uint32_t)q_d + (smem_u32(s_p) >> 4);
-    const uint32_t t_s = tmem_base, t_o = tmem_base + A2_O_COL;
+    const uint32_t q_lo = (uint32_t)q_d + (smem_u32(s_q) >> 4);
     mbar_wait(kv_full, 0);
-    uint32_t ph_p = 0, ph_oe = 0;
-    for (int tile = 0; tile < N_TILES; tile++) {
-      const int buf = tile & 1;
-      // the other Q buffer was last read by tile-1, whose MMAs completed before its last p_full
-      if (tile + 1 < N_TILES && elect_one()) load_q(tile + 1, buf ^ 1);
-      __syncwarp();
-      mbar_wait(&q_full[buf], (tile >> 1) & 1);
+
+    // S[step & 1] = Q(tile) K(part)^T ; the first QK of a tile waits for its Q buffer
+    auto issue_qk = [&](int step) {
+      const int tile = step / A2_NP, part = step - tile * A2_NP;
+      if (part == 0) mbar_wait(&q_full[tile & 1], (tile >> 1) & 1);
       tc_fence_after();
-      const uint32_t qt_lo = (uint32_t)q_d + (smem_u32(s_q + buf * A2_Q_BYTES) >> 4);
-#pragma unroll
-      for (int part = 0; part < 3; part++) {
-        const int key0 = part == 0 ? 0 : (part == 1 ? 144 : 272);
-        const int pn = part == 0 ? 144 : 128;
-        if (elect_one()) {
-          // S = Q K^T over this key part (2 k16 steps)
-          const uint32_t idesc_qk = umma_idesc_bf16(TILE_M, pn, 0, 0);
-          umma_bf16_lohi<0>(t_s, qt_lo, q_hi, k_lo + key0, k_hi, idesc_qk);
-          umma_bf16_lohi<1>(t_s, qt_lo + 2 * TILE_M, q_hi, k_lo + key0 + 2 * POS_ROWS, k_hi, idesc_qk);
-          umma_commit(s_full);
-        }
-        __syncwarp();
-        mbar_wait(p_full, ph_p);           // softmax done: S consumed, P written (and fenced)
-        ph_p ^= 1;
-        if (part == 0 && tile > 0) {       // previous tile's O has been read by the epilogue
-          mbar_wait(o_empty, ph_oe);
-          ph_oe ^= 1;
-        }
-        tc_fence_after();
-        if (elect_one()) {
-          for (int j = 0; j < pn / 16; j++) {
-            const uint32_t a = p_lo + 2 * j * TILE_M;
-            const uint32_t b = v_lo + key0 + 16 * j;
-            if (part == 0 && j == 0) umma_bf16_lohi<0>(t_o, a, q_hi, b, v_hi, idesc_pv);
-            else umma_bf16_lohi<1>(t_o, a, q_hi, b, v_hi, idesc_pv);
-          }
-          if (part == 2) umma_commit(o_full);
-        }
-        __syncwarp();
+      if (elect_one()) {
+        const uint32_t t_s = tmem_base + (step & 1) * A2_PN;
+        const uint32_t qa = q_lo + (tile & 1) * (A2_Q_BYTES >> 4);
+        const uint32_t kb = k_lo + part * A2_PN;
+        umma_bf16_lohi<0>(t_s, qa, q_hi, kb, k_hi, idesc_qk);
+        umma_bf16_lohi<1>(t_s, qa + 2 * TILE_M, q_hi, kb + 2 * POS_ROWS, k_hi, idesc_qk);
+        umma_commit(&s_full[step & 1]);
       }
+      __syncwarp();
+    };
+    issue_qk(0);
+    issue_qk(1);
+#pragma unroll 1
+    for (int step = 0; step < A2_STEPS; step++) {
+      const int tile = step / A2_NP, part = step - tile * A2_NP;
+      const int sb = step & 1, ob = tile & 1;
+      mbar_wait(&p_full[sb], (step >> 1) & 1);     // P[sb] written (and fenced), S[sb] consumed
+      if (part == 0 && tile >= 2) mbar_wait(&o_empty[ob], 0);   // epilogue of tile-2 has read O[ob]
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t t_o = tmem_base + A2_O_COL + ob * A2_NV;
+        const uint32_t pa = p_lo + sb * (A2_P_BYTES >> 4);
+        const uint32_t vb = v_lo + part * A2_PN;
+        if (part == 0) umma_bf16_lohi<0>(t_o, pa, q_hi, vb, v_hi, idesc_pv);
+        else umma_bf16_lohi<1>(t_o, pa, q_hi, vb, v_hi, idesc_pv);
+#pragma unroll
+        for (int j = 1; j < A2_PN / 16; j++)
+          umma_bf16_lohi<1>(t_o, pa + 2 * j * TILE_M, q_hi, vb + 16 * j, v_hi, idesc_pv);
+        if (part == A2_NP - 1) umma_commit(&o_full[ob]);
+      }
+      __syncwarp();
+      // the last QK of this tile completed before p_full(step): its Q buffer can take tile+2
+      if (part == A2_NP - 1 && tile + 2 < A2_NT && elect_one()) load_q(tile + 2);
+      __syncwarp();
+      if (step + 2 < A2_STEPS) issue_qk(step + 2);
     }
   } else {
     // =========================== softmax + epilogue warps ===========================
-    const int lg = warp & 3, half = warp >> 2;
+    const int lg = warp & 3, grp = warp >> 2;               // grp g handles steps s with (s & 1) == g
     const int trow = lg * 32 + lane;                        // TMEM lane = row within the tile
     const int st = threadIdx.x;                             // 0..255
     for (int r = st; r < POS_ROWS; r += 256) s_mask[r] = p.mask[(size_t)pos * POS_ROWS + r];
@@ -390,6 +382,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     for (int r = st; r < POS_ROWS; r += 256)
       *reinterpret_cast<uint4*>(s_v + A2_DCH * A2_PLANE + r * 16) =
           make_uint4(s_mask[r] ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    fence_async_smem();
     mbar_wait(kv_full, 0);
     // max_j |k_j|^2
     float mk = 0.0f;
@@ -413,56 +406,20 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
 #pragma unroll
     for (int w = 1; w < A2_SM_WARPS; w++) maxk2 = fmaxf(maxk2, s_red[w]);
     const uint32_t t_lane = tmem_base + ((uint32_t)(lg * 32) << 16);
-    uint32_t ph_s = 0, ph_o = 0;
-    for (int tile = 0; tile < N_TILES; tile++) {
-      const int buf = tile & 1;
-      const int r0 = (tile == 3) ? 272 : tile * TILE_M;
-      const int row = r0 + trow;
-      const bool active = (tile < 3) || (lg == 3);          // tile 3: only rows 384..399 are new
-      float c = 0.0f;
-      if (active) {
-        mbar_wait(&q_full[buf], (tile >> 1) & 1);
-        float ss = 0.0f;
-#pragma unroll
-        for (int ch = 0; ch < A2_DCH; ch++) {
-          const uint4 u = *reinterpret_cast<const uint4*>(s_q + buf * A2_Q_BYTES + (ch * TILE_M + trow) * 16);
-          const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
-                              bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
-#pragma unroll
-          for (int e = 0; e < 8; e++) ss = fmaf(f[e], f[e], ss);
-        }
-        c = fminf(sqrtf(ss * maxk2) * 1.0001f + 1e-3f, 96.0f);
-      }
-#pragma unroll
-      for (int part = 0; part < 3; part++) {
-        mbar_wait(s_full, ph_s);
-        ph_s ^= 1;
-        tc_fence_after();
-        if (active) {
-          if (part == 0) {
-            if (half == 0) softmax_cols<0, 80>(t_lane, c, s_p, trow);
-            else softmax_cols<80, 64>(t_lane, c, s_p, trow);
-          } else {
-            if (half == 0) softmax_cols<0, 64>(t_lane, c, s_p, trow);
-            else softmax_cols<64, 64>(t_lane, c, s_p, trow);
-          }
-        }
-        fence_async_smem();     // P (and, first time, the ones plane) visible to the async proxy
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_full);
-      }
-      // ---- epilogue of the tile: O / l, query mask, store (each half-warp owns 16 channels)
-      mbar_wait(o_full, ph_o);
-      ph_o ^= 1;
+
+    // O / l, query mask, store; both groups take part, each owns 16 of the head's 32 channels
+    auto epilogue = [&](int tile) {
+      const int ob = tile & 1;
+      const int row = ((tile == 3) ? 272 : tile * TILE_M) + trow;
+      mbar_wait(&o_full[ob], (tile >> 1) & 1);
       tc_fence_after();
       uint32_t o[16];
-      tmem_ld16(t_lane + A2_O_COL + half * 16, o);
-      const uint32_t lbits = tmem_ld1(t_lane + A2_O_COL + 32);
+      tmem_ld16(t_lane + A2_O_COL + ob * A2_NV + grp * 16, o);
+      const uint32_t lbits = tmem_ld1(t_lane + A2_O_COL + ob * A2_NV + 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(o_empty);
+      if (lane == 0) mbar_arrive(&o_empty[ob]);
       const bool write = (tile < 3) ? true : (row >= 384);
       if (write) {
         const bool on = s_mask[row] != 0;
@@ -474,9 +431,66 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
           w.y = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 2]) * inv, __uint_as_float(o[ch * 8 + 3]) * inv) : 0u;
           w.z = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 4]) * inv, __uint_as_float(o[ch * 8 + 5]) * inv) : 0u;
           w.w = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 6]) * inv, __uint_as_float(o[ch * 8 + 7]) * inv) : 0u;
-          *reinterpret_cast<uint4*>(p.out + ((size_t)(q_chunk0 + half * 2 + ch) * p.rows_alloc + prow0 + row) * 8) = w;
+          *reinterpret_cast<uint4*>(p.out + ((size_t)(q_chunk0 + grp * 2 + ch) * p.rows_alloc + prow0 + row) * 8) = w;
         }
       }
+    };
+
+    float c = 0.0f;
+    int c_tile = -1, epi_done = 0;
+#pragma unroll 1
+    for (int step = grp; step < A2_STEPS; step += 2) {
+      const int tile = step / A2_NP;
+      const int buf = tile & 1;
+      const bool active = (tile < 3) || (lg == 3);          // tile 3: only rows 384..399 are new
+      if (tile != c_tile) {                                 // new tile: shift c_i of this row
+        c_tile = tile;
+        if (active) {
+          mbar_wait(&q_full[buf], (tile >> 1) & 1);
+          float ss = 0.0f;
+#pragma unroll
+          for (int ch = 0; ch < A2_DCH; ch++) {
+            const uint4 u = *reinterpret_cast<const uint4*>(s_q + buf * A2_Q_BYTES + (ch * TILE_M + trow) * 16);
+            const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
+                                bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
+#pragma unroll
+            for (int e = 0; e < 8; e++) ss = fmaf(f[e], f[e], ss);
+          }
+          c = fminf(sqrtf(ss * maxk2) * 1.0001f + 1e-3f, 96.0f);
+        }
+      }
+      mbar_wait(&s_full[grp], (step >> 1) & 1);
+      tc_fence_after();
+      // s_full(step) was committed after PV(step-2) and, for step >= 5*tile+1, after the last PV of
+      // the previous tile: its O is complete, the epilogue does not stall
+      if (active) {
+        const uint32_t t_s = t_lane + grp * A2_PN;
+        uint8_t* pb = s_p + grp * A2_P_BYTES;
+        uint32_t v[32];
+        tmem_ld32(t_s, v);
+        tmem_ld_wait();
+        exp_store16(v, c, pb, 0, trow);
+        exp_store16(v + 16, c, pb, 2, trow);
+        tmem_ld32(t_s + 32, v);
+        tmem_ld_wait();
+        exp_store16(v, c, pb, 4, trow);
+        exp_store16(v + 16, c, pb, 6, trow);
+        tmem_ld16(t_s + 64, v);
+        tmem_ld_wait();
+        exp_store16(v, c, pb, 8, trow);
+      }
+      fence_async_smem();     // P visible to the async proxy
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&p_full[grp]);
+      if (epi_done < tile && step >= tile * A2_NP + 1) {
+        epilogue(epi_done);
+        epi_done++;
+      }
+    }
+    while (epi_done < A2_NT) {
+      epilogue(epi_done);
+      epi_done++;
     }
   }
   tc_fence_before();
