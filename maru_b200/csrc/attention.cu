@@ -466,18 +466,20 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       if (active) {
         const uint32_t t_s = t_lane + grp * A2_PN;
         uint8_t* pb = s_p + grp * A2_P_BYTES;
-        uint32_t v[32];
-        tmem_ld32(t_s, v);
+        // software pipelined: the next tcgen05.ld is in flight while this block's exps run
+        // (a tcgen05.ld + wait round trip is ~170 cycles, profiles/r1_tmem_microbench.txt)
+        uint32_t va[32], vb[32];
+        tmem_ld32(t_s, va);
         tmem_ld_wait();
-        exp_store16(v, c, pb, 0, trow);
-        exp_store16(v + 16, c, pb, 2, trow);
-        tmem_ld32(t_s + 32, v);
+        tmem_ld32(t_s + 32, vb);
+        exp_store16(va, c, pb, 0, trow);
+        exp_store16(va + 16, c, pb, 2, trow);
         tmem_ld_wait();
-        exp_store16(v, c, pb, 4, trow);
-        exp_store16(v + 16, c, pb, 6, trow);
-        tmem_ld16(t_s + 64, v);
+        tmem_ld16(t_s + 64, va);
+        exp_store16(vb, c, pb, 4, trow);
+        exp_store16(vb + 16, c, pb, 6, trow);
         tmem_ld_wait();
-        exp_store16(v, c, pb, 8, trow);
+        exp_store16(va, c, pb, 8, trow);
       }
       fence_async_smem();     // P visible to the async proxy
       tc_fence_before();
