@@ -295,12 +295,16 @@ def run_b200(args):
                 a['ms'] += l['ms']; a['flops'] += l['flops']; a['bytes'] += l['bytes']; a['launches'] += 1
 
     # ---------------- reduce over ranks ----------------------------------------------------------
-    t = torch.tensor([dev_ms, e2e_s, e2e_planes_s, t_wall], dtype=torch.float64, device=dev)
+    from maru_b200 import shard
+    agg = shard.reduce_stats(shard.RankStats(positions=B * args.steps, batches=args.steps,
+                                             device_ms=dev_ms, wall_s=t_wall), dist, dev)
+    t = torch.tensor([e2e_s, e2e_planes_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_s, e2e_planes_s, t_wall = [float(x) for x in t.tolist()]
-    total = world * B * args.steps
-    value = total / (dev_ms / 1e3)
+    e2e_s, e2e_planes_s = [float(x) for x in t.tolist()]
+    dev_ms, t_wall = agg['device_ms'], agg['wall_s']
+    total = agg['positions']                      # all ranks' positions / the slowest rank's time
+    value = shard.evals_per_sec(agg)
 
     if rank == 0:
         peaks = load_peaks()
