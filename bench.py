@@ -322,8 +322,14 @@ def run_b200(args):
         dom_key = max((k for k in prof if k[0] == 1 and prof[k]['launches']), key=lambda k: prof[k]['ms'])
         dom = prof[dom_key]
         achieved = dom['flops'] / (dom['ms'] / 1e3) / 1e12
+        traffic = None
+        try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
+            cap = json.loads((ROOT / 'profiles' / 'r1_conv3x3_ncu_full.json').read_text())
+            traffic = cap['_traffic_bytes_per_launch']['blk0.in0.c1']
+        except Exception:
+            pass
         roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16_burst'], unit='TFLOP/s',
-                        frac=achieved / peaks['bf16_burst'], traffic=None,
+                        frac=achieved / peaks['bf16_burst'], traffic=traffic,
                         kernel=f'conv_gemm 3x3 {dom_key[1]}->{dom_key[2]} ({dom["launches"]} timed launches)',
                         peak_source=peaks['source'] + ' (burst, kernel timed alone)',
                         flops_per_launch=dom['flops'] / dom['launches'],
