@@ -85,8 +85,10 @@ def _bind_nn(lib) -> None:
 
 
 def load(kind: str = 'board'):
-    """kind: 'board' (no libtorch), 'nn' (reference libtorch runtime) or 'dropin' (reference search
-    and queue linked against the substitute deepgo::Model that calls libmaru_b200.so)."""
+    """kind: 'board' (no libtorch), 'nn' (reference libtorch runtime), 'dropin' (reference search
+    and queue linked against the substitute deepgo::Model that calls libmaru_b200.so) or
+    'dropin_states' (reference search + Evaluator.h with the substitute Processor / Evaluator.cpp
+    that send compact maru_state records)."""
     if kind in _libs:
         return _libs[kind]
     path = REF_DIR / f'libmaru_ref_{kind}.so'
@@ -94,7 +96,7 @@ def load(kind: str = 'board'):
         raise FileNotFoundError(f'{path} missing: run `make -C oracle ref` where /root/reference exists')
     if kind == 'nn':
         import torch  # noqa: F401  libtorch must be initialised by Python first
-    if kind == 'dropin':
+    if kind.startswith('dropin'):
         os.environ.setdefault('MARU_B200_LIB', str(HERE.parent / 'maru_b200' / 'lib' / 'libmaru_b200.so'))
     lib = C.CDLL(str(path), mode=C.RTLD_LOCAL)
     _bind_board(lib)

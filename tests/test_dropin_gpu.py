@@ -72,3 +72,39 @@ def test_reference_evaluator_and_search_over_b200_model(libs, built_lib, model_d
     assert 0 <= best['x'] < 9 and 0 <= best['y'] < 9
     pl.close()
     proc.close()
+
+
+def test_compact_record_dropin_matches_plane_dropin(libs, built_lib, model_dir):
+    """maru_b200/dropin/states: the reference search + Evaluator.h over the substitute Processor /
+    Evaluator.cpp (448-byte records, K1 on the GPU) must give exactly what the plane drop-in gives."""
+    from oracle import ref
+    if not ref.available('dropin_states'):
+        pytest.skip('oracle/_ref/libmaru_ref_dropin_states.so not present')
+    path = model_dir('b2c64')
+    pa = ref.RefProcessor(str(path), gpus=[0], batch_size=64, kind='dropin')
+    pb = ref.RefProcessor(str(path), gpus=[0], batch_size=64, kind='dropin_states')
+    for size, n_moves, seed in ((9, 25, 1), (13, 60, 2), (19, 120, 3), (19, 5, 4)):
+        boards = []
+        for kind in ('dropin', 'dropin_states'):
+            rng = np.random.default_rng(seed)
+            b = ref.RefBoard(size, size, kind=kind)
+            c = 1
+            for _ in range(n_moves):
+                i = int(rng.choice(np.flatnonzero(b.get_enableds(c, False))))
+                b.play(i % size, i // size, c)
+                c = -c
+            boards.append((b, c))
+        xa, ya, pa_, va = pa.evaluate(*boards[0])
+        xb, yb, pb_, vb = pb.evaluate(*boards[1])
+        assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+        assert np.array_equal(pa_, pb_) and va == vb          # same trunk input -> identical bits
+    pl = ref.RefPlayer(pb, threads=8, width=9, height=9)
+    pl.initialize()
+    cands = pl.evaluate(visits=100)
+    assert sum(cd['visits'] for cd in cands) >= 90
+    pl.close()
+    # plain rows still work through the substitute Processor::execute
+    rows, _ = load_positions('9')
+    assert np.array_equal(pb.execute(rows[:8]), pa.execute(rows[:8]))
+    pa.close()
+    pb.close()
