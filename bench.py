@@ -222,6 +222,8 @@ def run_b200(args):
 
     B = args.batch
     ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=B)
+    if os.environ.get('MARU_DBG_BITS'):
+        ev.debug_set(1, int(os.environ['MARU_DBG_BITS']))
     info = ev.info()
     stream = torch.cuda.ExternalStream(ev.stream(), device=dev)
     states = synth.random_states(B, args.board, seed=1234 + rank)

@@ -141,7 +141,11 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * mma.sync attention kernel instead of the tcgen05 one (A/B). */
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
+#define MARU_DBG_TRACE_LAUNCH 2       /* index of the trunk launch whose pipeline is traced (-1: off) */
 int  maru_eval_debug_set(maru_eval* e, int key, int value);
+/* clock64 stamps of the traced conv launch: [n_ctas][32 tiles][8] = producer {wait,issue}, MMA warp
+ * {wait start, operands ready, issued}, epilogue warp {wait start, accumulator ready, done}. */
+int  maru_eval_debug_trace(maru_eval* e, long long* out, int n_ctas);
 
 /* ---- per-launch timing (roofline evidence) --------------------------------------------------- */
 /* Per-launch timing of the forward of n positions (device-resident compact records): after one

@@ -190,11 +190,13 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
     const float inv0 = on0 ? 1.0f / l0 : 0.0f, inv1 = on1 ? 1.0f / l1 : 0.0f;
 #pragma unroll
     for (int i = 0; i < D / 8; i++) {
-      __nv_bfloat16* dst = p.out + ((size_t)(q_chunk0 + i) * p.rows_alloc + prow0 + r0) * 8;
-      *reinterpret_cast<uint32_t*>(dst + g * 8 + tq * 2) =
-          on0 ? pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0) : 0u;
-      *reinterpret_cast<uint32_t*>(dst + (g + 8) * 8 + tq * 2) =
-          on1 ? pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1) : 0u;
+      const int m0 = pos * POS_ROWS + r0 + g, m1 = m0 + 8;
+      const size_t off0 = p.out_blocked ? blocked_offset(cch, q_chunk0 + i, m0)
+                                        : ((size_t)(q_chunk0 + i) * p.rows_alloc + GUARD_ROWS + m0) * 8;
+      const size_t off1 = p.out_blocked ? blocked_offset(cch, q_chunk0 + i, m1)
+                                        : ((size_t)(q_chunk0 + i) * p.rows_alloc + GUARD_ROWS + m1) * 8;
+      *reinterpret_cast<uint32_t*>(p.out + off0 + tq * 2) = on0 ? pack_bf16x2(o[i][0] * inv0, o[i][1] * inv0) : 0u;
+      *reinterpret_cast<uint32_t*>(p.out + off1 + tq * 2) = on1 ? pack_bf16x2(o[i][2] * inv1, o[i][3] * inv1) : 0u;
     }
   }
 }
@@ -431,7 +433,10 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
           w.y = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 2]) * inv, __uint_as_float(o[ch * 8 + 3]) * inv) : 0u;
           w.z = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 4]) * inv, __uint_as_float(o[ch * 8 + 5]) * inv) : 0u;
           w.w = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 6]) * inv, __uint_as_float(o[ch * 8 + 7]) * inv) : 0u;
-          *reinterpret_cast<uint4*>(p.out + ((size_t)(q_chunk0 + grp * 2 + ch) * p.rows_alloc + prow0 + row) * 8) = w;
+          const int plane = q_chunk0 + grp * 2 + ch;
+          const size_t off = p.out_blocked ? blocked_offset(cch, plane, pos * POS_ROWS + row)
+                                           : ((size_t)plane * p.rows_alloc + prow0 + row) * 8;
+          *reinterpret_cast<uint4*>(p.out + off) = w;
         }
       }
     };

@@ -139,9 +139,9 @@ int maru_encode_planes_device(maru_eval* ev, const maru_state* d_s, float* d_row
 int maru_eval_debug_planes(maru_eval* ev, int which, float* out, int n, int channels) {
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
-  const __nv_bfloat16* bufs[7] = {e->x0, e->h, e->r, e->s, e->qkv, e->o, e->g};
-  const int chans[7] = {maru::STEM_CIN, e->C, e->C / 2, e->C / 2, 3 * e->C, e->C, e->Ch};
-  if (which < 0 || which > 6 || bufs[which] == nullptr || n > e->max_batch || channels > chans[which]) {
+  const maru::Act* acts[7] = {&e->x0, &e->h, &e->r, &e->s, &e->qkv, &e->o, &e->g};
+  if (which < 0 || which > 6 || acts[which]->p == nullptr || n > e->max_batch ||
+      channels > acts[which]->channels) {
     maru::set_error("maru_eval_debug_planes: bad argument");
     return 1;
   }
@@ -149,7 +149,8 @@ int maru_eval_debug_planes(maru_eval* ev, int which, float* out, int n, int chan
   float* d = nullptr;
   const size_t bytes = (size_t)n * channels * maru::CELLS * 4;
   CKC(cudaMalloc(&d, bytes));
-  cudaError_t le = maru::launch_planes_to_nchw(bufs[which], e->rows_alloc, channels, d, n, e->stream);
+  cudaError_t le = maru::launch_planes_to_nchw(acts[which]->p, e->rows_alloc, channels, acts[which]->channels,
+                                               acts[which]->blocked ? 1 : 0, d, n, e->stream);
   if (le == cudaSuccess) le = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, e->stream);
   if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
   cudaFree(d);
@@ -166,6 +167,17 @@ int maru_eval_profile_states(maru_eval* ev, const maru_state* d_states, float* d
   return E(ev)->profile_states(d_states, d_out, n, out, max_launches, n_launches);
 }
 
+int maru_eval_debug_trace(maru_eval* ev, long long* out, int n_ctas) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  if (n_ctas > 256) n_ctas = 256;
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(cudaStreamSynchronize(e->stream));
+  CKC(cudaMemcpy(out, e->d_trace, (size_t)n_ctas * maru::TRACE_TILES * maru::TRACE_SLOTS * 8,
+                 cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
@@ -174,6 +186,7 @@ int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   e->clear_graphs();
   if (key == MARU_DBG_STOP_AFTER) e->dbg_stop_after = value;
   else if (key == MARU_DBG_DESC_BITS) e->dbg_desc = value;
+  else if (key == MARU_DBG_TRACE_LAUNCH) e->dbg_trace_launch = value;
   else {
     maru::set_error("maru_eval_debug_set: unknown key");
     return 1;

@@ -30,6 +30,11 @@ constexpr int TILE_M = 128;                  // rows per MMA tile (UMMA M)
 __host__ __device__ inline int flat_row(int y, int x) { return (y + 1) * PITCH + x; }
 __host__ __device__ inline int total_rows(int n) { return n * POS_ROWS + TAIL_ROWS; }
 
+// element offset of (plane, row m) in a tile-blocked tensor with `planes` planes
+__host__ __device__ inline size_t blocked_offset(int planes, int plane, int m) {
+  return ((((size_t)(m / TILE_M)) * planes + plane) * TILE_M + (m % TILE_M)) * 8;
+}
+
 constexpr int IN_PLANES = 33;
 constexpr int IN_INFOS = 7;
 constexpr int IN_ROW = 11920;

@@ -16,17 +16,18 @@
 //   * the epilogue (one TMEM lane = one row per thread) reads residuals and writes outputs as
 //     16-byte row-consecutive accesses: a warp store is one contiguous 512-byte segment.
 //
-// Roles (320 threads, persistent over M tiles of 128 rows, 1 CTA per SM):
-//   warp 0   : producer  — weights once, then per tile one input slab + mask (+ the residual tile)
-//              into an mbarrier ring of up to 4 stages: the epilogue never waits on a global load
-//   warp 1   : TMEM alloc + elected-lane tcgen05.mma issue (bias and residual are MMAs too),
-//              accumulators double-buffered in TMEM
-//   warps 2-9: epilogue  — tcgen05.ld, bf16 pack, packed ReLU, mask select, 16-byte stores
+// Roles (352 threads, persistent over M tiles of 128 rows, 1 CTA per SM):
+//   warp 0    : producer  — weights once (one bulk copy), then per tile the input slab, the mask and
+//               (if any) the residual tile into an mbarrier ring of <= 4 stages: one bulk copy per
+//               8-channel plane for chunk-planar tensors, ONE copy for tile-blocked tensors
+//   warps 1,10: elected-lane tcgen05.mma issue, alternating tiles / TMEM accumulators (bias and
+//               residual are MMAs too); warp 1 also owns the TMEM allocation
+//   warps 2-9 : epilogue  — tcgen05.ld, bf16 pack, packed ReLU, mask select, 16-byte stores
 #include "kernels.h"
 
 namespace maru {
 
-constexpr int CONV_THREADS = 320;  // warp 0 producer, warp 1 MMA, warps 2..9 epilogue
+constexpr int CONV_THREADS = 352;  // warp 0 producer, warps 1 and 10 MMA issue, warps 2..9 epilogue
 
 template <int CIN, int NT, int TAPS>
 struct ConvCfg {
@@ -44,7 +45,7 @@ struct ConvCfg {
   static constexpr int BAR_BYTES = 128;
   static constexpr int SMEM_LIMIT = 232448;                    // 227 KB per CTA
   static int fixed_bytes(bool has_res) {
-    return W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + 16 + (has_res ? IDENT_BYTES : 0);
+    return W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + (has_res ? IDENT_BYTES : 0);
   }
   // a stage = input slab + mask (+ residual tile when the layer has one); as many as fit, <= 4
   static int stage_bytes(bool has_res) { return SLAB_BYTES + MASK_BYTES + (has_res ? RES_BYTES : 0); }
@@ -57,7 +58,7 @@ struct ConvCfg {
                                    : (2 * NT <= 256) ? 256 : 512;
   static_assert(CIN % 16 == 0 && NT % 32 == 0 && NT >= 32 && NT <= 256, "UMMA shape");
   static_assert(TAPS == 1 || LEAD >= HALO, "slab lead must cover the 3x3 halo");
-  static_assert(W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + 16 + SLAB_BYTES + MASK_BYTES <= SMEM_LIMIT,
+  static_assert(W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + SLAB_BYTES + MASK_BYTES <= SMEM_LIMIT,
                 "one stage must fit");
 };
 
@@ -69,7 +70,7 @@ struct ConvCfg {
 template <int CIN, int NT, int TAPS>
 __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvParams p) {
   using Cfg = ConvCfg<CIN, NT, TAPS>;
-  extern __shared__ __align__(128) uint8_t smem[];
+  extern __shared__ __align__(1024) uint8_t smem[];
   constexpr int MAXS = Cfg::MAX_STAGES;
   const bool has_res = p.res != nullptr;
   const int STAGES = p.stages;
@@ -78,14 +79,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   uint8_t* s_ones = s_w + Cfg::W_BYTES;
   uint8_t* s_biasb = s_ones + Cfg::ONES_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_biasb + Cfg::BIASB_BYTES);
-  uint8_t* s_ident = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES + 16;
+  uint8_t* s_ident = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES;   // keeps stages 128-B aligned (TMA)
   uint8_t* s_stage = s_ident + (has_res ? Cfg::IDENT_BYTES : 0);
   uint64_t* full = bars;                   // [MAXS] input slab + mask (+ residual tile) landed
   uint64_t* empty = bars + MAXS;           // [MAXS] stage reusable
   uint64_t* tfull = bars + 2 * MAXS;       // [2] accumulator ready
   uint64_t* tempty = tfull + 2;            // [2] accumulator drained
   uint64_t* wbar = tempty + 2;             // weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);   // inside the 128-byte barrier block
 
   pdl_launch_dependents();                      // let the next layer's CTAs start their prologue
   const int warp = threadIdx.x >> 5;
@@ -152,34 +153,53 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
     if (elect_one()) {
       // weights of this group: [TAPS][KCH][cout_total][8] in HBM -> [TAPS][KCH][NT][8] in smem
       mbar_expect_tx(wbar, Cfg::W_BYTES);
-      for (int tc = 0; tc < TAPS * Cfg::KCH; tc++) {
-        const __nv_bfloat16* src = p.w + ((size_t)tc * p.cout_total + (size_t)group * NT) * 8;
-        bulk_load_1d(s_w + (size_t)tc * NT * 16, src, NT * 16, wbar);
+      if (p.cout_total == NT) {
+        bulk_load_1d(s_w, p.w, Cfg::W_BYTES, wbar);          // whole image is contiguous: one request
+      } else {
+        for (int tc = 0; tc < TAPS * Cfg::KCH; tc++) {
+          const __nv_bfloat16* src = p.w + ((size_t)tc * p.cout_total + (size_t)group * NT) * 8;
+          bulk_load_1d(s_w + (size_t)tc * NT * 16, src, NT * 16, wbar);
+        }
       }
     }
     __syncwarp();
     pdl_wait();   // everything below reads what the previous kernel wrote (activations, mask)
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    int tix = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tix++) {
+      long long* tr = (p.trace && blockIdx.y == 0 && tix < TRACE_TILES)
+                          ? p.trace + ((size_t)blockIdx.x * TRACE_TILES + tix) * TRACE_SLOTS : nullptr;
+      if (tr && lane == 0) tr[0] = clock64();
       mbar_wait(&empty[stage], phase ^ 1);
+      if (tr && lane == 0) tr[1] = clock64();
       if (elect_one()) {
         mbar_expect_tx(&full[stage], STAGE_BYTES);
         const size_t row0 = (size_t)GUARD_ROWS + (size_t)tile * TILE_M;
         uint8_t* dst = s_stage + stage * STAGE_BYTES;
+        if (TAPS == 1 && p.in_blocked) {
+          // tile-blocked input: the whole [KCH][128][16 B] slab is contiguous
+          bulk_load_1d(dst, p.in + ((size_t)tile * p.in_planes + p.in_chunk0) * (TILE_M * 8), Cfg::SLAB_BYTES,
+                       &full[stage]);
+        } else {
 #pragma unroll 1
-        for (int c = 0; c < Cfg::KCH; c++) {
-          const __nv_bfloat16* src = p.in + ((size_t)(p.in_chunk0 + c) * p.rows_alloc + row0 - Cfg::LEAD) * 8;
-          bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, &full[stage]);
+          for (int c = 0; c < Cfg::KCH; c++) {
+            const __nv_bfloat16* src = p.in + ((size_t)(p.in_chunk0 + c) * p.rows_alloc + row0 - Cfg::LEAD) * 8;
+            bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, &full[stage]);
+          }
         }
         bulk_load_1d(dst + Cfg::SLAB_BYTES, p.mask + (size_t)tile * TILE_M, Cfg::MASK_BYTES, &full[stage]);
         if (has_res) {
-#pragma unroll 1
-          for (int c = 0; c < NT / 8; c++) {
-            const __nv_bfloat16* src =
-                p.res + ((size_t)(p.res_chunk0 + group * (NT / 8) + c) * p.rows_alloc + row0) * 8;
-            bulk_load_1d(dst + Cfg::SLAB_BYTES + Cfg::MASK_BYTES + c * TILE_M * 16, src, TILE_M * 16,
+          uint8_t* rdst = dst + Cfg::SLAB_BYTES + Cfg::MASK_BYTES;
+          const int rc0 = p.res_chunk0 + group * (NT / 8);
+          if (p.res_blocked) {
+            bulk_load_1d(rdst, p.res + ((size_t)tile * p.res_planes + rc0) * (TILE_M * 8), Cfg::RES_BYTES,
                          &full[stage]);
+          } else {
+#pragma unroll 1
+            for (int c = 0; c < NT / 8; c++)
+              bulk_load_1d(rdst + c * TILE_M * 16, p.res + ((size_t)(rc0 + c) * p.rows_alloc + row0) * 8,
+                           TILE_M * 16, &full[stage]);
           }
         }
       }
@@ -189,8 +209,11 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
         phase ^= 1;
       }
     }
-  } else if (warp == 1) {
-    // =========================== MMA issuer ===========================
+  } else if (warp == 1 || warp == 10) {
+    // =========================== MMA issuers ===========================
+    // Two warps alternate tiles (and TMEM accumulators): the ~270 cycles of mbarrier polling before a
+    // tile and the blocking issue of its 37 MMAs (tools/trace_conv.py) overlap across the two.
+    const int mw = (warp == 1) ? 0 : 1;
     constexpr uint32_t idesc = umma_idesc_bf16(TILE_M, NT, 0, 0);
     // descriptors differ only in the 14-bit start-address field (smem < 256 KB: no carry)
     const uint64_t a_d = umma_desc(0, Cfg::SLAB_ROWS * 16, 128);   // slab:      LBO = slab plane
@@ -202,14 +225,17 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
     const uint32_t biasb_lo = (uint32_t)b_d + (smem_u32(s_biasb) >> 4);
     const uint32_t ident_lo = (uint32_t)b_d + (smem_u32(s_ident) >> 4);
     mbar_wait(wbar, 0);
-    int stage = 0;
-    uint32_t phase = 0;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
-      const int acc = it & 1;
+    for (int it = mw, tile = blockIdx.x + mw * gridDim.x; tile < n_tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = it & 1;                       // == mw
       const uint32_t acc_phase = (it >> 1) & 1;
+      const int stage = it % STAGES;
+      const uint32_t phase = (it / STAGES) & 1;
+      long long* tr = (p.trace && blockIdx.y == 0 && it < TRACE_TILES)
+                          ? p.trace + ((size_t)blockIdx.x * TRACE_TILES + it) * TRACE_SLOTS : nullptr;
+      if (tr && lane == 0) tr[2] = clock64();
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       mbar_wait(&full[stage], phase);
+      if (tr && lane == 0) tr[3] = clock64();
       tc_fence_after();
       if (elect_one()) {
         const uint32_t st_addr = smem_u32(s_stage + stage * STAGE_BYTES);
@@ -236,10 +262,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
         umma_commit(&tfull[acc]);    // accumulator complete
       }
       __syncwarp();
-      if (++stage == STAGES) {
-        stage = 0;
-        phase ^= 1;
-      }
+      if (tr && lane == 0) tr[4] = clock64();
     }
   } else {
     // =========================== epilogue (8 warps) ===========================
@@ -257,13 +280,21 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       const bool valid = row < m_rows;
       const size_t grow = (size_t)GUARD_ROWS + row;
       const uint8_t* s_mask = s_stage + stage * STAGE_BYTES + Cfg::SLAB_BYTES;
+      long long* tr = (p.trace && blockIdx.y == 0 && it < TRACE_TILES && warp == 2 && lane == 0)
+                          ? p.trace + ((size_t)blockIdx.x * TRACE_TILES + it) * TRACE_SLOTS : nullptr;
+      if (tr) tr[5] = clock64();
       mbar_wait(&full[stage], phase);                        // mask landed with the slab
       const bool on = valid && (s_mask[trow] != 0);
       mbar_wait(&tfull[acc], acc_phase);
+      if (tr) tr[6] = clock64();
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + half * CW;
       const int chunk0 = p.out_chunk0 + group * (NT / 8) + half * (CW / 8);
-      __nv_bfloat16* out_row = p.out + ((size_t)chunk0 * p.rows_alloc + grow) * 8;
+      // consecutive planes of this row are `pstride` elements apart in either layout
+      const size_t pstride = p.out_blocked ? (size_t)TILE_M * 8 : (size_t)p.rows_alloc * 8;
+      __nv_bfloat16* out_row = p.out_blocked
+                                   ? p.out + (((size_t)tile * p.out_planes + chunk0) * TILE_M + trow) * 8
+                                   : p.out + ((size_t)chunk0 * p.rows_alloc + grow) * 8;
       if constexpr (CW == 16) {
         uint32_t v[16];
         tmem_ld16(t_addr, v);
@@ -277,7 +308,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
             if (p.relu) pk = relu_bf16x2(pk);
             o[e] = on ? pk : 0u;
           }
-          if (valid) *reinterpret_cast<uint4*>(out_row + (size_t)q * p.rows_alloc * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+          if (valid) *reinterpret_cast<uint4*>(out_row + (size_t)q * pstride) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       } else {
 #pragma unroll 1
@@ -295,7 +326,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
               o[e] = on ? pk : 0u;
             }
             if (valid)
-              *reinterpret_cast<uint4*>(out_row + (size_t)(c0 / 8 + q) * p.rows_alloc * 8) =
+              *reinterpret_cast<uint4*>(out_row + (size_t)(c0 / 8 + q) * pstride) =
                   make_uint4(o[0], o[1], o[2], o[3]);
           }
         }
@@ -306,6 +337,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
         mbar_arrive(&tempty[acc]);
         mbar_arrive(&empty[stage]);
       }
+      if (tr) tr[7] = clock64();
       if (++stage == STAGES) {
         stage = 0;
         phase ^= 1;

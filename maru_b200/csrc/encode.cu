@@ -283,7 +283,8 @@ __global__ void __launch_bounds__(416) ingest_rows_kernel(const float* __restric
 
 // planes -> fp32 [n][channels][361] (parity/debug only)
 __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int rows_alloc,
-                                      int channels, float* __restrict__ out, int n) {
+                                      int channels, int total_channels, int blocked,
+                                      float* __restrict__ out, int n) {
   const size_t total = (size_t)n * channels * CELLS;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
@@ -291,8 +292,10 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int r
     const int c = (i / CELLS) % channels;
     const int pos = i / ((size_t)CELLS * channels);
     const int my = cell / BOARD, mx = cell - my * BOARD;
-    const size_t grow = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS + flat_row(my, mx);
-    out[i] = __bfloat162float(x[((size_t)(c / 8) * rows_alloc + grow) * 8 + (c % 8)]);
+    const int m = pos * POS_ROWS + flat_row(my, mx);
+    const size_t off = blocked ? blocked_offset(total_channels / 8, c / 8, m)
+                               : ((size_t)(c / 8) * rows_alloc + GUARD_ROWS + m) * 8;
+    out[i] = __bfloat162float(x[off + (c % 8)]);
   }
 }
 
@@ -314,10 +317,10 @@ cudaError_t launch_ingest_rows(const float* rows, __nv_bfloat16* x0, uint8_t* ma
   ingest_rows_kernel<<<n + 1, 416, 0, stream>>>(rows, x0, mask, rows_alloc, n, n_dev);
   return cudaGetLastError();
 }
-cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, float* out,
-                                  int n, cudaStream_t stream) {
+cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, int total_channels,
+                                  int blocked, float* out, int n, cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  planes_to_nchw_kernel<<<256, 256, 0, stream>>>(x, rows_alloc, channels, out, n);
+  planes_to_nchw_kernel<<<256, 256, 0, stream>>>(x, rows_alloc, channels, total_channels, blocked, out, n);
   return cudaGetLastError();
 }
 

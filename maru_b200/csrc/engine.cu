@@ -180,11 +180,14 @@ int Engine::upload_f32(const Pack& pk, const std::string& name, size_t count, fl
   return 0;
 }
 
-int Engine::alloc_planes(int channels, __nv_bfloat16** p) {
+int Engine::alloc_act(int channels, bool blocked, Act* a) {
+  // both layouts need (C/8) * 16 bytes per row; rows_alloc covers guard rows + whole tiles + slack
   const size_t bytes = (size_t)(channels / 8) * rows_alloc * 16;
-  CK(cudaMalloc(p, bytes));
-  CK(cudaMemset(*p, 0, bytes));
-  allocs.push_back(*p);
+  CK(cudaMalloc(&a->p, bytes));
+  CK(cudaMemset(a->p, 0, bytes));
+  allocs.push_back(a->p);
+  a->channels = channels;
+  a->blocked = blocked;
   return 0;
 }
 
@@ -257,18 +260,23 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   if (upload_f32(pk, "head.fc2.w", 3 * Cv, &w_fc2)) return 1;
   if (upload_f32(pk, "head.fc2.b", 3, &b_fc2)) return 1;
 
-  if (alloc_planes(STEM_CIN, &x0)) return 1;
-  if (alloc_planes(C, &h)) return 1;
-  if (alloc_planes(C / 2, &r)) return 1;
-  if (alloc_planes(C / 2, &s)) return 1;
+  // h and o are only consumed tile-locally (1x1 convs, residuals) -> tile-blocked; x0, r, s feed 3x3
+  // convs (halo) and qkv / g are read per position -> chunk-planar
+  if (alloc_act(STEM_CIN, false, &x0)) return 1;
+  if (alloc_act(C, true, &h)) return 1;
+  if (alloc_act(C / 2, false, &r)) return 1;
+  if (alloc_act(C / 2, false, &s)) return 1;
   if (n_attn > 0) {
-    if (alloc_planes(3 * C, &qkv)) return 1;
-    if (alloc_planes(C, &o)) return 1;
+    if (alloc_act(3 * C, false, &qkv)) return 1;
+    if (alloc_act(C, true, &o)) return 1;
   }
-  if (alloc_planes(Ch, &g)) return 1;
+  if (alloc_act(Ch, false, &g)) return 1;
   CK(cudaMalloc(&mask, (size_t)rows_alloc));
   CK(cudaMemset(mask, 0, (size_t)rows_alloc));
   allocs.push_back(mask);
+  CK(cudaMalloc(&d_trace, (size_t)256 * TRACE_TILES * TRACE_SLOTS * 8));
+  CK(cudaMemset(d_trace, 0, (size_t)256 * TRACE_TILES * TRACE_SLOTS * 8));
+  allocs.push_back(d_trace);
   CK(cudaMalloc(&d_n, 64));
   allocs.push_back(d_n);
   CK(cudaMalloc(&d_logits, (size_t)max_batch * 2 * CELLS * 4));
@@ -332,16 +340,27 @@ Engine::~Engine() {
 // ------------------------------------------------------------------------------------------
 // the launch sequence of one forward (trunk input planes + mask already written)
 // ------------------------------------------------------------------------------------------
-int Engine::conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res,
-                 __nv_bfloat16* out, int relu, int n, const int* n_dev, cudaStream_t st) {
+int Engine::conv(const ConvLayer& L, const Act& in, const Act* res, const Act& out, int relu, int n,
+                 const int* n_dev, cudaStream_t st) {
   ConvParams p;
-  p.in = in;
+  memset(&p, 0, sizeof p);
+  if (in.blocked && L.taps != 1) {
+    set_error("internal: tile-blocked tensor fed to a 3x3 convolution");
+    return 1;
+  }
+  p.in = in.p;
+  p.in_blocked = in.blocked;
+  p.in_planes = in.channels / 8;
+  p.res_blocked = res ? res->blocked : 0;
+  p.res_planes = res ? res->channels / 8 : 0;
+  p.out_blocked = out.blocked;
+  p.out_planes = out.channels / 8;
   p.in_chunk0 = 0;
   p.w = L.w;
   p.bias = L.b;
-  p.res = res;
+  p.res = res ? res->p : nullptr;
   p.res_chunk0 = 0;
-  p.out = out;
+  p.out = out.p;
   p.out_chunk0 = 0;
   p.mask = mask;
   p.rows_alloc = rows_alloc;
@@ -351,6 +370,7 @@ int Engine::conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat1
   p.n_dev = n_dev;
   p.stages = 0;
   p.pdl = (dbg_desc & 1) ? 0 : 1;
+  p.trace = (dbg_trace_launch >= 0 && launches_done == dbg_trace_launch) ? d_trace : nullptr;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
   launches_done++;
   {
@@ -455,15 +475,16 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
     if (conv(B.reduce, h, nullptr, r, 1, n, n_dev, st)) return 1;
     for (int j = 0; j < 2; j++) {
       if (conv(B.c[2 * j], r, nullptr, s, 1, n, n_dev, st)) return 1;
-      if (conv(B.c[2 * j + 1], s, r, r, 1, n, n_dev, st)) return 1;  // r = relu(r + conv(s)), in place
+      if (conv(B.c[2 * j + 1], s, &r, r, 1, n, n_dev, st)) return 1;  // r = relu(r + conv(s)), in place
     }
-    if (conv(B.expand, r, h, h, 1, n, n_dev, st)) return 1;          // h = relu(h + conv(r)), in place
+    if (conv(B.expand, r, &h, h, 1, n, n_dev, st)) return 1;         // h = relu(h + conv(r)), in place
     if (attn_every > 0 && (i + 1) % attn_every == 0 && ai < n_attn) {
       Attn& A = att[ai++];
       if (conv(A.qkv, h, nullptr, qkv, 0, n, n_dev, st)) return 1;
       AttnParams ap;
-      ap.qkv = qkv;
-      ap.out = o;
+      ap.qkv = qkv.p;
+      ap.out = o.p;
+      ap.out_blocked = o.blocked;
       ap.mask = mask;
       ap.rows_alloc = rows_alloc;
       ap.n = n;
@@ -480,12 +501,12 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
         for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) CK(launch_attention(ap, st));
         prof_end(st);
       }
-      if (conv(A.proj, o, h, h, 0, n, n_dev, st)) return 1;           // h = h + proj(o), in place
+      if (conv(A.proj, o, &h, h, 0, n, n_dev, st)) return 1;          // h = h + proj(o), in place
     }
   }
   if (conv(headg, h, nullptr, g, 1, n, n_dev, st)) return 1;
   HeadParams hp;
-  hp.g = g;
+  hp.g = g.p;
   hp.mask = mask;
   hp.w_planes = w_planes;
   hp.b_planes = b_planes;
@@ -515,12 +536,12 @@ int Engine::launch_all(int kind, const void* d_in, float* d_out, int n, const in
     prof_begin("encode", 0, 0, IN_PLANES, 0, 0.0,
                ((double)sizeof(maru_state) + (double)CELLS * IN_PLANES * 2.0) * n, st);
     for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
-      CK(launch_encode_trunk(static_cast<const maru_state*>(d_in), x0, mask, rows_alloc, n, n_dev, st));
+      CK(launch_encode_trunk(static_cast<const maru_state*>(d_in), x0.p, mask, rows_alloc, n, n_dev, st));
     prof_end(st);
   } else {
     prof_begin("ingest", 0, 0, IN_PLANES, 0, 0.0, ((double)IN_ROW * 4.0 + (double)CELLS * IN_PLANES * 2.0) * n,
                st);
-    CK(launch_ingest_rows(static_cast<const float*>(d_in), x0, mask, rows_alloc, n, n_dev, st));
+    CK(launch_ingest_rows(static_cast<const float*>(d_in), x0.p, mask, rows_alloc, n, n_dev, st));
     prof_end(st);
   }
   return launch_trunk(n, n_dev, d_out, st);

@@ -33,6 +33,13 @@ struct Attn {
 
 enum { KIND_PLANES = 0, KIND_STATES = 1 };
 
+// activation tensor: chunk-planar [C/8][rows_alloc][8] or tile-blocked [tile][C/8][128][8] (kernels.h)
+struct Act {
+  __nv_bfloat16* p = nullptr;
+  int channels = 0;
+  bool blocked = false;
+};
+
 // device + pinned staging for one in-flight batch (the queue double-buffers over two of these)
 struct Slot {
   float* d_rows = nullptr;
@@ -68,8 +75,7 @@ struct Engine {
   float *w_planes = nullptr, *b_planes = nullptr, *w_fc1 = nullptr, *b_fc1 = nullptr,
         *w_fc2 = nullptr, *b_fc2 = nullptr;
 
-  __nv_bfloat16 *x0 = nullptr, *h = nullptr, *r = nullptr, *s = nullptr, *qkv = nullptr,
-                *o = nullptr, *g = nullptr;
+  Act x0, h, r, s, qkv, o, g;
   uint8_t* mask = nullptr;
   int* d_n = nullptr;
   int* h_n = nullptr;
@@ -82,6 +88,8 @@ struct Engine {
   int dbg_stop_after = -1;  // debug: stop the launch sequence after this many trunk launches
   int dbg_desc = 0;         // debug: bit0 = disable programmatic dependent launch
   int launches_done = 0;
+  long long* d_trace = nullptr;   // conv pipeline trace (debug key 2 = index of the conv launch to trace)
+  int dbg_trace_launch = -1;
   void clear_graphs();
 
   // per-launch profiling (maru_eval_profile_states): when prof != nullptr every launch is bracketed
@@ -105,10 +113,10 @@ struct Engine {
 
   int upload_conv(const Pack& pk, const std::string& name, int cin, int cout, int taps, ConvLayer& L);
   int upload_f32(const Pack& pk, const std::string& name, size_t count, float** dst);
-  int alloc_planes(int channels, __nv_bfloat16** p);
+  int alloc_act(int channels, bool blocked, Act* a);
 
-  int conv(const ConvLayer& L, const __nv_bfloat16* in, const __nv_bfloat16* res, __nv_bfloat16* out,
-           int relu, int n, const int* n_dev, cudaStream_t st);
+  int conv(const ConvLayer& L, const Act& in, const Act* res, const Act& out, int relu, int n,
+           const int* n_dev, cudaStream_t st);
   int launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st);
   int launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev, cudaStream_t st);
   int forward_device(int kind, const void* d_in, float* d_out, int n);  // async on `stream`

@@ -35,9 +35,18 @@ struct ConvParams {
   int relu;
   int stages;                // pipeline depth (filled by the launcher from the smem budget)
   int pdl;                   // launch with programmatic dependent launch (see common.cuh)
+  // Tensors that are only ever consumed tile-locally (1x1 convs, residuals: the C-channel trunk h
+  // and the attention output o) are stored TILE-BLOCKED: [tile of 128 rows][plane][128 rows][8 ch],
+  // so that a tile's input slab / residual tile is ONE contiguous bulk copy (the TMA unit accepts a
+  // request only every ~50-70 cycles; 33 per-plane requests per tile made the 1x1 layers
+  // request-bound). Tensors read with a 3x3 halo or per position stay chunk-planar.
+  int in_blocked, res_blocked, out_blocked;
+  int in_planes, res_planes, out_planes;   // total planes (channels / 8) of those tensors
   const int* n_dev;          // optional: number of positions read on the device (graph replay with
                              // a smaller batch than the one captured); overrides m_rows
+  long long* trace;          // optional [gridDim.x][TRACE_TILES][TRACE_SLOTS] clock64 stamps (bring-up)
 };
+constexpr int TRACE_TILES = 32, TRACE_SLOTS = 8;
 
 cudaError_t configure_conv_gemm();
 cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,
@@ -56,13 +65,14 @@ cudaError_t launch_encode_trunk(const maru_state* states, __nv_bfloat16* x0, uin
 cudaError_t launch_ingest_rows(const float* rows, __nv_bfloat16* x0, uint8_t* mask, int rows_alloc,
                                int n, const int* n_dev, cudaStream_t stream);
 // trunk input planes -> fp32 [n][channels][361] (debug / parity)
-cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, float* out,
-                                  int n, cudaStream_t stream);
+cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, int total_channels,
+                                  int blocked, float* out, int n, cudaStream_t stream);
 
 // ---- K4: attention core (attention.cu) -------------------------------------------------------
 struct AttnParams {
   const __nv_bfloat16* qkv;  // planes: q [0,C), k [C,2C), v [2C,3C); q pre-scaled by log2(e)/sqrt(d)
   __nv_bfloat16* out;        // planes [0,C)
+  int out_blocked;           // output tensor is tile-blocked (consumed by the 1x1 projection only)
   const uint8_t* mask;
   int rows_alloc;
   int n;                     // positions

@@ -17,7 +17,7 @@ __device__ __forceinline__ uint64_t desc_sw128(uint32_t saddr) {
 }
 
 template <int N, int NACC, int LAYOUT>
-__global__ void __launch_bounds__(128) bench(int iters, long long* out) {
+__global__ void __launch_bounds__(128) bench(int iters, long long* out, int aoff = 0) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) bench(int iters, long long* out) {
     uint64_t da[4], db[4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      if (LAYOUT == 0) { da[k] = umma_desc(a0 + k * 2 * 2816, 2816, 128); db[k] = umma_desc(b0 + k * 2 * N * 16, N * 16, 128); }
+      if (LAYOUT == 0) { da[k] = umma_desc(a0 + aoff * 16 + k * 2 * 2816, 2816, 128); db[k] = umma_desc(b0 + k * 2 * N * 16, N * 16, 128); }
       else { da[k] = desc_sw128(a0 + k * 32); db[k] = desc_sw128(b0 + k * 32); }
     }
     long long t0 = clock64();
@@ -58,15 +58,25 @@ template <int N, int NACC, int LAYOUT> void run1(int blocks, long long* d_out) {
   auto k = bench<N, NACC, LAYOUT>;
   cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
   const int iters = 4000;
-  k<<<blocks, 128, 64 * 1024>>>(iters, d_out);
+  k<<<blocks, 128, 64 * 1024>>>(iters, d_out, 0);
   cudaDeviceSynchronize();
-  k<<<blocks, 128, 64 * 1024>>>(iters, d_out);
+  k<<<blocks, 128, 64 * 1024>>>(iters, d_out, 0);
   cudaError_t e = cudaDeviceSynchronize();
   std::vector<long long> h(blocks);
   cudaMemcpy(h.data(), d_out, blocks * 8, cudaMemcpyDeviceToHost);
   long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
   printf("N=%3d layout=%s nacc=%d blocks=%3d  cycles/mma=%7.1f  (ideal %d)  %s\n", N, LAYOUT ? "sw128" : "none ",
          NACC, blocks, (double)mx / iters, 128 * N / 256, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+template <int N> void run_off(int aoff, long long* d_out) {
+  auto k = bench<N, 1, 0>;
+  cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+  const int iters = 4000;
+  k<<<148, 128, 64 * 1024>>>(iters, d_out, aoff); cudaDeviceSynchronize();
+  k<<<148, 128, 64 * 1024>>>(iters, d_out, aoff); cudaDeviceSynchronize();
+  std::vector<long long> h(148); cudaMemcpy(h.data(), d_out, 148 * 8, cudaMemcpyDeviceToHost);
+  long long mx = 0; for (auto v : h) mx = v > mx ? v : mx;
+  printf("N=%3d layout=none A start offset = %d rows (x16 B): cycles/mma=%7.1f\n", N, aoff, (double)mx / iters);
 }
 template <int N> void run(int blocks, long long* d_out) {
   run1<N, 1, 0>(blocks, d_out); run1<N, 2, 0>(blocks, d_out);
@@ -76,6 +86,8 @@ template <int N> void run(int blocks, long long* d_out) {
 
 int main() {
   long long* d_out; cudaMalloc(&d_out, 148 * 8);
-  for (int blocks : {1, 148}) { run<32>(blocks, d_out); run<64>(blocks, d_out); run<128>(blocks, d_out); run<256>(blocks, d_out); }
+  for (int aoff : {0, 1, 3, 4, 5, 7, 8}) { run_off<64>(aoff, d_out); }
+  for (int aoff : {0, 1, 4}) { run_off<128>(aoff, d_out); }
+  for (int blocks : {148}) { run<32>(blocks, d_out); run<64>(blocks, d_out); run<128>(blocks, d_out); run<256>(blocks, d_out); }
   return 0;
 }
