@@ -138,7 +138,8 @@ int  maru_eval_debug_planes(maru_eval* e, int which, float* out, int n, int chan
 int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 /* Debug knobs. key 0: stop the launch sequence after `value` trunk launches (<0: run everything;
  * the heads then do not run). key 1: bit0 = disable programmatic dependent launch (A/B timing), bit2 = use the legacy
- * mma.sync attention kernel instead of the tcgen05 one (A/B). */
+ * mma.sync attention kernel instead of the tcgen05 one (A/B), bit3 = enable the experimental
+ * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower). */
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
 #define MARU_DBG_TRACE_LAUNCH 2       /* index of the trunk launch whose pipeline is traced (-1: off) */

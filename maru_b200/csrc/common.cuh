@@ -46,7 +46,7 @@ constexpr int STEM_KOMI_LO = 40;  // residual of the bf16 split of info scalar 2
 #ifdef __CUDACC__
 
 #ifndef MARU_SPIN_LIMIT
-#define MARU_SPIN_LIMIT (1u << 26)  // bounded waits: a protocol bug traps instead of hanging the GPU
+#define MARU_SPIN_LIMIT (1u << 24)  // bounded waits: a protocol bug traps instead of hanging the GPU
 #endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -256,6 +256,13 @@ __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory");
 }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 
 // ---------------------------------------------------------------- misc
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

@@ -27,7 +27,7 @@
 
 namespace maru {
 
-constexpr int CONV_THREADS = 352;  // warp 0 producer, warps 1 and 10 MMA issue, warps 2..9 epilogue
+constexpr int CONV_THREADS = 384;  // warp 0 producer, warps 1,10 MMA issue, warps 2..9 epilogue, warp 11 tile flags
 
 template <int CIN, int NT, int TAPS>
 struct ConvCfg {
@@ -86,7 +86,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   uint64_t* tfull = bars + 2 * MAXS;       // [2] accumulator ready
   uint64_t* tempty = tfull + 2;            // [2] accumulator drained
   uint64_t* wbar = tempty + 2;             // weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);   // inside the 128-byte barrier block
+  // number of (tile, epilogue warp) store completions so far: a counter, not an mbarrier, because the
+  // flag signaller may fall more than one phase behind the epilogue
+  volatile uint32_t* stored = reinterpret_cast<volatile uint32_t*>(wbar + 1);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);   // last slot of the 128-byte barrier block
 
   pdl_launch_dependents();                      // let the next layer's CTAs start their prologue
   const int warp = threadIdx.x >> 5;
@@ -107,6 +110,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       mbar_init(&tempty[i], 8);
     }
     mbar_init(wbar, 1);
+    *stored = 0;
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -163,15 +167,57 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       }
     }
     __syncwarp();
-    pdl_wait();   // everything below reads what the previous kernel wrote (activations, mask)
+    // Without tile flags: wait for the whole previous grid. With flags the mask (written by the
+    // encode kernel, several full dependencies upstream) and the residual are
+    // already complete by transitivity; only the input tiles are polled below.
+    if (p.in_flags == nullptr) pdl_wait();
     int stage = 0;
     uint32_t phase = 0;
     int tix = 0;
+    unsigned fnext1 = 0u, fnext2 = 0u;   // flag values prefetched for the next / the one after next tile
+    if (p.in_flags != nullptr) {
+      const int nl = (TAPS == 9) ? 3 : 1;
+      const int t0 = ((TAPS == 9) ? (int)blockIdx.x - 1 + lane : (int)blockIdx.x);
+      const int t1 = t0 + (int)gridDim.x;
+      fnext1 = (lane < nl && t0 >= 0 && t0 < n_tiles) ? ld_acquire_gpu(p.in_flags + t0) : 0u;
+      fnext2 = (lane < nl && t1 >= 0 && t1 < n_tiles) ? ld_acquire_gpu(p.in_flags + t1) : 0u;
+    }
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, tix++) {
       long long* tr = (p.trace && blockIdx.y == 0 && tix < TRACE_TILES)
                           ? p.trace + ((size_t)blockIdx.x * TRACE_TILES + tix) * TRACE_SLOTS : nullptr;
       if (tr && lane == 0) tr[0] = clock64();
+      // Tiles this slab reads: tile-1 .. tile+1 for a 3x3 (24-row halo), the tile itself for a 1x1.
+      // The flag loads are software-pipelined two tiles ahead (an acquire load is an L2 round trip
+      // of ~1 us, longer than a tile period): fnext2 holds the value loaded two iterations ago.
+      unsigned fval = 0u;
+      bool fpoll = false;
+      int ft = 0;
+      if (p.in_flags != nullptr) {
+        const int nl = (TAPS == 9) ? 3 : 1;
+        ft = (TAPS == 9) ? tile - 1 + lane : tile;
+        fpoll = lane < nl && ft >= 0 && ft < n_tiles;
+        fval = fnext1;                                   // loaded for this tile two iterations ago
+        fnext1 = fnext2;
+        const int t2 = ft + 2 * (int)gridDim.x;          // prefetch for the tile after next
+        fnext2 = (lane < nl && t2 >= 0 && t2 < n_tiles) ? ld_acquire_gpu(p.in_flags + t2) : 0u;
+      }
       mbar_wait(&empty[stage], phase ^ 1);
+      if (p.in_flags != nullptr) {
+        if (fpoll) {
+          uint32_t spins = 0;
+          while (fval < p.in_expect) {
+            __nanosleep(128);
+            fval = ld_acquire_gpu(p.in_flags + ft);
+            if (++spins > MARU_SPIN_LIMIT) {
+              printf("maru: tile flag wait timed out (block %d tile %d)\n", (int)blockIdx.x, ft);
+              __trap();
+            }
+          }
+        }
+        __syncwarp();
+        // no reader-side proxy fence: it would drain the bulk copies already in flight and serialise
+        // the stage ring; the writer publishes with fence.proxy.async + gpu fence before the flag
+      }
       if (tr && lane == 0) tr[1] = clock64();
       if (elect_one()) {
         mbar_expect_tx(&full[stage], STAGE_BYTES);
@@ -264,6 +310,29 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       __syncwarp();
       if (tr && lane == 0) tr[4] = clock64();
     }
+  } else if (warp == 11) {
+    // =========================== tile-flag signaller ===========================
+    // The gpu-scope fence that publishes a finished tile to the next layer's CTAs costs hundreds of
+    // cycles; it runs here, off the epilogue warps' critical path (CTA barrier -> fence -> atomic).
+    if (p.out_flags != nullptr) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+        if (lane == 0) {
+          uint32_t spins = 0;
+          while (*stored < 8u * (uint32_t)(it + 1)) {
+            __nanosleep(256);   // a tight LDS loop would steal shared-memory cycles from the UMMA operand fetch
+            if (++spins > MARU_SPIN_LIMIT) {
+              printf("maru: store counter wait timed out (block %d)\n", (int)blockIdx.x);
+              __trap();
+            }
+          }
+          fence_proxy_async_all();             // the consumers read these rows through the async proxy
+          __threadfence();                     // acquire the epilogue warps' stores, publish gpu-wide
+          atomicAdd(p.out_flags + tile, 8u);
+        }
+        __syncwarp();
+      }
+    }
   } else {
     // =========================== epilogue (8 warps) ===========================
     constexpr int CW = NT / 2;               // columns per warp
@@ -336,6 +405,10 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       if (lane == 0) {
         mbar_arrive(&tempty[acc]);
         mbar_arrive(&empty[stage]);
+        if (p.out_flags != nullptr) {
+          __threadfence_block();                                   // this warp's stores before the count
+          atomicAdd_block(const_cast<uint32_t*>(stored), 1u);
+        }
       }
       if (tr) tr[7] = clock64();
       if (++stage == STAGES) {

@@ -271,6 +271,15 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     if (alloc_act(C, true, &o)) return 1;
   }
   if (alloc_act(Ch, false, &g)) return 1;
+  {
+    n_tiles_max = (total_rows(max_batch) + TILE_M - 1) / TILE_M;
+    Act* acts[7] = {&x0, &h, &r, &s, &qkv, &o, &g};
+    flags_bytes = (size_t)7 * n_tiles_max * sizeof(unsigned);
+    CK(cudaMalloc(&d_flags, flags_bytes));
+    CK(cudaMemset(d_flags, 0, flags_bytes));
+    allocs.push_back(d_flags);
+    for (int i = 0; i < 7; i++) acts[i]->flags = d_flags + (size_t)i * n_tiles_max;
+  }
   CK(cudaMalloc(&mask, (size_t)rows_alloc));
   CK(cudaMemset(mask, 0, (size_t)rows_alloc));
   allocs.push_back(mask);
@@ -340,8 +349,8 @@ Engine::~Engine() {
 // ------------------------------------------------------------------------------------------
 // the launch sequence of one forward (trunk input planes + mask already written)
 // ------------------------------------------------------------------------------------------
-int Engine::conv(const ConvLayer& L, const Act& in, const Act* res, const Act& out, int relu, int n,
-                 const int* n_dev, cudaStream_t st) {
+int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int n, const int* n_dev,
+                 cudaStream_t st) {
   ConvParams p;
   memset(&p, 0, sizeof p);
   if (in.blocked && L.taps != 1) {
@@ -370,6 +379,13 @@ int Engine::conv(const ConvLayer& L, const Act& in, const Act* res, const Act& o
   p.n_dev = n_dev;
   p.stages = 0;
   p.pdl = (dbg_desc & 1) ? 0 : 1;
+  // Per-tile cross-layer flags are an EXPERIMENT that lost ("what did not work"): the forward
+  // is ~20 % slower with them than with plain grid dependencies, so they are off unless debug bit 3
+  // is set; never while profiling (repeated launches of one layer).
+  const bool use_flags = p.pdl && prof == nullptr && (dbg_desc & 8);
+  p.in_flags = (use_flags && in.flagged) ? in.flags : nullptr;
+  p.in_expect = in.version;
+  p.out_flags = use_flags ? out.flags : nullptr;
   p.trace = (dbg_trace_launch >= 0 && launches_done == dbg_trace_launch) ? d_trace : nullptr;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
   launches_done++;
@@ -385,6 +401,12 @@ int Engine::conv(const ConvLayer& L, const Act& in, const Act* res, const Act& o
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
     CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
   prof_end(st);
+  if (use_flags) {
+    out.version += 8u * (unsigned)(L.cout / L.nt);   // 8 epilogue warps per CTA, one CTA per channel group
+    out.flagged = true;
+  } else {
+    out.flagged = false;
+  }
   return 0;
 }
 
@@ -468,6 +490,15 @@ void Engine::clear_graphs() {
 
 int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st) {
   launches_done = 0;
+  {
+    // per-tile completion counters start from zero in every forward (also under graph replay)
+    CK(cudaMemsetAsync(d_flags, 0, flags_bytes, st));
+    Act* acts[7] = {&x0, &h, &r, &s, &qkv, &o, &g};
+    for (Act* a : acts) {
+      a->version = 0;
+      a->flagged = false;
+    }
+  }
   if (conv(stem, x0, nullptr, h, 1, n, n_dev, st)) return 1;
   int ai = 0;
   for (int i = 0; i < blocks; i++) {
@@ -500,6 +531,7 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
                    4.0 * T * T * C * n, T * 4.0 * C * 2.0 * n, st);
         for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) CK(launch_attention(ap, st));
         prof_end(st);
+        o.flagged = false;   // written by a kernel without tile flags: consumers use the grid dependency
       }
       if (conv(A.proj, o, &h, h, 0, n, n_dev, st)) return 1;          // h = h + proj(o), in place
     }

@@ -38,6 +38,9 @@ struct Act {
   __nv_bfloat16* p = nullptr;
   int channels = 0;
   bool blocked = false;
+  unsigned* flags = nullptr;   // per-tile completion counters (cross-layer pipelining)
+  unsigned version = 0;        // host-side: counter value every tile reaches once the last writer is done
+  bool flagged = false;        // the current contents were produced by a flag-bumping conv
 };
 
 // device + pinned staging for one in-flight batch (the queue double-buffers over two of these)
@@ -114,9 +117,12 @@ struct Engine {
   int upload_conv(const Pack& pk, const std::string& name, int cin, int cout, int taps, ConvLayer& L);
   int upload_f32(const Pack& pk, const std::string& name, size_t count, float** dst);
   int alloc_act(int channels, bool blocked, Act* a);
+  unsigned* d_flags = nullptr;   // all Act::flags live in this one allocation (one memset per forward)
+  size_t flags_bytes = 0;
+  int n_tiles_max = 0;
 
-  int conv(const ConvLayer& L, const Act& in, const Act* res, const Act& out, int relu, int n,
-           const int* n_dev, cudaStream_t st);
+  int conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int n, const int* n_dev,
+           cudaStream_t st);
   int launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st);
   int launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev, cudaStream_t st);
   int forward_device(int kind, const void* d_in, float* d_out, int n);  // async on `stream`

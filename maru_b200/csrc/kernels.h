@@ -40,6 +40,13 @@ struct ConvParams {
   // so that a tile's input slab / residual tile is ONE contiguous bulk copy (the TMA unit accepts a
   // request only every ~50-70 cycles; 33 per-plane requests per tile made the 1x1 layers
   // request-bound). Tensors read with a 3x3 halo or per position stay chunk-planar.
+  // Cross-layer pipelining: instead of waiting for the whole previous grid (griddepcontrol.wait), a
+  // conv that consumes another conv's output waits only for the 3 (3x3) or 1 (1x1) producer tiles
+  // it reads. Every epilogue warp bumps out_flags[tile] after its stores; the consumer's producer
+  // warp polls in_flags[tile-1..tile+1] >= in_expect. nullptr => plain grid dependency.
+  const unsigned* in_flags;
+  unsigned in_expect;
+  unsigned* out_flags;
   int in_blocked, res_blocked, out_blocked;
   int in_planes, res_planes, out_planes;   // total planes (channels / 8) of those tensors
   const int* n_dev;          // optional: number of positions read on the device (graph replay with
