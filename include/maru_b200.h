@@ -143,7 +143,11 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
 #define MARU_DBG_TRACE_LAUNCH 2       /* index of the trunk launch whose pipeline is traced (-1: off) */
+#define MARU_DBG_TIMELINE 3           /* 1: every conv launch stamps %globaltimer (see debug_timeline)  */
 int  maru_eval_debug_set(maru_eval* e, int key, int value);
+/* [64 launches][first CTA, last CTA][8] ns stamps: entry, prologue done, dependency resolved, first
+ * operands landed, first accumulator ready, exit. */
+int  maru_eval_debug_timeline(maru_eval* e, long long* out);
 /* clock64 stamps of the traced conv launch: [n_ctas][32 tiles][8] = producer {wait,issue}, MMA warp
  * {wait start, operands ready, issued}, epilogue warp {wait start, accumulator ready, done}. */
 int  maru_eval_debug_trace(maru_eval* e, long long* out, int n_ctas);

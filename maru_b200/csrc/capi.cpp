@@ -178,6 +178,15 @@ int maru_eval_debug_trace(maru_eval* ev, long long* out, int n_ctas) {
   return 0;
 }
 
+int maru_eval_debug_timeline(maru_eval* ev, long long* out) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(cudaStreamSynchronize(e->stream));
+  CKC(cudaMemcpy(out, e->d_timeline, 64 * 2 * 8 * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
@@ -187,6 +196,7 @@ int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   if (key == MARU_DBG_STOP_AFTER) e->dbg_stop_after = value;
   else if (key == MARU_DBG_DESC_BITS) e->dbg_desc = value;
   else if (key == MARU_DBG_TRACE_LAUNCH) e->dbg_trace_launch = value;
+  else if (key == MARU_DBG_TIMELINE) e->dbg_timeline = value;
   else {
     maru::set_error("maru_eval_debug_set: unknown key");
     return 1;

@@ -94,11 +94,32 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   pdl_launch_dependents();                      // let the next layer's CTAs start their prologue
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  // timeline (bring-up): first and last CTA of group 0 stamp entry / prologue / dependency / first
+  // operands / first accumulator / exit with the global nanosecond timer
+  long long* tl = nullptr;
+  if (p.timeline != nullptr && blockIdx.y == 0 && (blockIdx.x == 0 || blockIdx.x == gridDim.x - 1))
+    tl = p.timeline + ((size_t)p.seq * 2 + (blockIdx.x == 0 ? 0 : 1)) * 8;
+  if (tl && threadIdx.x == 0) tl[0] = globaltimer_ns();
   const int group = blockIdx.y;                 // output-channel group of NT channels
   const int m_rows = (p.n_dev != nullptr) ? total_rows(*p.n_dev) : p.m_rows;
   const int n_tiles = (m_rows + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
+    // The weights do not depend on the previous layer: request them before anything else so the
+    // ~2 us L2 round trip of the 74-147 KB image overlaps the rest of the prologue, the dependency
+    // wait and the first slab load (tools/timeline.py).
+    mbar_init(wbar, 1);
+    fence_mbar_init();
+    mbar_expect_tx(wbar, Cfg::W_BYTES);
+    if (p.cout_total == NT) {
+      bulk_load_1d(s_w, p.w, Cfg::W_BYTES, wbar);            // whole image is contiguous: one request
+    } else {
+      // weights of this group: [TAPS][KCH][cout_total][8] in HBM -> [TAPS][KCH][NT][8] in smem
+      for (int tc = 0; tc < TAPS * Cfg::KCH; tc++) {
+        const __nv_bfloat16* src = p.w + ((size_t)tc * p.cout_total + (size_t)group * NT) * 8;
+        bulk_load_1d(s_w + (size_t)tc * NT * 16, src, NT * 16, wbar);
+      }
+    }
     for (int i = 0; i < MAXS; i++) {
       mbar_init(&full[i], 1);
       // a stage is free once the MMA commit retired (slab, residual) and the 8 epilogue warps are
@@ -109,7 +130,6 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 8);
     }
-    mbar_init(wbar, 1);
     *stored = 0;
     fence_mbar_init();
   }
@@ -148,29 +168,18 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tl && threadIdx.x == 0) tl[1] = globaltimer_ns();
 
   // Roles are WARP-uniform and a single elected lane issues the async instructions: in a
   // thread-divergent branch ptxas wraps every UTCHMMA / UBLKCP in an ELECT + BRA.U.ANY loop
   // (measured ~115 cycles per MMA instead of 48, profiles/r1_umma_microbench.txt).
   if (warp == 0) {
     // =========================== producer ===========================
-    if (elect_one()) {
-      // weights of this group: [TAPS][KCH][cout_total][8] in HBM -> [TAPS][KCH][NT][8] in smem
-      mbar_expect_tx(wbar, Cfg::W_BYTES);
-      if (p.cout_total == NT) {
-        bulk_load_1d(s_w, p.w, Cfg::W_BYTES, wbar);          // whole image is contiguous: one request
-      } else {
-        for (int tc = 0; tc < TAPS * Cfg::KCH; tc++) {
-          const __nv_bfloat16* src = p.w + ((size_t)tc * p.cout_total + (size_t)group * NT) * 8;
-          bulk_load_1d(s_w + (size_t)tc * NT * 16, src, NT * 16, wbar);
-        }
-      }
-    }
-    __syncwarp();
     // Without tile flags: wait for the whole previous grid. With flags the mask (written by the
     // encode kernel, several full dependencies upstream) and the residual are
     // already complete by transitivity; only the input tiles are polled below.
     if (p.in_flags == nullptr) pdl_wait();
+    if (tl && lane == 0) tl[2] = globaltimer_ns();
     int stage = 0;
     uint32_t phase = 0;
     int tix = 0;
@@ -281,6 +290,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       if (tr && lane == 0) tr[2] = clock64();
       mbar_wait(&tempty[acc], acc_phase ^ 1);
       mbar_wait(&full[stage], phase);
+      if (tl && lane == 0 && it == 0) tl[3] = globaltimer_ns();
       if (tr && lane == 0) tr[3] = clock64();
       tc_fence_after();
       if (elect_one()) {
@@ -355,6 +365,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       mbar_wait(&full[stage], phase);                        // mask landed with the slab
       const bool on = valid && (s_mask[trow] != 0);
       mbar_wait(&tfull[acc], acc_phase);
+      if (tl && it == 0 && warp == 2 && lane == 0) tl[4] = globaltimer_ns();
       if (tr) tr[6] = clock64();
       tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(lg * 32) << 16) + acc * NT + half * CW;
@@ -420,6 +431,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
 
   tc_fence_before();
   __syncthreads();
+  if (tl && threadIdx.x == 0) tl[5] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -429,9 +441,14 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
 // ------------------------------------------------------------------------------------------
 template <int CIN, int NT, int TAPS>
 static cudaError_t configure_cfg() {
-  return cudaFuncSetAttribute(conv_gemm_kernel<CIN, NT, TAPS>,
-                              cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              ConvCfg<CIN, NT, TAPS>::SMEM_LIMIT);
+  cudaError_t e = cudaFuncSetAttribute(conv_gemm_kernel<CIN, NT, TAPS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       ConvCfg<CIN, NT, TAPS>::SMEM_LIMIT);
+  if (e != cudaSuccess) return e;
+  // every kernel of the forward asks for the same (maximum) shared-memory carveout so that the SMs
+  // never have to be drained and re-partitioned between consecutive launches
+  return cudaFuncSetAttribute(conv_gemm_kernel<CIN, NT, TAPS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
 }
 
 template <int CIN, int NT, int TAPS>

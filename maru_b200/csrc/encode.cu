@@ -299,6 +299,17 @@ __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int r
   }
 }
 
+cudaError_t configure_heads();
+cudaError_t configure_misc_kernels() {
+  cudaError_t e = configure_heads();
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(encode_trunk_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                           cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(ingest_rows_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_encode_rows(const maru_state* states, float* rows, int n, const int* n_dev,
                                cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;

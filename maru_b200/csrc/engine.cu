@@ -215,6 +215,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   sm_count = prop.multiProcessorCount;
   CK(configure_conv_gemm());
   CK(configure_attention());
+  CK(configure_misc_kernels());
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
   CK(cudaEventCreate(&ev0));
   CK(cudaEventCreate(&ev1));
@@ -286,6 +287,9 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   CK(cudaMalloc(&d_trace, (size_t)256 * TRACE_TILES * TRACE_SLOTS * 8));
   CK(cudaMemset(d_trace, 0, (size_t)256 * TRACE_TILES * TRACE_SLOTS * 8));
   allocs.push_back(d_trace);
+  CK(cudaMalloc(&d_timeline, 64 * 2 * 8 * 8));
+  CK(cudaMemset(d_timeline, 0, 64 * 2 * 8 * 8));
+  allocs.push_back(d_timeline);
   CK(cudaMalloc(&d_n, 64));
   allocs.push_back(d_n);
   CK(cudaMalloc(&d_logits, (size_t)max_batch * 2 * CELLS * 4));
@@ -387,6 +391,8 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   p.in_expect = in.version;
   p.out_flags = use_flags ? out.flags : nullptr;
   p.trace = (dbg_trace_launch >= 0 && launches_done == dbg_trace_launch) ? d_trace : nullptr;
+  p.timeline = (dbg_timeline && launches_done < 64) ? d_timeline : nullptr;
+  p.seq = launches_done;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
   launches_done++;
   {

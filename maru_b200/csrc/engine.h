@@ -93,6 +93,8 @@ struct Engine {
   int launches_done = 0;
   long long* d_trace = nullptr;   // conv pipeline trace (debug key 2 = index of the conv launch to trace)
   int dbg_trace_launch = -1;
+  long long* d_timeline = nullptr;   // [64 launches][2][8] globaltimer stamps (debug key 3 = on/off)
+  int dbg_timeline = 0;
   void clear_graphs();
 
   // per-launch profiling (maru_eval_profile_states): when prof != nullptr every launch is bracketed

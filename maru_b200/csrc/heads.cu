@@ -199,6 +199,11 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   }
 }
 
+cudaError_t configure_heads() {
+  return cudaFuncSetAttribute(heads_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                              cudaSharedmemCarveoutMaxShared);
+}
+
 cudaError_t launch_heads(const HeadParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   if (p.ch > HEAD_MAX_CH || p.ch % 8 != 0 || p.cv > HEAD_MAX_CV) return cudaErrorInvalidValue;

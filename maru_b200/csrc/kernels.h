@@ -52,6 +52,8 @@ struct ConvParams {
   const int* n_dev;          // optional: number of positions read on the device (graph replay with
                              // a smaller batch than the one captured); overrides m_rows
   long long* trace;          // optional [gridDim.x][TRACE_TILES][TRACE_SLOTS] clock64 stamps (bring-up)
+  long long* timeline;       // optional [launch seq][2 CTAs][8] %globaltimer stamps of every conv launch
+  int seq;
 };
 constexpr int TRACE_TILES = 32, TRACE_SLOTS = 8;
 
@@ -112,5 +114,6 @@ struct HeadParams {
   int pdl;
 };
 cudaError_t launch_heads(const HeadParams& p, cudaStream_t stream);
+cudaError_t configure_misc_kernels();   // same shared-memory carveout for encode / heads kernels
 
 }  // namespace maru
