@@ -12,7 +12,8 @@
 
 namespace maru {
 
-constexpr int HEAD_THREADS = 256;
+constexpr int HEAD_THREADS = 416;      // one thread per padded row (400) in the per-cell phase
+constexpr int HEAD_WARPS = HEAD_THREADS / 32;
 constexpr int HEAD_MAX_CH = 32;
 constexpr int HEAD_MAX_CV = 128;
 
@@ -21,23 +22,36 @@ __device__ __forceinline__ float warp_max(float v) {
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
+// single-instruction warp reductions (REDUX): non-negative floats order like their bit patterns, and
+// the channel sums are taken in 20.12 fixed point (g is bf16: 2^-12 is below its rounding noise)
+__device__ __forceinline__ unsigned redux_max_u32(unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.max.u32 %0, %1, 0xffffffff;\n" : "=r"(r) : "r"(v));
+  return r;
+}
+__device__ __forceinline__ unsigned redux_add_u32(unsigned v) {
+  unsigned r;
+  asm volatile("redux.sync.add.u32 %0, %1, 0xffffffff;\n" : "=r"(r) : "r"(v));
+  return r;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
+// One CTA per position, one thread per padded row: the row's 32 head features stay in registers
+// from the single global read to the last use (logits, territory / value planes, pooling), the
+// policy softmax is a two-level shuffle reduction, and only the tiny value MLP goes through smem.
 __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p) {
-  __shared__ __align__(16) __nv_bfloat16 s_g[HEAD_MAX_CH / 8][POS_ROWS + 1][8];  // chunk-planar copy
-  __shared__ float s_logit[2][POS_ROWS];
-  __shared__ uint8_t s_mask[POS_ROWS];
   __shared__ float s_wp[6][HEAD_MAX_CH];
   __shared__ float s_bp[6];
-  __shared__ float s_red[2][HEAD_THREADS / 32];
-  __shared__ float s_part[8][2 * HEAD_MAX_CH];
+  __shared__ float s_red[4][HEAD_WARPS];                 // max0, max1 then sum0, sum1 per warp
+  __shared__ float s_psum[HEAD_WARPS][HEAD_MAX_CH];      // per-warp channel sums
+  __shared__ float s_pmax[HEAD_WARPS][HEAD_MAX_CH];
+  __shared__ float s_cnt[HEAD_WARPS];
   __shared__ float s_pool[2 * HEAD_MAX_CH];
   __shared__ float s_hid[HEAD_MAX_CV];
-  __shared__ float s_stat[4];
 
   pdl_launch_dependents();
   const int pos = blockIdx.x;
@@ -45,52 +59,51 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   const int tid = threadIdx.x;
   const int ch = p.ch;
   const int warp = tid >> 5, lane = tid & 31;
+  const int n_chunks = ch / 8;
 
   for (int i = tid; i < 6 * ch; i += HEAD_THREADS) s_wp[i / ch][i % ch] = p.w_planes[i];
   if (tid < 6) s_bp[tid] = p.b_planes[tid];
   pdl_wait();   // g and mask come from the previous kernels
-  for (int r = tid; r < POS_ROWS; r += HEAD_THREADS) s_mask[r] = p.mask[(size_t)pos * POS_ROWS + r];
-  // g tile: [ch/8 planes][400 rows][8] -> smem fp32 [row][ch]; 16-byte row-consecutive loads
-  const int n_chunks = ch / 8;
-  for (int i = tid; i < n_chunks * POS_ROWS; i += HEAD_THREADS) {
-    const int c = i / POS_ROWS, r = i - c * POS_ROWS;
-    const size_t grow = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS + r;
-    *reinterpret_cast<uint4*>(&s_g[c][r][0]) =
-        *reinterpret_cast<const uint4*>(p.g + ((size_t)c * p.rows_alloc + grow) * 8);
-  }
-  __syncthreads();
 
-  float* out = p.out + (size_t)pos * OUT_ROW;
-
-  // ---- per-cell logits; territory / point-value planes written directly
-  float lmax0 = -INFINITY, lmax1 = -INFINITY;
-  for (int r = tid; r < POS_ROWS; r += HEAD_THREADS) {
-    const int gy = r / PITCH, x = r - gy * PITCH;
-    if (gy < 1 || x >= BOARD) continue;
-    const int cell = (gy - 1) * BOARD + x;
-    const bool on = s_mask[r] != 0;
-    float z[6];
+  const int r = tid;                                     // padded row of this thread
+  const bool in_pos = r < POS_ROWS;
+  const int gy = r / PITCH, x = r - gy * PITCH;
+  const bool cell_ok = in_pos && gy >= 1 && x < BOARD;   // a real 19x19 cell (maybe off-board)
+  const int cell = (gy - 1) * BOARD + x;
+  const bool on = in_pos && (p.mask[(size_t)pos * POS_ROWS + (in_pos ? r : 0)] != 0);
+  float gv[HEAD_MAX_CH];
 #pragma unroll
-    for (int k = 0; k < 6; k++) z[k] = s_bp[k];
-    for (int c8 = 0; c8 < n_chunks; c8++) {
-      const uint4 v = *reinterpret_cast<const uint4*>(&s_g[c8][r][0]);
-      const float gv[8] = {bf16_lo(v.x), bf16_hi(v.x), bf16_lo(v.y), bf16_hi(v.y),
-                           bf16_lo(v.z), bf16_hi(v.z), bf16_lo(v.w), bf16_hi(v.w)};
-#pragma unroll
-      for (int e = 0; e < 8; e++) {
-#pragma unroll
-        for (int k = 0; k < 6; k++) z[k] = fmaf(s_wp[k][c8 * 8 + e], gv[e], z[k]);
-      }
+  for (int c8 = 0; c8 < HEAD_MAX_CH / 8; c8++) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (in_pos && c8 < n_chunks) {
+      const size_t grow = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS + r;
+      v = *reinterpret_cast<const uint4*>(p.g + ((size_t)c8 * p.rows_alloc + grow) * 8);
     }
-    s_logit[0][r] = z[0];
-    s_logit[1][r] = z[1];
+    gv[c8 * 8 + 0] = bf16_lo(v.x); gv[c8 * 8 + 1] = bf16_hi(v.x);
+    gv[c8 * 8 + 2] = bf16_lo(v.y); gv[c8 * 8 + 3] = bf16_hi(v.y);
+    gv[c8 * 8 + 4] = bf16_lo(v.z); gv[c8 * 8 + 5] = bf16_hi(v.z);
+    gv[c8 * 8 + 6] = bf16_lo(v.w); gv[c8 * 8 + 7] = bf16_hi(v.w);
+  }
+  __syncthreads();                                       // head-plane weights in smem
+
+  // ---- per-cell logits
+  float z[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) z[k] = s_bp[k];
+#pragma unroll
+  for (int c = 0; c < HEAD_MAX_CH; c++) {
+    if (c < ch) {
+#pragma unroll
+      for (int k = 0; k < 6; k++) z[k] = fmaf(s_wp[k][c], gv[c], z[k]);
+    }
+  }
+  float* out = p.out + (size_t)pos * OUT_ROW;
+  if (cell_ok) {
     if (p.logits != nullptr) {
       p.logits[((size_t)pos * 2 + 0) * CELLS + cell] = z[0];
       p.logits[((size_t)pos * 2 + 1) * CELLS + cell] = z[1];
     }
     if (on) {
-      lmax0 = fmaxf(lmax0, z[0]);
-      lmax1 = fmaxf(lmax1, z[1]);
       const float tm = fmaxf(z[2], fmaxf(z[3], z[4]));
       const float e2 = __expf(z[2] - tm), e3 = __expf(z[3] - tm), e4 = __expf(z[4] - tm);
       const float inv = 1.0f / (e2 + e3 + e4);
@@ -105,97 +118,81 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
       out[5 * CELLS + cell] = 0.0f;
     }
   }
-  // ---- policy softmax over on-board cells (two planes)
-  lmax0 = warp_max(lmax0);
-  lmax1 = warp_max(lmax1);
-  if (lane == 0) {
-    s_red[0][warp] = lmax0;
-    s_red[1][warp] = lmax1;
-  }
-  __syncthreads();
-  if (tid < 2) {
-    float m = -INFINITY;
-    for (int w = 0; w < HEAD_THREADS / 32; w++) m = fmaxf(m, s_red[tid][w]);
-    s_stat[tid] = m;
-  }
-  __syncthreads();
-  const float m0 = s_stat[0], m1 = s_stat[1];
-  float sum0 = 0.0f, sum1 = 0.0f;
-  for (int r = tid; r < POS_ROWS; r += HEAD_THREADS) {
-    if (s_mask[r]) {
-      const float e0 = __expf(s_logit[0][r] - m0), e1 = __expf(s_logit[1][r] - m1);
-      s_logit[0][r] = e0;
-      s_logit[1][r] = e1;
-      sum0 += e0;
-      sum1 += e1;
-    }
-  }
-  sum0 = warp_sum(sum0);
-  sum1 = warp_sum(sum1);
-  __syncthreads();
-  if (lane == 0) {
-    s_red[0][warp] = sum0;
-    s_red[1][warp] = sum1;
-  }
-  __syncthreads();
-  if (tid < 2) {
-    float s = 0.0f;
-    for (int w = 0; w < HEAD_THREADS / 32; w++) s += s_red[tid][w];
-    s_stat[2 + tid] = s;
-  }
-  __syncthreads();
-  const float inv0 = 1.0f / s_stat[2], inv1 = 1.0f / s_stat[3];
-  for (int r = tid; r < POS_ROWS; r += HEAD_THREADS) {
-    const int gy = r / PITCH, x = r - gy * PITCH;
-    if (gy < 1 || x >= BOARD) continue;
-    const int cell = (gy - 1) * BOARD + x;
-    const bool on = s_mask[r] != 0;
-    out[0 * CELLS + cell] = on ? s_logit[0][r] * inv0 : 0.0f;
-    out[1 * CELLS + cell] = on ? s_logit[1][r] * inv1 : 0.0f;
-  }
-
-  // ---- pooled features: mean over on-board cells and max (g >= 0, off-board rows are 0)
+  // ---- block maxima of the two policy planes + per-warp pooling partials
   {
-    const int c = tid % HEAD_MAX_CH, grp = tid / HEAD_MAX_CH;  // 32 channels x 8 row groups
-    float s = 0.0f, mx = 0.0f, cnt = 0.0f;
-    if (c < ch) {
-      for (int r = grp; r < POS_ROWS; r += 8) {
-        if (s_mask[r]) {
-          const float gv = __bfloat162float(s_g[c >> 3][r][c & 7]);
-          s += gv;
-          mx = fmaxf(mx, gv);
-          cnt += 1.0f;
-        }
+    const float m0 = warp_max(on ? z[0] : -INFINITY), m1 = warp_max(on ? z[1] : -INFINITY);
+    const float cnt = warp_sum(on ? 1.0f : 0.0f);
+    if (lane == 0) {
+      s_red[0][warp] = m0;
+      s_red[1][warp] = m1;
+      s_cnt[warp] = cnt;
+    }
+    // channel sums / maxima over the warp's 32 rows (g >= 0 and exactly 0 off-board)
+#pragma unroll
+    for (int c = 0; c < HEAD_MAX_CH; c++) {
+      const unsigned sv = redux_add_u32(__float2uint_rn(gv[c] * 4096.0f));
+      const unsigned mv = redux_max_u32(__float_as_uint(gv[c]));
+      if (lane == c) {
+        s_psum[warp][c] = (float)sv * (1.0f / 4096.0f);
+        s_pmax[warp][c] = __uint_as_float(mv);
       }
     }
-    s_part[grp][c] = s;
-    s_part[grp][HEAD_MAX_CH + c] = mx;
-    if (c == 0) s_red[0][grp] = cnt;
   }
   __syncthreads();
-  if (tid < ch) {
-    float s = 0.0f, mx = 0.0f, cnt = 0.0f;
-    for (int g8 = 0; g8 < 8; g8++) {
-      s += s_part[g8][tid];
-      mx = fmaxf(mx, s_part[g8][HEAD_MAX_CH + tid]);
-      cnt += s_red[0][g8];
+  float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+  for (int w = 0; w < HEAD_WARPS; w++) {
+    bm0 = fmaxf(bm0, s_red[0][w]);
+    bm1 = fmaxf(bm1, s_red[1][w]);
+  }
+  const float e0 = on ? __expf(z[0] - bm0) : 0.0f, e1 = on ? __expf(z[1] - bm1) : 0.0f;
+  {
+    const float s0 = warp_sum(e0), s1 = warp_sum(e1);
+    if (lane == 0) {
+      s_red[2][warp] = s0;
+      s_red[3][warp] = s1;
     }
-    s_pool[tid] = s / cnt;
-    s_pool[ch + tid] = mx;
+  }
+  if (tid < ch) {                                        // finish the pooling while the sums settle
+    float sv = 0.0f, mv = 0.0f, cnt = 0.0f;
+#pragma unroll
+    for (int w = 0; w < HEAD_WARPS; w++) {
+      sv += s_psum[w][tid];
+      mv = fmaxf(mv, s_pmax[w][tid]);
+      cnt += s_cnt[w];
+    }
+    s_pool[tid] = sv / cnt;
+    s_pool[ch + tid] = mv;
   }
   __syncthreads();
-  if (tid < p.cv) {
-    float a = p.b_fc1[tid];
-    const float* w = p.w_fc1 + (size_t)tid * 2 * ch;
-    for (int k = 0; k < 2 * ch; k++) a = fmaf(w[k], s_pool[k], a);
-    s_hid[tid] = fmaxf(a, 0.0f);
+  float t0 = 0.0f, t1 = 0.0f;
+#pragma unroll
+  for (int w = 0; w < HEAD_WARPS; w++) {
+    t0 += s_red[2][w];
+    t1 += s_red[3][w];
+  }
+  if (cell_ok) {
+    out[0 * CELLS + cell] = e0 / t0;
+    out[1 * CELLS + cell] = e1 / t1;
+  }
+  // ---- value / score MLP: fc1 rows are read coalesced-by-row by one warp each
+  for (int j = warp; j < p.cv; j += HEAD_WARPS) {
+    const float* w = p.w_fc1 + (size_t)j * 2 * ch;
+    float a = 0.0f;
+    for (int k = lane; k < 2 * ch; k += 32) a = fmaf(w[k], s_pool[k], a);
+    a = warp_sum(a);
+    if (lane == 0) s_hid[j] = fmaxf(a + p.b_fc1[j], 0.0f);
   }
   __syncthreads();
-  if (tid < 3) {
-    float a = p.b_fc2[tid];
-    const float* w = p.w_fc2 + (size_t)tid * p.cv;
-    for (int k = 0; k < p.cv; k++) a = fmaf(w[k], s_hid[k], a);
-    out[6 * CELLS + tid] = (tid == 0) ? 1.0f / (1.0f + __expf(-a)) : a;
+  if (warp < 3) {
+    const float* w = p.w_fc2 + (size_t)warp * p.cv;
+    float a = 0.0f;
+    for (int k = lane; k < p.cv; k += 32) a = fmaf(w[k], s_hid[k], a);
+    a = warp_sum(a);
+    if (lane == 0) {
+      a += p.b_fc2[warp];
+      out[6 * CELLS + warp] = (warp == 0) ? 1.0f / (1.0f + __expf(-a)) : a;
+    }
   }
 }
 

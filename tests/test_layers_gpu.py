@@ -32,7 +32,7 @@ def run_stages(ev, arch, T, rows, upto=None):
     return report, out, logits
 
 
-@pytest.mark.parametrize('name', ['b2c64', 'b4c128'])
+@pytest.mark.parametrize('name', ['b2c64', 'b4c128', 'b10c256'])
 def test_every_stage_matches_port(built_lib, model_dir, name):
     import maru_b200
     from oracle import net_port

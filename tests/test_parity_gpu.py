@@ -98,3 +98,18 @@ def test_live_reference_b4c128(built_lib, model_dir, name):
         print('top-1 agreement per size', rates)
     finally:
         e.close()
+
+
+def test_empty_and_ragged_batches(ev):
+    """n = 0, n = 1, n not a multiple of anything, mixed board sizes in one batch."""
+    import maru_b200
+    assert ev.forward(np.zeros((0, 11920), np.float32)).shape == (0, 2169)
+    assert ev.forward_states(np.zeros((0, 448), np.uint8)).shape == (0, 2169)
+    rows = np.concatenate([load_positions(t)[0][:7] for t in ('9', '19', '5x7', '13', '9x13')])
+    states = np.concatenate([load_positions(t)[1][:7] for t in ('9', '19', '5x7', '13', '9x13')])
+    mixed = ev.forward_states(states)
+    assert np.array_equal(mixed, ev.forward(rows))
+    for i in (0, 8, 20, 34):                                  # each position alone == in the mixed batch
+        assert np.array_equal(ev.forward_states(states[i:i + 1])[0], mixed[i])
+    with pytest.raises(ValueError):
+        ev.forward(np.zeros((3, 100), np.float32))
