@@ -11,7 +11,9 @@ independent: weak scaling, no data-path collective; NCCL only reduces the timing
   value        : evals/s with the compact records already resident in HBM (CUDA-event timed on the
                  evaluator's stream, L2 flushed between steps, max over ranks)
   e2e          : the same metric through the blocking C-ABI call with HOST buffers
-                 (maru_eval_forward_states: pinned records H2D + kernels + outputs D2H per step)
+                 (maru_eval_forward_leaves: pinned compact records H2D + kernels + move priors and
+                 value D2H per step — the transport of the substitute Evaluator.cpp; the full-row and
+                 fp32-plane contracts are timed next to it as e2e.full_rows / e2e.planes)
   roofline     : dominant kernel (3x3 implicit-GEMM conv) algorithmic FLOPs / CUDA-event duration,
                  against the measured bf16 peak of MEASURED_PEAKS.json
   cpu_baseline : the reference runtime (deepgo::Processor on libtorch CPU) on a bounded sample
@@ -272,6 +274,18 @@ def run_b200(args):
         assert rc == 0
     sync_all()
     e2e_s = time.perf_counter() - t0
+    # compact results out (maru_leaf: masked move priors + value scalars, what Evaluator::evaluate keeps,
+    # Evaluator.cpp:55-80) — the transport of the substitute Evaluator.cpp / the leaf queue
+    h_leaf = torch.empty((B, maru_b200.LEAF_SIZE), dtype=torch.float32).pin_memory()
+    for _ in range(3):
+        lib.maru_eval_forward_leaves(ev.handle, h_states.data_ptr(), h_leaf.data_ptr(), B)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        rc = lib.maru_eval_forward_leaves(ev.handle, h_states.data_ptr(), h_leaf.data_ptr(), B)
+        assert rc == 0
+    sync_all()
+    e2e_leaf_s = time.perf_counter() - t0
     # reference-shaped rows in (47 680 B/position), same call the substitute deepgo::Model makes
     d_rows = torch.empty((B, maru_b200.INPUT_SIZE), dtype=torch.float32, device=dev)
     ev.encode_planes_device(d_states.data_ptr(), d_rows.data_ptr(), B)
@@ -300,10 +314,10 @@ def run_b200(args):
     from maru_b200 import shard
     agg = shard.reduce_stats(shard.RankStats(positions=B * args.steps, batches=args.steps,
                                              device_ms=dev_ms, wall_s=t_wall), dist, dev)
-    t = torch.tensor([e2e_s, e2e_planes_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_s, e2e_planes_s, e2e_leaf_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_planes_s = [float(x) for x in t.tolist()]
+    e2e_s, e2e_planes_s, e2e_leaf_s = [float(x) for x in t.tolist()]
     dev_ms, t_wall = agg['device_ms'], agg['wall_s']
     total = agg['positions']                      # all ranks' positions / the slowest rank's time
     value = shard.evals_per_sec(agg)
@@ -356,10 +370,15 @@ def run_b200(args):
             config=dict(base_config(args, world), l2='flushed between steps (256 MiB write)',
                         launches_per_step=info.launches_per_forward, flops_per_eval=info.flops_per_eval,
                         flops_per_eval_executed=info.flops_per_eval_executed),
-            e2e=dict(value=total / e2e_s, unit=UNIT, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
-                     d2h_bytes_per_step=B * maru_b200.OUTPUT_SIZE * 4,
-                     api='maru_eval_forward_states (blocking, pinned host buffers)',
+            e2e=dict(value=total / e2e_leaf_s, unit=UNIT, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
+                     d2h_bytes_per_step=B * maru_b200.LEAF_SIZE * 4,
+                     api='maru_eval_forward_leaves (blocking, pinned host buffers): compact records in, '
+                         'move priors + value out — the transport of the substitute Evaluator.cpp',
+                     full_rows=dict(value=total / e2e_s, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
+                                    d2h_bytes_per_step=B * maru_b200.OUTPUT_SIZE * 4,
+                                    api='maru_eval_forward_states (compact records in, 2169-float rows out)'),
                      planes=dict(value=total / e2e_planes_s, h2d_bytes_per_step=B * maru_b200.INPUT_SIZE * 4,
+                                 d2h_bytes_per_step=B * maru_b200.OUTPUT_SIZE * 4,
                                  api='maru_eval_forward_planes (reference Model::forward contract)')),
             gpu_launches=info.launches_per_forward * args.steps,
             clocks=clock, roofline=roofline, cpu_baseline=cpu, kernels=table,

@@ -79,6 +79,19 @@ typedef struct maru_state {
   uint8_t move_mask[48];   /* optional: bit (y*width+x) = legal && territory==EMPTY (Evaluator.cpp:60-68) */
 } maru_state;              /* sizeof == 448 */
 
+/*
+ * Compact evaluation result: what Evaluator::evaluate keeps of the 2169-float output row
+ * (Evaluator.cpp:55-80) — the move prior of every candidate cell and the value scalars; 1456 bytes
+ * instead of 8676. prior[y*width + x] = output plane 0 at the centred model cell
+ * ((19-h)/2 + y)*19 + (19-w)/2 + x (Evaluator.cpp:57-69) when the record's move_mask allows the
+ * cell (or the record carries no mask), else exactly 0. No renormalisation (Evaluator.cpp:63-72).
+ */
+typedef struct maru_leaf {
+  float prior[361];        /* board order y*width + x; entries >= width*height are 0               */
+  float value;             /* output scalar 0: win probability of the side to move (row[2166])     */
+  float score[2];          /* output scalars 1, 2 (row[2167], row[2168])                           */
+} maru_leaf;               /* sizeof == 1456 */
+
 typedef struct maru_eval maru_eval;     /* one evaluator = one GPU, one stream, one weight replica */
 typedef struct maru_queue maru_queue;   /* leaf-batch queue over >=1 evaluators (Processor mirror)  */
 
@@ -112,9 +125,14 @@ int  maru_eval_forward_planes(maru_eval* e, const float* in, float* out, int n);
 /* s: [n] compact records; encoding happens on the GPU (K1). out: [n][2169] fp32. */
 int  maru_eval_forward_states(maru_eval* e, const maru_state* s, float* out, int n);
 
+/* s: [n] compact records in, [n] compact results out: the search's own transport (448 B up, 1456 B
+ * down per leaf instead of 47 680 / 8 676). Policy gather and masking happen in the heads kernel. */
+int  maru_eval_forward_leaves(maru_eval* e, const maru_state* s, maru_leaf* out, int n);
+
 /* ---- device-resident forwards (inputs/outputs already in HBM; used by bench `value`) -------- */
 int  maru_eval_forward_states_device(maru_eval* e, const maru_state* d_states, float* d_out, int n);
 int  maru_eval_forward_planes_device(maru_eval* e, const float* d_in, float* d_out, int n);
+int  maru_eval_forward_leaves_device(maru_eval* e, const maru_state* d_states, maru_leaf* d_out, int n);
 int  maru_eval_sync(maru_eval* e);
 void* maru_eval_stream(maru_eval* e);   /* the evaluator's cudaStream_t (for CUDA-event timing)      */
 
@@ -177,6 +195,8 @@ void maru_queue_destroy(maru_queue* q);
 int  maru_queue_execute(maru_queue* q, const float* in, float* out, int n);
 /* Same, compact records in (the path the substitute Evaluator uses). */
 int  maru_queue_execute_states(maru_queue* q, const maru_state* s, float* out, int n);
+/* Compact records in, compact results out (what the substitute Evaluator.cpp calls). */
+int  maru_queue_execute_leaves(maru_queue* q, const maru_state* s, maru_leaf* out, int n);
 
 typedef struct maru_queue_stats {
   uint64_t jobs, positions, batches;

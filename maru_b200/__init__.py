@@ -5,8 +5,8 @@ Python face of libmaru_b200.so (C ABI in include/maru_b200.h). PyTorch is import
 evaluation itself is hand-written sm_100a CUDA behind ctypes. There is no CPU fallback: if the
 shared library is missing or no B200 is visible, construction raises.
 """
-from .capi import (INPUT_SIZE, OUTPUT_SIZE, STATE_SIZE, Evaluator, LeafQueue, MaruB200Error,
+from .capi import (INPUT_SIZE, LEAF_SIZE, OUTPUT_SIZE, STATE_SIZE, Evaluator, LeafQueue, MaruB200Error,
                    Processor, lib_path, load_library)
 
-__all__ = ['INPUT_SIZE', 'OUTPUT_SIZE', 'STATE_SIZE', 'Evaluator', 'LeafQueue', 'MaruB200Error',
+__all__ = ['INPUT_SIZE', 'LEAF_SIZE', 'OUTPUT_SIZE', 'STATE_SIZE', 'Evaluator', 'LeafQueue', 'MaruB200Error',
            'Processor', 'lib_path', 'load_library']

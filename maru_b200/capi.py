@@ -16,6 +16,7 @@ import numpy as np
 INPUT_SIZE = 11920    # reference src/deepgo/config.py:48
 OUTPUT_SIZE = 2169    # reference src/deepgo/config.py:50
 STATE_SIZE = 448      # sizeof(maru_state)
+LEAF_SIZE = 364       # sizeof(maru_leaf) / 4: prior[361], value, score[2]
 FLAG_NO_GRAPH = 1
 
 
@@ -48,7 +49,8 @@ class QueueStats(C.Structure):
 # every symbol include/maru_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     'maru_eval_create', 'maru_eval_destroy', 'maru_eval_get_info', 'maru_eval_forward_planes',
-    'maru_eval_forward_states', 'maru_eval_forward_states_device',
+    'maru_eval_forward_states', 'maru_eval_forward_states_device', 'maru_eval_forward_leaves',
+    'maru_eval_forward_leaves_device', 'maru_queue_execute_leaves',
     'maru_eval_forward_planes_device', 'maru_eval_sync', 'maru_eval_stream', 'maru_encode_planes',
     'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
     'maru_eval_debug_set', 'maru_eval_debug_trace', 'maru_eval_debug_timeline', 'maru_eval_profile_states',
@@ -83,6 +85,9 @@ def load_library():
     lib.maru_eval_forward_planes.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_forward_states.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_forward_states_device.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_forward_leaves.argtypes = [vp, vp, vp, ci]
+    lib.maru_eval_forward_leaves_device.argtypes = [vp, vp, vp, ci]
+    lib.maru_queue_execute_leaves.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_forward_planes_device.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_sync.argtypes = [vp]
     lib.maru_eval_stream.argtypes = [vp]
@@ -180,6 +185,17 @@ class Evaluator:
                'maru_eval_forward_states')
         return out
 
+    def forward_leaves(self, states: np.ndarray) -> np.ndarray:
+        """[N,448] compact records -> [N,364] fp32 compact results (maru_leaf: prior[361] in board
+        order y*width+x, masked by the record's move_mask; value; score[2]) — what
+        Evaluator::evaluate keeps of the output row (Evaluator.cpp:55-80)."""
+        s = _rows(states, STATE_SIZE, np.uint8)
+        out = np.zeros((s.shape[0], LEAF_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_eval_forward_leaves(self.handle, s.ctypes.data,
+                                                           out.ctypes.data, s.shape[0]),
+               'maru_eval_forward_leaves')
+        return out
+
     def encode_planes(self, states: np.ndarray) -> np.ndarray:
         """[N,448] compact records -> [N,11920] fp32 rows, bit-exact Board::getInputs."""
         s = _rows(states, STATE_SIZE, np.uint8)
@@ -221,6 +237,10 @@ class Evaluator:
     def forward_states_device(self, d_states: int, d_out: int, n: int) -> None:
         _check(self.lib, self.lib.maru_eval_forward_states_device(self.handle, d_states, d_out, n),
                'maru_eval_forward_states_device')
+
+    def forward_leaves_device(self, d_states: int, d_out: int, n: int) -> None:
+        _check(self.lib, self.lib.maru_eval_forward_leaves_device(self.handle, d_states, d_out, n),
+               'maru_eval_forward_leaves_device')
 
     def forward_planes_device(self, d_in: int, d_out: int, n: int) -> None:
         _check(self.lib, self.lib.maru_eval_forward_planes_device(self.handle, d_in, d_out, n),
@@ -283,6 +303,14 @@ class LeafQueue:
                'maru_queue_execute_states')
         return out
 
+    def execute_leaves(self, states: np.ndarray) -> np.ndarray:
+        s = _rows(states, STATE_SIZE, np.uint8)
+        out = np.zeros((s.shape[0], LEAF_SIZE), np.float32)
+        _check(self.lib, self.lib.maru_queue_execute_leaves(self.handle, s.ctypes.data,
+                                                            out.ctypes.data, s.shape[0]),
+               'maru_queue_execute_leaves')
+        return out
+
     def stats(self) -> QueueStats:
         st = QueueStats()
         self.lib.maru_queue_get_stats(self.handle, C.byref(st))
@@ -314,6 +342,9 @@ class Processor:
 
     def execute_states(self, states: np.ndarray) -> np.ndarray:
         return self.queue.execute_states(states)
+
+    def execute_leaves(self, states: np.ndarray) -> np.ndarray:
+        return self.queue.execute_leaves(states)
 
     def close(self) -> None:
         self.queue.close()

@@ -86,6 +86,25 @@ int maru_eval_forward_states(maru_eval* e, const maru_state* s, float* out, int 
   return E(e)->forward_host(maru::KIND_STATES, s, out, n);
 }
 
+int maru_eval_forward_leaves(maru_eval* e, const maru_state* s, maru_leaf* out, int n) {
+  if (e == nullptr || s == nullptr || out == nullptr || n < 0) {
+    maru::set_error("maru_eval_forward_leaves: bad argument");
+    return 1;
+  }
+  return E(e)->forward_host(maru::KIND_LEAVES, s, out, n);
+}
+
+int maru_eval_forward_leaves_device(maru_eval* ev, const maru_state* d_states, maru_leaf* d_out, int n) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  for (int off = 0; off < n; off += e->max_batch) {
+    const int m = n - off < e->max_batch ? n - off : e->max_batch;
+    if (e->forward_device(maru::KIND_LEAVES, d_states + off, d_out + off, m)) return 1;
+  }
+  return 0;
+}
+
 int maru_eval_forward_states_device(maru_eval* ev, const maru_state* d_states, float* d_out, int n) {
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);

@@ -494,7 +494,7 @@ void Engine::clear_graphs() {
   graphs.clear();
 }
 
-int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st) {
+int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st) {
   launches_done = 0;
   {
     // per-tile completion counters start from zero in every forward (also under graph replay)
@@ -552,7 +552,9 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
   hp.b_fc1 = b_fc1;
   hp.w_fc2 = w_fc2;
   hp.b_fc2 = b_fc2;
-  hp.out = d_out;
+  hp.out = (kind == KIND_LEAVES) ? nullptr : static_cast<float*>(d_out);
+  hp.leaf = (kind == KIND_LEAVES) ? static_cast<maru_leaf*>(d_out) : nullptr;
+  hp.states = (kind == KIND_LEAVES) ? static_cast<const maru_state*>(d_in) : nullptr;
   hp.logits = d_logits;
   hp.rows_alloc = rows_alloc;
   hp.n = n;
@@ -562,15 +564,15 @@ int Engine::launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st)
   hp.pdl = (dbg_desc & 1) ? 0 : 1;
   if (dbg_stop_after >= 0) return 0;
   prof_begin("heads", 4, Ch, 6, 0, (2.0 * CELLS * Ch * 6 + 2.0 * 2 * Ch * Cv + 2.0 * Cv * 3) * n,
-             ((double)CELLS * Ch * 2 + OUT_ROW * 4.0) * n, st);
+             ((double)CELLS * Ch * 2 + (double)out_row_bytes(kind)) * n, st);
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) CK(launch_heads(hp, st));
   prof_end(st);
   return 0;
 }
 
-int Engine::launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev,
+int Engine::launch_all(int kind, const void* d_in, void* d_out, int n, const int* n_dev,
                        cudaStream_t st) {
-  if (kind == KIND_STATES) {
+  if (kind != KIND_PLANES) {
     prof_begin("encode", 0, 0, IN_PLANES, 0, 0.0,
                ((double)sizeof(maru_state) + (double)CELLS * IN_PLANES * 2.0) * n, st);
     for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
@@ -582,7 +584,7 @@ int Engine::launch_all(int kind, const void* d_in, float* d_out, int n, const in
     CK(launch_ingest_rows(static_cast<const float*>(d_in), x0.p, mask, rows_alloc, n, n_dev, st));
     prof_end(st);
   }
-  return launch_trunk(n, n_dev, d_out, st);
+  return launch_trunk(kind, d_in, d_out, n, n_dev, st);
 }
 
 static int bucket_for(int n, int max_batch) {
@@ -592,7 +594,7 @@ static int bucket_for(int n, int max_batch) {
 }
 
 // Enqueue one forward of n <= max_batch positions on `stream` (no host sync).
-int Engine::forward_device(int kind, const void* d_in, float* d_out, int n) {
+int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
   if (n <= 0) return 0;
   if (n > max_batch) {
     set_error("batch larger than max_batch");
@@ -630,20 +632,20 @@ int Engine::forward_device(int kind, const void* d_in, float* d_out, int n) {
 
 // Blocking forward on host buffers: H2D, kernels, D2H (Model::forward, Model.cpp:88-100).
 // `in` / `out` may be pageable (the reference passes stack arrays, Evaluator.cpp:48-49).
-int Engine::forward_host(int kind, const void* in, float* out, int n) {
+int Engine::forward_host(int kind, const void* in, void* out, int n) {
   std::lock_guard<std::mutex> lock(mu);
   CK(cudaSetDevice(gpu_id));
-  const size_t in_row = kind == KIND_STATES ? sizeof(maru_state) : (size_t)IN_ROW * 4;
+  const size_t in_row = in_row_bytes(kind), out_row = out_row_bytes(kind);
   for (int off = 0; off < n; off += max_batch) {
     const int m = (n - off < max_batch) ? n - off : max_batch;
     Slot& sl = slot[2];
-    void* d_in = kind == KIND_STATES ? (void*)sl.d_states : (void*)sl.d_rows;
+    void* d_in = kind != KIND_PLANES ? (void*)sl.d_states : (void*)sl.d_rows;
     CK(cudaMemcpyAsync(d_in, static_cast<const uint8_t*>(in) + (size_t)off * in_row, (size_t)m * in_row,
                        cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(sl.t0, stream));
     if (forward_device(kind, d_in, sl.d_out, m)) return 1;
     CK(cudaEventRecord(sl.t1, stream));
-    CK(cudaMemcpyAsync(out + (size_t)off * OUT_ROW, sl.d_out, (size_t)m * OUT_ROW * 4,
+    CK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + (size_t)off * out_row, sl.d_out, (size_t)m * out_row,
                        cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     float ms = 0;
@@ -657,14 +659,14 @@ int Engine::enqueue_slot(int kind, int slot_idx, int n) {
   std::lock_guard<std::mutex> lock(mu);
   CK(cudaSetDevice(gpu_id));
   Slot& sl = slot[slot_idx];
-  const size_t in_row = kind == KIND_STATES ? sizeof(maru_state) : (size_t)IN_ROW * 4;
-  void* d_in = kind == KIND_STATES ? (void*)sl.d_states : (void*)sl.d_rows;
-  const void* h_in = kind == KIND_STATES ? (const void*)sl.h_states : (const void*)sl.h_rows;
+  const size_t in_row = in_row_bytes(kind);
+  void* d_in = kind != KIND_PLANES ? (void*)sl.d_states : (void*)sl.d_rows;
+  const void* h_in = kind != KIND_PLANES ? (const void*)sl.h_states : (const void*)sl.h_rows;
   CK(cudaMemcpyAsync(d_in, h_in, (size_t)n * in_row, cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(sl.t0, stream));
   if (forward_device(kind, d_in, sl.d_out, n)) return 1;
   CK(cudaEventRecord(sl.t1, stream));
-  CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)n * OUT_ROW * 4, cudaMemcpyDeviceToHost, stream));
+  CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)n * out_row_bytes(kind), cudaMemcpyDeviceToHost, stream));
   CK(cudaEventRecord(sl.done, stream));
   return 0;
 }

@@ -31,7 +31,10 @@ struct Attn {
   ConvLayer qkv, proj;
 };
 
-enum { KIND_PLANES = 0, KIND_STATES = 1 };
+// transport of one forward: fp32 plane rows -> rows, compact records -> rows, compact records -> compact results
+enum { KIND_PLANES = 0, KIND_STATES = 1, KIND_LEAVES = 2 };
+inline size_t in_row_bytes(int kind) { return kind == KIND_PLANES ? (size_t)IN_ROW * 4 : sizeof(maru_state); }
+inline size_t out_row_bytes(int kind) { return kind == KIND_LEAVES ? sizeof(maru_leaf) : (size_t)OUT_ROW * 4; }
 
 // activation tensor: chunk-planar [C/8][rows_alloc][8] or tile-blocked [tile][C/8][128][8] (kernels.h)
 struct Act {
@@ -125,10 +128,10 @@ struct Engine {
 
   int conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int n, const int* n_dev,
            cudaStream_t st);
-  int launch_trunk(int n, const int* n_dev, float* d_out, cudaStream_t st);
-  int launch_all(int kind, const void* d_in, float* d_out, int n, const int* n_dev, cudaStream_t st);
-  int forward_device(int kind, const void* d_in, float* d_out, int n);  // async on `stream`
-  int forward_host(int kind, const void* in, float* out, int n);        // blocking, host buffers
+  int launch_trunk(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st);
+  int launch_all(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st);
+  int forward_device(int kind, const void* d_in, void* d_out, int n);  // async on `stream`
+  int forward_host(int kind, const void* in, void* out, int n);        // blocking, host buffers
   // leaf-queue pipeline: inputs already gathered in slot.h_*; enqueue H2D + forward + D2H (async)
   int enqueue_slot(int kind, int slot_idx, int n);
   int wait_slot(int slot_idx, float* device_ms);

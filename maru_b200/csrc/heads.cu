@@ -7,6 +7,8 @@
 //   planes 2..4: 3-way territory softmax per cell, times M
 //   plane 5    : sigmoid, times M
 //   scalars    : fc2(relu(fc1([mean_onboard(g), max(g)])));  [0] through sigmoid
+// and / or the compact result maru_leaf (masked move priors + the 3 scalars, 1456 B) that
+// Evaluator::evaluate actually keeps (Evaluator.cpp:55-80).
 // One CTA per position.  Algorithmic bytes per position: 361*Ch*2 read + 2169*4 written.
 #include "kernels.h"
 
@@ -97,12 +99,12 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
       for (int k = 0; k < 6; k++) z[k] = fmaf(s_wp[k][c], gv[c], z[k]);
     }
   }
-  float* out = p.out + (size_t)pos * OUT_ROW;
-  if (cell_ok) {
-    if (p.logits != nullptr) {
-      p.logits[((size_t)pos * 2 + 0) * CELLS + cell] = z[0];
-      p.logits[((size_t)pos * 2 + 1) * CELLS + cell] = z[1];
-    }
+  float* out = (p.out != nullptr) ? p.out + (size_t)pos * OUT_ROW : nullptr;
+  if (cell_ok && p.logits != nullptr) {
+    p.logits[((size_t)pos * 2 + 0) * CELLS + cell] = z[0];
+    p.logits[((size_t)pos * 2 + 1) * CELLS + cell] = z[1];
+  }
+  if (cell_ok && out != nullptr) {
     if (on) {
       const float tm = fmaxf(z[2], fmaxf(z[3], z[4]));
       const float e2 = __expf(z[2] - tm), e3 = __expf(z[3] - tm), e4 = __expf(z[4] - tm);
@@ -171,9 +173,24 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
     t0 += s_red[2][w];
     t1 += s_red[3][w];
   }
-  if (cell_ok) {
+  if (cell_ok && out != nullptr) {
     out[0 * CELLS + cell] = e0 / t0;
     out[1 * CELLS + cell] = e1 / t1;
+  }
+  if (p.leaf != nullptr) {
+    // Compact result (Evaluator.cpp:55-72): the prior of board cell (bx,by) is output plane 0 at the
+    // centred model cell; cells the host marked illegal / fixed territory get exactly 0. The same
+    // division as the full row, so the two transports agree bit for bit.
+    maru_leaf* lf = p.leaf + pos;
+    const maru_state* st = p.states + pos;
+    const int w = st->width, h = st->height;
+    if (cell_ok && on) {
+      const int bx = x - (BOARD - w) / 2, by = (gy - 1) - (BOARD - h) / 2;
+      const int idx = by * w + bx;
+      const bool allowed = !(st->flags & MARU_STATE_HAS_MASK) || ((st->move_mask[idx >> 3] >> (idx & 7)) & 1u);
+      lf->prior[idx] = allowed ? e0 / t0 : 0.0f;
+    }
+    if (tid >= w * h && tid < CELLS) lf->prior[tid] = 0.0f;   // tail of the fixed-size record
   }
   // ---- value / score MLP: fc1 rows are read coalesced-by-row by one warp each
   for (int j = warp; j < p.cv; j += HEAD_WARPS) {
@@ -191,7 +208,12 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
     a = warp_sum(a);
     if (lane == 0) {
       a += p.b_fc2[warp];
-      out[6 * CELLS + warp] = (warp == 0) ? 1.0f / (1.0f + __expf(-a)) : a;
+      const float v = (warp == 0) ? 1.0f / (1.0f + __expf(-a)) : a;
+      if (out != nullptr) out[6 * CELLS + warp] = v;
+      if (p.leaf != nullptr) {
+        if (warp == 0) p.leaf[pos].value = v;
+        else p.leaf[pos].score[warp - 1] = v;
+      }
     }
   }
 }

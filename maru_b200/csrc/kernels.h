@@ -104,7 +104,9 @@ struct HeadParams {
   const float* b_fc1;        // [Cv]
   const float* w_fc2;        // [3][Cv]
   const float* b_fc2;        // [3]
-  float* out;                // [n][2169]
+  float* out;                // [n][2169] reference rows, or nullptr
+  maru_leaf* leaf;           // [n] compact results (masked move priors + value scalars), or nullptr
+  const maru_state* states;  // records of the batch (board geometry + move_mask), needed with `leaf`
   float* logits;             // optional [n][2][361] pre-softmax policy logits
   int rows_alloc;
   int n;

@@ -30,7 +30,7 @@ namespace maru {
 struct Job {
   int kind;
   const void* in;
-  float* out;
+  void* out;
   int n;
   int rc = 0;
   std::string err;
@@ -91,10 +91,11 @@ static void complete(maru_queue* q, Worker* w, InFlight& f) {
   int rc = w->e->wait_slot(f.slot, &ms);
   const std::string err = rc ? g_last_error : std::string();
   if (!rc) {
-    const float* src = w->e->slot[f.slot].h_out;
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(w->e->slot[f.slot].h_out);
+    const size_t row = out_row_bytes(f.jobs.empty() ? KIND_STATES : f.jobs[0]->kind);
     for (Job* j : f.jobs) {
-      std::memcpy(j->out, src, (size_t)j->n * OUT_ROW * sizeof(float));
-      src += (size_t)j->n * OUT_ROW;
+      std::memcpy(j->out, src, (size_t)j->n * row);
+      src += (size_t)j->n * row;
     }
   }
   {
@@ -165,7 +166,7 @@ static void worker_main(maru_queue* q, Worker* w) {
     // gather into the free pinned slot while the previous batch (other slot) is still on the GPU
     Slot& sl = w->e->slot[next_slot];
     const int kind = jobs[0]->kind;
-    if (kind == KIND_STATES) {
+    if (kind != KIND_PLANES) {
       maru_state* dst = sl.h_states;
       for (Job* j : jobs) {
         std::memcpy(dst, j->in, (size_t)j->n * sizeof(maru_state));
@@ -193,7 +194,7 @@ static void worker_main(maru_queue* q, Worker* w) {
   }
 }
 
-static int queue_execute(maru_queue* q, int kind, const void* in, float* out, int n) {
+static int queue_execute(maru_queue* q, int kind, const void* in, void* out, int n) {
   if (q == nullptr || in == nullptr || out == nullptr || n < 0) {
     set_error("maru_queue_execute: bad argument");
     return 1;
@@ -283,6 +284,10 @@ int maru_queue_execute(maru_queue* q, const float* in, float* out, int n) {
 
 int maru_queue_execute_states(maru_queue* q, const maru_state* s, float* out, int n) {
   return maru::queue_execute(q, maru::KIND_STATES, s, out, n);
+}
+
+int maru_queue_execute_leaves(maru_queue* q, const maru_state* s, maru_leaf* out, int n) {
+  return maru::queue_execute(q, maru::KIND_LEAVES, s, out, n);
 }
 
 int maru_queue_get_stats(maru_queue* q, maru_queue_stats* st) {

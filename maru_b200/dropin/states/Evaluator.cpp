@@ -6,7 +6,8 @@
 //   * value = 2 p - 1 of output scalar 0, negated when White is to move           (Evaluator.cpp:75-80)
 // What changes is the transport: instead of expanding 11 920 floats on the host (Board::getInputs)
 // the position is captured as a 448-byte maru_state through the Board's public getters and the
-// planes are built by the K1 kernel on the GPU.
+// planes are built by the K1 kernel on the GPU; the result comes back as a 1456-byte maru_leaf
+// (priors of the candidate cells + value) instead of the 2169-float row.
 #include "Evaluator.h"
 
 #include "state_from_board.h"
@@ -34,18 +35,19 @@ void Evaluator::evaluate(Board* board, int32_t color) {
 
   maru_state state;
   maru_b200::state_from_board(board, color, _komi, _rule, _superko, /*with_move_mask=*/true, &state);
-  float result[MODEL_OUTPUT_SIZE];
-  _processor->executeStates(&state, result, 1);
+  // The legal / non-territory filter (Evaluator.cpp:60-68) does not depend on the network, so it is
+  // taken BEFORE the evaluation and travels in the record; the heads kernel gathers the priors of
+  // exactly those cells (board order) next to the value scalars: 1456 B back instead of 8676 B.
+  maru_leaf leaf;
+  _processor->executeLeaves(&state, &leaf, 1);
 
   const int32_t w = state.width, h = state.height;
-  const int32_t left = (MODEL_SIZE - w) / 2, top = (MODEL_SIZE - h) / 2;
   for (int32_t cell = 0; cell < w * h; cell++) {
     if ((state.move_mask[cell >> 3] >> (cell & 7)) & 1u) {
-      const int32_t x = cell % w, y = cell / w;
-      _policies.emplace_back(x, y, result[(top + y) * MODEL_SIZE + (left + x)], 0);
+      _policies.emplace_back(cell % w, cell / w, leaf.prior[cell], 0);
     }
   }
-  const float win = result[MODEL_PREDICTIONS * MODEL_SIZE * MODEL_SIZE];
+  const float win = leaf.value;
   _value = (color == WHITE) ? 1.0f - 2.0f * win : 2.0f * win - 1.0f;
   _evaluated = true;
 }

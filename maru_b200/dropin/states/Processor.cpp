@@ -17,6 +17,7 @@ struct Processor::Api {
   void (*queue_destroy)(void*) = nullptr;
   int (*queue_execute)(void*, const float*, float*, int) = nullptr;
   int (*queue_execute_states)(void*, const maru_state*, float*, int) = nullptr;
+  int (*queue_execute_leaves)(void*, const maru_state*, maru_leaf*, int) = nullptr;
   const char* (*last_error)(void) = nullptr;
 
   template <class F>
@@ -34,6 +35,7 @@ struct Processor::Api {
     bind(queue_destroy, "maru_queue_destroy");
     bind(queue_execute, "maru_queue_execute");
     bind(queue_execute_states, "maru_queue_execute_states");
+    bind(queue_execute_leaves, "maru_queue_execute_leaves");
     bind(last_error, "maru_last_error");
   }
 };
@@ -75,6 +77,11 @@ void Processor::execute(float* inputs, float* outputs, int32_t size) {
 
 void Processor::executeStates(const maru_state* states, float* outputs, int32_t size) {
   if (_api->queue_execute_states(_queue, states, outputs, size) != 0)
+    throw std::runtime_error(_api->last_error());
+}
+
+void Processor::executeLeaves(const maru_state* states, maru_leaf* leaves, int32_t size) {
+  if (_api->queue_execute_leaves(_queue, states, leaves, size) != 0)
     throw std::runtime_error(_api->last_error());
 }
 

@@ -1,7 +1,8 @@
 // Substitute for the reference's deepgo::Processor (reference src/deepgo/native/cpp/Processor.h:11-45)
 // for the COMPACT-RECORD variant of the drop-in: same constructor and execute() as the reference, plus
-// executeStates() which the substitute Evaluator.cpp uses so that leaves cross PCIe as 448-byte
-// maru_state records instead of 47 680-byte fp32 rows.  Backed by the leaf-batch queue of
+// executeStates() / executeLeaves(); the substitute Evaluator.cpp uses the latter so that leaves cross
+// PCIe as 448-byte maru_state records up (instead of 47 680-byte fp32 rows) and 1456-byte maru_leaf
+// results down (instead of 8 676-byte rows).  Backed by the leaf-batch queue of
 // libmaru_b200.so (maru_queue_*), so deepgo::Executor / ExecutorJob / Model are not needed at all.
 #pragma once
 
@@ -40,6 +41,8 @@ class Processor {
   void execute(float* inputs, float* outputs, int32_t size);
   // added: compact records in, same outputs
   void executeStates(const maru_state* states, float* outputs, int32_t size);
+  // added: compact records in, compact results out (masked move priors + value, 1456 B per leaf)
+  void executeLeaves(const maru_state* states, maru_leaf* leaves, int32_t size);
 
  private:
   struct Api;
