@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 // v2: tcgen05 / TMEM attention for head_dim 32.
 //
 // One CTA = (position, head), two CTAs co-resident per SM (256 TMEM columns, ~113 KB smem each).
-// The 4 query tiles x 5 key parts (400 padded keys = 5 x 80) form one linear sequence of 20 steps:
+// The 3 query tiles x 5 key parts (400 padded keys = 5 x 80) form one linear sequence of 15 steps:
 //     S  = Q K^T          tcgen05.mma  M=128, N=80, K=32    (Q, K: K-major chunk-planar images)
 //     P  = exp2(S - c_i)  one TMEM lane (= query row) per thread, bf16 to shared memory
 //     O += P [V | 1]      tcgen05.mma  M=128, N=48, K=80    (V read as an MN-major B operand; the
@@ -217,7 +217,10 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 // softmax is shift invariant, p <= 1 cannot overflow, and because V rows and the ones column of
 // off-board keys are zero, the key mask costs nothing in the inner loop and the key parts are
 // independent (no online rescaling of O).
-// Query tiles start at rows 0, 128, 256 and 272; in the last one only rows 384..399 are new.
+// Query tiles start at padded rows 20, 148 and 276: row 20 is the first real board row (rows 0..19 are
+// the position's top halo, whose output stays at the zeros the buffer was created with), and the 380
+// rows 20..399 fit 3 tiles of 128 (rows 400..403 of the last tile belong to the next position's halo
+// or to the tail rows: they are computed and dropped).
 // =============================================================================================
 constexpr int A2_SM_WARPS = 8;              // warps 0..7 softmax/epilogue: lane group = w & 3, group = w >> 2
 constexpr int A2_WARPS = A2_SM_WARPS + 1;   // warp 8: control (bulk loads + MMA issue)
@@ -228,7 +231,8 @@ constexpr int A2_K_BYTES = A2_DCH * A2_PLANE;
 constexpr int A2_V_BYTES = (A2_DCH + 1) * A2_PLANE;   // + ones plane; the 6th plane aliases P (unused cols)
 constexpr int A2_PN = 80;                   // keys per step
 constexpr int A2_NP = POS_ROWS / A2_PN;     // 5 parts
-constexpr int A2_NT = 4;                    // query tiles
+constexpr int A2_NT = 3;                    // query tiles
+constexpr int A2_Q0 = PITCH;                // first query row: skip the top halo row of the position
 constexpr int A2_STEPS = A2_NT * A2_NP;
 constexpr int A2_P_BYTES = (A2_PN / 8) * TILE_M * 16; // 20 480 per buffer
 constexpr int A2_Q_BYTES = A2_DCH * TILE_M * 16;
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     // =========================== control warp: bulk loads + MMA issue ===========================
     auto load_q = [&](int tile) {
       const int buf = tile & 1;
-      const int r0 = (tile == 3) ? 272 : tile * TILE_M;
+      const int r0 = A2_Q0 + tile * TILE_M;
       mbar_expect_tx(&q_full[buf], A2_Q_BYTES);
       for (int c = 0; c < A2_DCH; c++)
         bulk_load_1d(s_q + buf * A2_Q_BYTES + c * TILE_M * 16,
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     // O / l, query mask, store; both groups take part, each owns 16 of the head's 32 channels
     auto epilogue = [&](int tile) {
       const int ob = tile & 1;
-      const int row = ((tile == 3) ? 272 : tile * TILE_M) + trow;
+      const int row = A2_Q0 + tile * TILE_M + trow;
       mbar_wait(&o_full[ob], (tile >> 1) & 1);
       tc_fence_after();
       uint32_t o[16];
@@ -422,8 +426,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
-      const bool write = (tile < 3) ? true : (row >= 384);
-      if (write) {
+      if (row < POS_ROWS) {
         const bool on = s_mask[row] != 0;
         const float inv = on ? 1.0f / __uint_as_float(lbits) : 0.0f;
 #pragma unroll
@@ -447,10 +450,9 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     for (int step = grp; step < A2_STEPS; step += 2) {
       const int tile = step / A2_NP;
       const int buf = tile & 1;
-      const bool active = (tile < 3) || (lg == 3);          // tile 3: only rows 384..399 are new
       if (tile != c_tile) {                                 // new tile: shift c_i of this row
         c_tile = tile;
-        if (active) {
+        {
           mbar_wait(&q_full[buf], (tile >> 1) & 1);
           float ss = 0.0f;
 #pragma unroll
@@ -468,7 +470,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       tc_fence_after();
       // s_full(step) was committed after PV(step-2) and, for step >= 5*tile+1, after the last PV of
       // the previous tile: its O is complete, the epilogue does not stall
-      if (active) {
+      {
         const uint32_t t_s = t_lane + grp * A2_PN;
         uint8_t* pb = s_p + grp * A2_P_BYTES;
         // software pipelined: the next tcgen05.ld is in flight while this block's exps run
