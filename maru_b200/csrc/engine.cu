@@ -318,7 +318,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     flops_alg += 2 * T * c * Ch + 2 * T * Ch * 6 + 2.0 * (2 * Ch) * Cv + 2.0 * Cv * 3;
     flops_exec = 2 * Tp * STEM_CIN * c * 9;
     flops_exec += blocks * (2 * (2 * Tp * c * (c / 2)) + 4 * (2 * Tp * (c / 2) * (c / 2) * 9));
-    flops_exec += n_attn * (2 * Tp * c * 3 * c + 4 * Tp * Tp * c + 2 * Tp * c * c);
+    flops_exec += n_attn * (2 * Tp * c * 3 * c + 4 * 384.0 * Tp * c + 2 * Tp * c * c);   // 3 query tiles x 400 keys
     flops_exec += 2 * Tp * c * Ch + 2 * T * Ch * 6 + 2.0 * (2 * Ch) * Cv + 2.0 * Cv * 3;
   }
   launches_per_forward = 1 + 1 + blocks * 6 + n_attn * 3 + 2;
