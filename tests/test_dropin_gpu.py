@@ -108,3 +108,30 @@ def test_compact_record_dropin_matches_plane_dropin(libs, built_lib, model_dir):
     assert np.array_equal(pb.execute(rows[:8]), pa.execute(rows[:8]))
     pa.close()
     pb.close()
+
+
+def test_selfplay_scheduler_gumbel_root_over_reference_search(libs, built_lib, model_dir):
+    """Row f1: G concurrent games of the reference MCTS, sequential halving at the root through the
+    reference's equally / width / noise hooks (Node.cpp:71-225), one leaf-batch queue for all games."""
+    from maru_b200 import selfplay
+    from oracle import ref
+    if not ref.available('dropin_states'):
+        pytest.skip('oracle/_ref/libmaru_ref_dropin_states.so not present')
+    proc = ref.RefProcessor(str(model_dir('b2c64')), gpus=[0], batch_size=64, kind='dropin_states')
+    players = []
+
+    def make(_g):
+        players.append(ref.RefPlayer(proc, threads=2, width=9, height=9))
+        return players[-1]
+    sched = selfplay.SelfPlayScheduler(make, n_games=6, visits=24, max_moves=3, root='gumbel', width=8,
+                                       noise=1.0)
+    st = sched.run()
+    assert len(sched.records) == 6 and st.batches == 18
+    for rec in sched.records:
+        assert len(rec.moves) == 3 and len(set(rec.moves)) == 3          # three distinct legal points
+        assert all(0 <= x < 9 and 0 <= y < 9 for x, y in rec.moves)
+        assert rec.visits >= 24                                          # >= one full budget of new descents
+    assert st.visits == sum(r.visits for r in sched.records) and st.wall_s > 0
+    for p in players:
+        p.close()
+    proc.close()
