@@ -241,15 +241,40 @@ constexpr int A2_TMEM_COLS = 256;
 constexpr int A2_O_COL = 2 * A2_PN;         // O buffers at columns 160 and 208
 constexpr int A2_NV = 48;                   // V columns (32) + ones + padding to a multiple of 16
 
-// 16 S columns -> 16 probabilities -> two 16-byte P chunks of this row
+// exp2 on the FMA / ALU pipes for x <= 0: round-to-nearest split x = n + f, |f| <= 0.5, degree-3 minimax
+// 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), exponent added as an integer.
+// The MUFU pipe (16 ex2 per clock per SM) is the busiest pipe of this kernel (ncu: 60 %); moving a
+// share of the exponentials off it lets both pipes work in parallel.
+__device__ __forceinline__ float exp2_fma(float x) {
+  x = fmaxf(x, -120.0f);
+  const float t = x + 12582912.0f;            // 1.5 * 2^23: n lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);
+  float p = fmaf(f, 0.05517162f, 0.24261113f);
+  p = fmaf(p, f, 0.69326097f);
+  p = fmaf(p, f, 0.99992806f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// 16 S columns -> 16 probabilities -> two 16-byte P chunks of this row. POLY: the second chunk's
+// exponentials run on the FMA pipe instead of the MUFU.
+// which of the 5 exp_store16 calls of a step use the FMA-pipe exponential for their second chunk
+// (measured per layer at batch 256, share of the exps on the FMA pipe: 0 % 65.7 us, 10 % 65.0, 20 % 63.0,
+// 30 % 61.7, 40 % 65.1, 50 % 67.0)
+#ifndef MARU_ATT_POLY_MASK
+#define MARU_ATT_POLY_MASK 0x15
+#endif
+constexpr int A2_POLY_MASK = MARU_ATT_POLY_MASK;
+
+template <bool POLY>
 __device__ __forceinline__ void exp_store16(const uint32_t* v, float c, uint8_t* s_p, int chunk, int trow) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 4; e++)
-      o[e] = pack_bf16x2(ex2_approx(__uint_as_float(v[h * 8 + 2 * e]) - c),
-                         ex2_approx(__uint_as_float(v[h * 8 + 2 * e + 1]) - c));
+    for (int e = 0; e < 4; e++) {
+      const float x0 = __uint_as_float(v[h * 8 + 2 * e]) - c, x1 = __uint_as_float(v[h * 8 + 2 * e + 1]) - c;
+      o[e] = (POLY && h == 1) ? pack_bf16x2(exp2_fma(x0), exp2_fma(x1)) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+    }
     *reinterpret_cast<uint4*>(s_p + ((chunk + h) * TILE_M + trow) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
@@ -479,14 +504,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         tmem_ld32(t_s, va);
         tmem_ld_wait();
         tmem_ld32(t_s + 32, vb);
-        exp_store16(va, c, pb, 0, trow);
-        exp_store16(va + 16, c, pb, 2, trow);
+        exp_store16<(A2_POLY_MASK >> 0) & 1>(va, c, pb, 0, trow);
+        exp_store16<(A2_POLY_MASK >> 1) & 1>(va + 16, c, pb, 2, trow);
         tmem_ld_wait();
         tmem_ld16(t_s + 64, va);
-        exp_store16(vb, c, pb, 4, trow);
-        exp_store16(vb + 16, c, pb, 6, trow);
+        exp_store16<(A2_POLY_MASK >> 2) & 1>(vb, c, pb, 4, trow);
+        exp_store16<(A2_POLY_MASK >> 3) & 1>(vb + 16, c, pb, 6, trow);
         tmem_ld_wait();
-        exp_store16(va, c, pb, 8, trow);
+        exp_store16<(A2_POLY_MASK >> 4) & 1>(va, c, pb, 8, trow);
       }
       fence_async_smem();     // P visible to the async proxy
       tc_fence_before();
