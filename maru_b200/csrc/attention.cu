@@ -400,6 +400,9 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       // the last QK of this tile completed before p_full(step): its Q buffer can take tile+2
       if (part == A2_NP - 1 && tile + 2 < A2_NT && elect_one()) load_q(tile + 2);
       __syncwarp();
+      // QK(step+2) is issued AFTER PV(step): its commit (s_full) then also covers PV(step), which is
+      // what allows the softmax group to overwrite P[sb] at step+2. (Issuing it earlier, as soon as S[sb]
+      // had been read out, was tried: no gain, and it needs an extra P-free barrier.)
       if (step + 2 < A2_STEPS) issue_qk(step + 2);
     }
   } else {
@@ -407,7 +410,8 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     const int lg = warp & 3, grp = warp >> 2;               // grp g handles steps s with (s & 1) == g
     const int trow = lg * 32 + lane;                        // TMEM lane = row within the tile
     const int st = threadIdx.x;                             // 0..255
-    for (int r = st; r < POS_ROWS; r += 256) s_mask[r] = p.mask[(size_t)pos * POS_ROWS + r];
+    if (st < POS_ROWS / 16)                                 // 400 mask bytes = 25 16-byte vectors
+      reinterpret_cast<uint4*>(s_mask)[st] = reinterpret_cast<const uint4*>(p.mask + (size_t)pos * POS_ROWS)[st];
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
     // ones plane of V: 1.0 for on-board keys, 0 otherwise (row sums + key mask in one column)
     for (int r = st; r < POS_ROWS; r += 256)
