@@ -157,7 +157,10 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 /* Debug knobs. key 0: stop the launch sequence after `value` trunk launches (<0: run everything;
  * the heads then do not run). key 1: bit0 = disable programmatic dependent launch (A/B timing), bit2 = use the legacy
  * mma.sync attention kernel instead of the tcgen05 one (A/B), bit3 = enable the experimental
- * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower). */
+ * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower),
+ * bit5 = run consecutive conv layers as persistent multi-layer chain kernels with grid barriers
+ * (conv_chain.cu; correct, measured slower than one PDL launch per layer), bit6 = with bit5: record
+ * per-layer stamps (maru_eval_debug_stamps). */
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
 #define MARU_DBG_TRACE_LAUNCH 2       /* index of the trunk launch whose pipeline is traced (-1: off) */
@@ -166,6 +169,10 @@ int  maru_eval_debug_set(maru_eval* e, int key, int value);
 /* [64 launches][first CTA, last CTA][8] ns stamps: entry, prologue done, dependency resolved, first
  * operands landed, first accumulator ready, exit. */
 int  maru_eval_debug_timeline(maru_eval* e, long long* out);
+/* Persistent chain kernels (debug key 1 bit6 set): [128 layers][4] ns stamps of CTA 0 — layer start,
+ * first operands landed, CTA done with the layer, weights landed — chains back to back, each followed
+ * by one [end, 0, 0, 0] row. */
+int  maru_eval_debug_stamps(maru_eval* e, long long* out);
 /* clock64 stamps of the traced conv launch: [n_ctas][32 tiles][8] = producer {wait,issue}, MMA warp
  * {wait start, operands ready, issued}, epilogue warp {wait start, accumulator ready, done}. */
 int  maru_eval_debug_trace(maru_eval* e, long long* out, int n_ctas);

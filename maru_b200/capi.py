@@ -53,7 +53,7 @@ ABI_SYMBOLS = [
     'maru_eval_forward_leaves_device', 'maru_queue_execute_leaves',
     'maru_eval_forward_planes_device', 'maru_eval_sync', 'maru_eval_stream', 'maru_encode_planes',
     'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
-    'maru_eval_debug_set', 'maru_eval_debug_trace', 'maru_eval_debug_timeline', 'maru_eval_profile_states',
+    'maru_eval_debug_set', 'maru_eval_debug_trace', 'maru_eval_debug_timeline', 'maru_eval_debug_stamps', 'maru_eval_profile_states',
     'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
     'maru_queue_get_stats', 'maru_last_error', 'maru_abi_version',
 ]
@@ -98,6 +98,7 @@ def load_library():
     lib.maru_eval_debug_set.argtypes = [vp, ci, ci]
     lib.maru_eval_debug_trace.argtypes = [vp, vp, ci]
     lib.maru_eval_debug_timeline.argtypes = [vp, vp]
+    lib.maru_eval_debug_stamps.argtypes = [vp, vp]
     lib.maru_eval_profile_states.argtypes = [vp, vp, vp, ci, C.POINTER(LaunchTime), ci,
                                              C.POINTER(ci)]
     lib.maru_eval_debug_policy_logits.argtypes = [vp, vp, ci]
@@ -221,6 +222,11 @@ class Evaluator:
         out = np.zeros((64, 2, 8), np.int64)
         _check(self.lib, self.lib.maru_eval_debug_timeline(self.handle, out.ctypes.data),
                'maru_eval_debug_timeline')
+        return out
+
+    def debug_stamps(self) -> np.ndarray:
+        out = np.zeros((128, 4), np.int64)
+        _check(self.lib, self.lib.maru_eval_debug_stamps(self.handle, out.ctypes.data), 'maru_eval_debug_stamps')
         return out
 
     def debug_set(self, key: int, value: int) -> None:

@@ -206,6 +206,15 @@ int maru_eval_debug_timeline(maru_eval* ev, long long* out) {
   return 0;
 }
 
+int maru_eval_debug_stamps(maru_eval* ev, long long* out) {
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  CKC(cudaSetDevice(e->gpu_id));
+  CKC(cudaStreamSynchronize(e->stream));
+  CKC(cudaMemcpy(out, e->d_stamps, 512 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);

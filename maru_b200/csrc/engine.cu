@@ -165,6 +165,55 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
   CK(cudaMemcpy(L.b, pk.data.data() + b->offset, (size_t)cout * 4, cudaMemcpyHostToDevice));
   allocs.push_back(L.w);
   allocs.push_back(L.b);
+
+  // chain blob: per channel group [TAPS][KCH][nt][8] weights followed by the bias operand of the bias
+  // MMA ([2 k-chunks][nt rows][8]: (hi, lo, 0...) in chunk 0) -> one bulk copy per CTA and layer
+  const int cands[4] = {L.nt, 128, 64, 32};
+  for (int nt : cands) {
+    if (cout % nt == 0 && conv_chain_supports(cin, nt, taps)) {
+      L.nt_chain = nt;
+      break;
+    }
+  }
+  if (L.nt_chain > 0) {
+    const int nt = L.nt_chain, groups = cout / nt;
+    const size_t wb = (size_t)taps * cin * nt * 2, bb = (size_t)2 * nt * 16;
+    std::vector<uint8_t> blob((wb + bb) * groups, 0);
+    const float* bias = reinterpret_cast<const float*>(pk.data.data() + b->offset);
+    auto bf16_rn = [](float f) -> uint16_t {
+      uint32_t u;
+      memcpy(&u, &f, 4);
+      if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);     // inf / nan
+      u += 0x7FFFu + ((u >> 16) & 1u);
+      return (uint16_t)(u >> 16);
+    };
+    auto bf16_to_f = [](uint16_t h) -> float {
+      uint32_t u = (uint32_t)h << 16;
+      float f;
+      memcpy(&f, &u, 4);
+      return f;
+    };
+    for (int g = 0; g < groups; g++) {
+      uint16_t* wdst = reinterpret_cast<uint16_t*>(blob.data() + (wb + bb) * g);
+      for (int t = 0; t < taps; t++)
+        for (int c8 = 0; c8 < kch; c8++)
+          for (int r = 0; r < nt; r++)
+            for (int e = 0; e < 8; e++)
+              wdst[(((size_t)t * kch + c8) * nt + r) * 8 + e] =
+                  src[((size_t)t * cout + g * nt + r) * cin + c8 * 8 + e];
+      uint16_t* bdst = reinterpret_cast<uint16_t*>(blob.data() + (wb + bb) * g + wb);
+      for (int r = 0; r < nt; r++) {
+        const float bv = bias[g * nt + r];
+        const uint16_t hi = bf16_rn(bv);
+        const uint16_t lo = bf16_rn(bv - bf16_to_f(hi));
+        bdst[(size_t)r * 8 + 0] = hi;
+        bdst[(size_t)r * 8 + 1] = lo;
+      }
+    }
+    CK(cudaMalloc(&L.blob, blob.size()));
+    CK(cudaMemcpy(L.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    allocs.push_back(L.blob);
+  }
   return 0;
 }
 
@@ -214,6 +263,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   }
   sm_count = prop.multiProcessorCount;
   CK(configure_conv_gemm());
+  CK(configure_conv_chain());
   CK(configure_attention());
   CK(configure_misc_kernels());
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -279,6 +329,12 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     CK(cudaMalloc(&d_flags, flags_bytes));
     CK(cudaMemset(d_flags, 0, flags_bytes));
     allocs.push_back(d_flags);
+    CK(cudaMalloc(&d_sync, 256 * sizeof(unsigned)));
+    CK(cudaMemset(d_sync, 0, 256 * sizeof(unsigned)));
+    allocs.push_back(d_sync);
+    CK(cudaMalloc(&d_stamps, 512 * sizeof(long long)));
+    CK(cudaMemset(d_stamps, 0, 512 * sizeof(long long)));
+    allocs.push_back(d_stamps);
     for (int i = 0; i < 7; i++) acts[i]->flags = d_flags + (size_t)i * n_tiles_max;
   }
   CK(cudaMalloc(&mask, (size_t)rows_alloc));
@@ -390,7 +446,7 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   p.in_flags = (use_flags && in.flagged) ? in.flags : nullptr;
   p.in_expect = in.version;
   p.out_flags = use_flags ? out.flags : nullptr;
-  p.trace = (dbg_trace_launch >= 0 && launches_done == dbg_trace_launch) ? d_trace : nullptr;
+  p.trace = (dbg_trace_launch >= 0 && launches_done == dbg_trace_launch && !(dbg_desc & 64)) ? d_trace : nullptr;
   p.timeline = (dbg_timeline && launches_done < 64) ? d_timeline : nullptr;
   p.seq = launches_done;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
@@ -404,6 +460,57 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
     const double by = T * (cin_alg + L.cout + (res ? L.cout : 0)) * 2.0 + (double)L.taps * L.cin * L.cout * 2.0;
     prof_begin(L.name.c_str(), L.taps == 9 ? 1 : 2, L.cin, L.cout, L.taps, fl, by, st);
   }
+  // Chain mode (EXPERIMENT, debug bit 5; measured slower, DESIGN.md "what did not work"): consecutive
+  // conv layers are collected and launched as ONE persistent kernel by flush_chain(). The default is one
+  // PDL launch per layer; layers whose weights leave no room for two pipeline stages next to the
+  // chain's always run that way.
+  const bool chainable = prof == nullptr && !use_flags && (dbg_desc & 32) && p.trace == nullptr &&
+                         p.timeline == nullptr && L.nt_chain > 0;
+  if (chainable) {
+    for (int attempt = 0; attempt < 2; attempt++) {
+      const int blob = (conv_chain_blob_bytes(L.cin, L.nt_chain, L.taps) + 1023) & ~1023;
+      const int w_new = blob > pending_w ? blob : pending_w;
+      bool fits = pending.n_layers < CHAIN_MAX && conv_chain_stages(L.cin, L.nt_chain, L.taps, res != nullptr, w_new) >= 2;
+      for (int k = 0; fits && k < pending.n_layers; k++) {
+        const ChainLayer& Q = pending.layer[k];
+        fits = conv_chain_stages(Q.cin, Q.nt, Q.taps, Q.res != nullptr, w_new) >= 2;
+      }
+      if (fits) {
+        ChainLayer& Q = pending.layer[pending.n_layers];
+        Q.in = p.in;
+        Q.res = p.res;
+        Q.out = p.out;
+        Q.blob = L.blob;
+        Q.in_blocked = p.in_blocked;
+        Q.in_planes = p.in_planes;
+        Q.res_blocked = p.res_blocked;
+        Q.res_planes = p.res_planes;
+        Q.out_blocked = p.out_blocked;
+        Q.out_planes = p.out_planes;
+        Q.cin = L.cin;
+        Q.nt = L.nt_chain;
+        Q.taps = L.taps;
+        Q.cout_total = L.cout;
+        Q.relu = relu;
+        Q.stages = 0;
+        if (pending.n_layers == 0) {
+          pending_single = p;
+          pending_first = &L;
+          pending.m_rows = p.m_rows;
+          pending.n_dev = n_dev;
+          pending.pdl = p.pdl;
+        }
+        pending.n_layers++;
+        pending_w = w_new;
+        out.flagged = false;
+        return 0;
+      }
+      if (pending.n_layers == 0) break;       // does not fit even alone: one-layer launch below
+      if (flush_chain(st)) return 1;
+    }
+  }
+  if (flush_chain(st)) return 1;
+  n_launched++;
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
     CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
   prof_end(st);
@@ -488,6 +595,35 @@ int Engine::profile_states(const maru_state* d_states, float* d_out, int n, maru
   return 0;
 }
 
+int Engine::flush_chain(cudaStream_t st) {
+  if (pending.n_layers == 0) return 0;
+  n_launched++;
+  const int nl = pending.n_layers;
+  pending.n_layers = 0;
+  pending_w = 0;
+  if (nl == 1) {
+    CK(launch_conv_gemm(pending_single, pending_first->cin, pending_first->nt, pending_first->taps, sm_count, st));
+    return 0;
+  }
+  if (sync_used + nl > 256) {
+    set_error("internal: too many chained layers in one forward");
+    return 1;
+  }
+  pending.n_layers = nl;
+  pending.mask = mask;
+  pending.rows_alloc = rows_alloc;
+  pending.sync = d_sync + sync_used;
+  pending.stamps = (dbg_desc & 64) ? d_stamps + stamps_used : nullptr;
+  pending.trace = (dbg_desc & 64) && stamps_used == 0 && dbg_trace_launch >= 0 ? d_stamps + 256 : nullptr;   // first chain only
+  pending.trace_layer = dbg_trace_launch;
+  sync_used += nl;
+  stamps_used += 4 * nl + 4;
+  const cudaError_t e = launch_conv_chain(pending, sm_count, st);
+  pending.n_layers = 0;
+  CK(e);
+  return 0;
+}
+
 void Engine::clear_graphs() {
   for (auto& kv : graphs)
     if (kv.second) cudaGraphExecDestroy(kv.second);
@@ -499,6 +635,11 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
   {
     // per-tile completion counters start from zero in every forward (also under graph replay)
     CK(cudaMemsetAsync(d_flags, 0, flags_bytes, st));
+    CK(cudaMemsetAsync(d_sync, 0, 256 * sizeof(unsigned), st));
+    sync_used = 0;
+    stamps_used = 0;
+    pending.n_layers = 0;
+    pending_w = 0;
     Act* acts[7] = {&x0, &h, &r, &s, &qkv, &o, &g};
     for (Act* a : acts) {
       a->version = 0;
@@ -530,8 +671,10 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
       ap.n_dev = n_dev;
       ap.pdl = (dbg_desc & 1) ? 0 : 1;
       ap.dbg = (dbg_desc >> 1) & 3;
+      if (flush_chain(st)) return 1;
       if (!(dbg_stop_after >= 0 && launches_done >= dbg_stop_after)) {
         launches_done++;
+        n_launched++;
         const double T = CELLS;
         prof_begin(("att" + std::to_string(ai - 1) + ".core").c_str(), 3, C, C, 0,
                    4.0 * T * T * C * n, T * 4.0 * C * 2.0 * n, st);
@@ -562,7 +705,9 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
   hp.cv = Cv;
   hp.n_dev = n_dev;
   hp.pdl = (dbg_desc & 1) ? 0 : 1;
+  if (flush_chain(st)) return 1;
   if (dbg_stop_after >= 0) return 0;
+  n_launched++;
   prof_begin("heads", 4, Ch, 6, 0, (2.0 * CELLS * Ch * 6 + 2.0 * 2 * Ch * Cv + 2.0 * Cv * 3) * n,
              ((double)CELLS * Ch * 2 + (double)out_row_bytes(kind)) * n, st);
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) CK(launch_heads(hp, st));
@@ -572,6 +717,7 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
 
 int Engine::launch_all(int kind, const void* d_in, void* d_out, int n, const int* n_dev,
                        cudaStream_t st) {
+  n_launched = 1;   // the encode / ingest kernel
   if (kind != KIND_PLANES) {
     prof_begin("encode", 0, 0, IN_PLANES, 0, 0.0,
                ((double)sizeof(maru_state) + (double)CELLS * IN_PLANES * 2.0) * n, st);
@@ -584,7 +730,9 @@ int Engine::launch_all(int kind, const void* d_in, void* d_out, int n, const int
     CK(launch_ingest_rows(static_cast<const float*>(d_in), x0.p, mask, rows_alloc, n, n_dev, st));
     prof_end(st);
   }
-  return launch_trunk(kind, d_in, d_out, n, n_dev, st);
+  const int rc = launch_trunk(kind, d_in, d_out, n, n_dev, st);
+  if (rc == 0 && prof == nullptr && dbg_stop_after < 0) launches_per_forward = n_launched;
+  return rc;
 }
 
 static int bucket_for(int n, int max_batch) {

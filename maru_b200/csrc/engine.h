@@ -23,6 +23,10 @@ struct ConvLayer {
   int cin = 0, cout = 0, taps = 0, nt = 0;
   __nv_bfloat16* w = nullptr;
   float* b = nullptr;
+  // persistent chain kernel (conv_chain.cu): per channel group [W image | bias image], and the
+  // channels-per-tile it was packed for (0: this layer cannot run inside a chain)
+  uint8_t* blob = nullptr;
+  int nt_chain = 0;
 };
 struct Block {
   ConvLayer reduce, c[4], expand;
@@ -128,6 +132,17 @@ struct Engine {
 
   int conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int n, const int* n_dev,
            cudaStream_t st);
+  // consecutive conv layers are collected here and launched as ONE persistent kernel by flush_chain()
+  ChainParams pending;
+  ConvParams pending_single;        // the same layer as a one-layer launch (a chain of one falls back to it)
+  const ConvLayer* pending_first = nullptr;
+  int pending_w = 0;                // weight-blob region of the pending chain
+  unsigned* d_sync = nullptr;       // grid-barrier counters of all chains of one forward (zeroed per forward)
+  int sync_used = 0;
+  long long* d_stamps = nullptr;    // per-layer %globaltimer stamps of the chains (profiling)
+  int stamps_used = 0;
+  int n_launched = 0;               // kernels launched by the forward being enqueued
+  int flush_chain(cudaStream_t st);
   int launch_trunk(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st);
   int launch_all(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st);
   int forward_device(int kind, const void* d_in, void* d_out, int n);  // async on `stream`

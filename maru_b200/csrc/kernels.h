@@ -57,6 +57,41 @@ struct ConvParams {
 };
 constexpr int TRACE_TILES = 32, TRACE_SLOTS = 8;
 
+// ---- persistent multi-layer conv kernel (conv_chain.cu) ---------------------------------------
+// A CHAIN of consecutive conv layers runs in ONE kernel (one CTA per SM, all co-resident) with a
+// grid-wide barrier between layers: a kernel boundary costs ~4.6 us before the first dependent load
+// (tools/timeline.py), a barrier + the first slab load ~2 us.
+struct ChainLayer {
+  const __nv_bfloat16* in;
+  const __nv_bfloat16* res;    // optional residual (may alias out)
+  __nv_bfloat16* out;
+  const uint8_t* blob;         // [groups][W image of the group | bias image 2*NT*16 B]: one bulk copy per CTA
+  int in_blocked, in_planes, res_blocked, res_planes, out_blocked, out_planes;
+  int cin, nt, taps, cout_total, relu, stages;
+};
+constexpr int CHAIN_MAX = 16;
+struct ChainParams {
+  ChainLayer layer[CHAIN_MAX];
+  int n_layers;
+  const uint8_t* mask;
+  int rows_alloc;
+  int m_rows;
+  const int* n_dev;
+  int w_region;                // shared-memory bytes reserved for the weight blob (max over the layers)
+  unsigned* sync;              // [n_layers] grid-barrier arrival counters, zero when the kernel starts
+  long long* stamps;           // optional [n_layers + 1][4] %globaltimer of CTA 0: layer start, first operands, done, weights
+  long long* trace;            // optional [32 tiles][8] per-tile stamps of CTA 0 in layer `trace_layer` (bring-up)
+  int trace_layer;
+  int pdl;
+};
+cudaError_t configure_conv_chain();
+bool conv_chain_supports(int cin, int nt, int taps);
+int conv_chain_blob_bytes(int cin, int nt, int taps);     // bytes of one group's blob
+// pipeline stages a layer gets inside a chain whose weight-blob region is w_region bytes (< 2: does not fit)
+int conv_chain_stages(int cin, int nt, int taps, bool has_res, int w_region);
+// fills stages / w_region; returns cudaErrorInvalidConfiguration when a layer does not fit
+cudaError_t launch_conv_chain(ChainParams& cp, int sm_count, cudaStream_t stream);
+
 cudaError_t configure_conv_gemm();
 cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,
                              cudaStream_t stream);

@@ -73,3 +73,22 @@ def test_every_stage_matches_port(built_lib, model_dir, name):
         assert np.abs(got - out).max() < 1e-2
     finally:
         ev.close()
+
+
+def test_chain_kernel_mode_is_bit_identical(built_lib, model_dir):
+    """The experimental persistent multi-layer conv kernel (debug bit 5, conv_chain.cu) runs the same
+    layer math behind grid barriers: its outputs must equal the default one-launch-per-layer path."""
+    import maru_b200
+    from maru_b200 import synth
+    for name, n in (('b2c64', 13), ('b4c128', 40)):
+        ev = maru_b200.Evaluator(model_dir(name), gpu=0, max_batch=64, flags=maru_b200.capi.FLAG_NO_GRAPH)
+        try:
+            st = synth.random_states(n, 19, seed=5)
+            want = ev.forward_states(st)
+            launches = ev.info().launches_per_forward
+            ev.debug_set(1, 32)
+            got = ev.forward_states(st)
+            assert np.array_equal(got, want)
+            assert ev.info().launches_per_forward < launches        # layers really were chained
+        finally:
+            ev.close()

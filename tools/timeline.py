@@ -12,6 +12,7 @@ model, _ = model_files('b4c128')
 ev = maru_b200.Evaluator(model, gpu=0, max_batch=B, flags=int(sys.argv[2]) if len(sys.argv) > 2 else 0)
 st = synth.random_states(B, 19, seed=7)
 ev.debug_set(3, 1)
+if len(sys.argv) > 3: ev.debug_set(1, int(sys.argv[3]))
 for _ in range(4): ev.forward_states(st)
 tl = ev.debug_timeline()
 t0 = tl[0, 0, 0]
