@@ -20,7 +20,7 @@ struct ConvCfg {
   static constexpr int RES_BYTES = TILE_M * NT * 2;            // residual tile [NT/8][128][16 B]
   static constexpr int MASK_BYTES = TILE_M;                    // board mask of the tile's rows
   static constexpr int MAX_STAGES = 4;
-  static constexpr int BAR_BYTES = 128;
+  static constexpr int BAR_BYTES = 256;
   static constexpr int SMEM_LIMIT = 232448;                    // 227 KB per CTA
   static int fixed_bytes(bool has_res) {
     return W_BYTES + ONES_BYTES + BIASB_BYTES + BAR_BYTES + (has_res ? IDENT_BYTES : 0);

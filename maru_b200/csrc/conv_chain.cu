@@ -28,7 +28,8 @@ constexpr int CHAIN_BAR_BYTES = 256;
 constexpr int CHAIN_MAXS = 4;
 
 struct ChainBars {
-  uint64_t* full;     // [4] slab + mask (+ residual) landed
+  uint64_t* full;     // [2][4] slab + mask (+ residual) of an even / odd tile landed: one set per MMA warp, so
+                      // that neither warp ever skips a phase of a barrier it waits on (see conv_gemm.cu)
   uint64_t* empty;    // [4] stage reusable (MMA commit + 8 epilogue warps)
   uint64_t* tfull;    // [2] accumulator ready
   uint64_t* tempty;   // [2] accumulator drained (8 epilogue warps)
@@ -38,7 +39,8 @@ struct ChainBars {
 
 // per-thread pipeline state that survives layer boundaries (the mbarriers are never re-initialised)
 struct ChainState {
-  uint32_t slot_par;   // bit s: parity of the number of uses of stage slot s so far
+  uint32_t slot_par;   // bit s: parity of the number of uses of stage slot s so far (empty[] barriers)
+  uint32_t full_par;   // bit 4*(tile parity)+s: parity of the uses of full[tile parity][s] so far
   uint32_t acc_par;    // bit a: parity of the number of uses of accumulator a so far
   uint32_t n_active;   // layers in which this CTA had a role so far (weight blob / mdone phases)
 };
@@ -114,36 +116,37 @@ __device__ __forceinline__ void chain_layer(const ChainParams& cp, const ChainLa
   if (warp == 0) {
     // =========================== producer ===========================
     uint32_t par = st.slot_par;
-    int stage = 0;
-    for (int tile = bx; tile < n_tiles; tile += gx) {
+    int stage = 0, it = 0;
+    for (int tile = bx; tile < n_tiles; tile += gx, it++) {
       mbar_wait(&B.empty[stage], ((par >> stage) & 1u) ^ 1u);
       par ^= 1u << stage;
+      uint64_t* fbar = &B.full[(it & 1) * CHAIN_MAXS + stage];
       if (tr != nullptr && lane == 0) tr[((tile - bx) / gx) * 8 + 0] = globaltimer_ns();
       if (elect_one()) {
-        mbar_expect_tx(&B.full[stage], STAGE_BYTES);
+        mbar_expect_tx(fbar, STAGE_BYTES);
         const size_t row0 = (size_t)GUARD_ROWS + (size_t)tile * TILE_M;
         uint8_t* dst = s_stage + stage * STAGE_BYTES;
         if (TAPS == 1 && L.in_blocked) {
-          bulk_load_1d(dst, L.in + (size_t)tile * L.in_planes * (TILE_M * 8), Cfg::SLAB_BYTES, &B.full[stage]);
+          bulk_load_1d(dst, L.in + (size_t)tile * L.in_planes * (TILE_M * 8), Cfg::SLAB_BYTES, fbar);
         } else {
 #pragma unroll 1
           for (int c = 0; c < Cfg::KCH; c++) {
             const __nv_bfloat16* src = L.in + ((size_t)c * cp.rows_alloc + row0 - Cfg::LEAD) * 8;
-            bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, &B.full[stage]);
+            bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, fbar);
           }
         }
-        bulk_load_1d(dst + Cfg::SLAB_BYTES, cp.mask + (size_t)tile * TILE_M, Cfg::MASK_BYTES, &B.full[stage]);
+        bulk_load_1d(dst + Cfg::SLAB_BYTES, cp.mask + (size_t)tile * TILE_M, Cfg::MASK_BYTES, fbar);
         if (has_res) {
           uint8_t* rdst = dst + Cfg::SLAB_BYTES + Cfg::MASK_BYTES;
           const int rc0 = group * (NT / 8);
           if (L.res_blocked) {
             bulk_load_1d(rdst, L.res + ((size_t)tile * L.res_planes + rc0) * (TILE_M * 8), Cfg::RES_BYTES,
-                         &B.full[stage]);
+                         fbar);
           } else {
 #pragma unroll 1
             for (int c = 0; c < NT / 8; c++)
               bulk_load_1d(rdst + c * TILE_M * 16, L.res + ((size_t)(rc0 + c) * cp.rows_alloc + row0) * 8,
-                           TILE_M * 16, &B.full[stage]);
+                           TILE_M * 16, fbar);
           }
         }
       }
@@ -164,18 +167,19 @@ __device__ __forceinline__ void chain_layer(const ChainParams& cp, const ChainLa
     const uint32_t ident_lo = (uint32_t)b_d + (smem_u32(s_ident) >> 4);
     mbar_wait(B.wbar, st.n_active & 1u);                           // this layer's weights + bias image
     if (stamp != nullptr && warp == 1 && lane == 0) stamp[3] = globaltimer_ns();   // weights landed
-    uint32_t spar = st.slot_par, apar = st.acc_par;
+    uint32_t fpar = st.full_par, apar = st.acc_par;
     int stage = 0, it = 0;
     for (int tile = bx; tile < n_tiles; tile += gx, it++) {
       const int acc = it & 1;
-      const uint32_t fph = (spar >> stage) & 1u, eph = ((apar >> acc) & 1u) ^ 1u;
-      spar ^= 1u << stage;
+      const int fslot = acc * CHAIN_MAXS + stage;
+      const uint32_t fph = (fpar >> fslot) & 1u, eph = ((apar >> acc) & 1u) ^ 1u;
+      fpar ^= 1u << fslot;
       apar ^= 1u << acc;
       const int my_stage = stage;
       if (++stage == STAGES) stage = 0;
       if (acc != mw) continue;
       mbar_wait(&B.tempty[acc], eph);
-      mbar_wait(&B.full[my_stage], fph);
+      mbar_wait(&B.full[mw * CHAIN_MAXS + my_stage], fph);
       if (stamp != nullptr && it == 0 && lane == 0) stamp[1] = globaltimer_ns();   // first operands landed
       if (tr != nullptr && lane == 0) tr[it * 8 + 1] = globaltimer_ns();
       tc_fence_after();
@@ -214,19 +218,20 @@ __device__ __forceinline__ void chain_layer(const ChainParams& cp, const ChainLa
     constexpr int CW = NT / 2;               // columns per warp
     const int lg = warp & 3;                 // TMEM lane group this warp may access
     const int half = (warp - 2) >> 2;        // which half of the NT columns
-    uint32_t spar = st.slot_par, apar = st.acc_par;
+    uint32_t fpar = st.full_par, apar = st.acc_par;
     int stage = 0, it = 0;
     for (int tile = bx; tile < n_tiles; tile += gx, it++) {
       const int acc = it & 1;
-      const uint32_t fph = (spar >> stage) & 1u, tph = (apar >> acc) & 1u;
-      spar ^= 1u << stage;
+      const int fslot = acc * CHAIN_MAXS + stage;
+      const uint32_t fph = (fpar >> fslot) & 1u, tph = (apar >> acc) & 1u;
+      fpar ^= 1u << fslot;
       apar ^= 1u << acc;
       const int trow = lg * 32 + lane;
       const int row = tile * TILE_M + trow;
       const bool valid = row < m_rows;
       const size_t grow = (size_t)GUARD_ROWS + row;
       const uint8_t* s_mask = s_stage + stage * STAGE_BYTES + Cfg::SLAB_BYTES;
-      mbar_wait(&B.full[stage], fph);                        // mask landed with the slab
+      mbar_wait(&B.full[fslot], fph);                        // mask landed with the slab
       const bool on = valid && (s_mask[trow] != 0);
       mbar_wait(&B.tfull[acc], tph);
       if (tr != nullptr && warp == 2 && lane == 0) tr[it * 8 + 3] = globaltimer_ns();
@@ -289,6 +294,7 @@ __device__ __forceinline__ void chain_layer(const ChainParams& cp, const ChainLa
     int stage = 0, it = 0;
     for (int tile = bx; tile < n_tiles; tile += gx, it++) {
       st.slot_par ^= 1u << stage;
+      st.full_par ^= 1u << ((it & 1) * CHAIN_MAXS + stage);
       st.acc_par ^= 1u << (it & 1);
       if (++stage == STAGES) stage = 0;
     }
@@ -306,8 +312,8 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) conv_chain_kernel(const __gr
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + cp.w_region);
   ChainBars B;
   B.full = bars;
-  B.empty = bars + CHAIN_MAXS;
-  B.tfull = bars + 2 * CHAIN_MAXS;
+  B.empty = bars + 2 * CHAIN_MAXS;
+  B.tfull = bars + 3 * CHAIN_MAXS;
   B.tempty = B.tfull + 2;
   B.wbar = B.tempty + 2;
   B.mdone = B.wbar + 1;
@@ -318,6 +324,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) conv_chain_kernel(const __gr
   if (threadIdx.x == 0) {
     for (int i = 0; i < CHAIN_MAXS; i++) {
       mbar_init(&B.full[i], 1);
+      mbar_init(&B.full[CHAIN_MAXS + i], 1);
       mbar_init(&B.empty[i], 9);     // MMA commit + 8 epilogue warps
     }
     for (int i = 0; i < 2; i++) {
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(CHAIN_THREADS, 1) conv_chain_kernel(const __gr
 
   ChainState st;
   st.slot_par = 0u;
+  st.full_par = 0u;
   st.acc_par = 0u;
   st.n_active = 0u;
   for (int l = 0; l < cp.n_layers; l++) {

@@ -46,15 +46,22 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_biasb + Cfg::BIASB_BYTES);
   uint8_t* s_ident = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES;   // keeps stages 128-B aligned (TMA)
   uint8_t* s_stage = s_ident + (has_res ? Cfg::IDENT_BYTES : 0);
-  uint64_t* full = bars;                   // [MAXS] input slab + mask (+ residual tile) landed
-  uint64_t* empty = bars + MAXS;           // [MAXS] stage reusable
-  uint64_t* tfull = bars + 2 * MAXS;       // [2] accumulator ready
+  // "stage landed" barriers come in TWO sets, one per MMA-issuing warp (tiles alternate between the two
+  // warps): a warp that only sees every second tile would otherwise skip phases of a shared barrier
+  // whenever the stage count is odd — its parity wait for tile it+2 is already satisfied by the phase
+  // of tile it, before the data of it+2 (or even it+1) has landed. Found by the full-size determinism
+  // test on the 1-stage 128->64 3x3 layers of the C=256 net.
+  uint64_t* full = bars;                   // [2][MAXS] input slab + mask (+ residual tile) of an even / odd tile landed
+  uint64_t* empty = bars + 2 * MAXS;       // [MAXS] stage reusable
+  uint64_t* tfull = bars + 3 * MAXS;       // [2] accumulator ready
   uint64_t* tempty = tfull + 2;            // [2] accumulator drained
   uint64_t* wbar = tempty + 2;             // weights landed
   // number of (tile, epilogue warp) store completions so far: a counter, not an mbarrier, because the
   // flag signaller may fall more than one phase behind the epilogue
   volatile uint32_t* stored = reinterpret_cast<volatile uint32_t*>(wbar + 1);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);   // last slot of the 128-byte barrier block
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);   // last slot of the 256-byte barrier block
+  // uses of full[tile parity][stage] repeat every STAGES tiles (even count) or 2*STAGES tiles (odd count)
+  const int full_period = (STAGES & 1) ? 2 * STAGES : STAGES;
 
   pdl_launch_dependents();                      // let the next layer's CTAs start their prologue
   const int warp = threadIdx.x >> 5;
@@ -87,6 +94,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
     }
     for (int i = 0; i < MAXS; i++) {
       mbar_init(&full[i], 1);
+      mbar_init(&full[MAXS + i], 1);
       // a stage is free once the MMA commit retired (slab, residual) and the 8 epilogue warps are
       // done with its mask
       mbar_init(&empty[i], 9);
@@ -194,32 +202,33 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       }
       if (tr && lane == 0) tr[1] = clock64();
       if (elect_one()) {
-        mbar_expect_tx(&full[stage], STAGE_BYTES);
+        uint64_t* fbar = &full[(tix & 1) * MAXS + stage];   // the set of the MMA warp that owns this tile
+        mbar_expect_tx(fbar, STAGE_BYTES);
         const size_t row0 = (size_t)GUARD_ROWS + (size_t)tile * TILE_M;
         uint8_t* dst = s_stage + stage * STAGE_BYTES;
         if (TAPS == 1 && p.in_blocked) {
           // tile-blocked input: the whole [KCH][128][16 B] slab is contiguous
           bulk_load_1d(dst, p.in + ((size_t)tile * p.in_planes + p.in_chunk0) * (TILE_M * 8), Cfg::SLAB_BYTES,
-                       &full[stage]);
+                       fbar);
         } else {
 #pragma unroll 1
           for (int c = 0; c < Cfg::KCH; c++) {
             const __nv_bfloat16* src = p.in + ((size_t)(p.in_chunk0 + c) * p.rows_alloc + row0 - Cfg::LEAD) * 8;
-            bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, &full[stage]);
+            bulk_load_1d(dst + c * Cfg::SLAB_ROWS * 16, src, Cfg::SLAB_ROWS * 16, fbar);
           }
         }
-        bulk_load_1d(dst + Cfg::SLAB_BYTES, p.mask + (size_t)tile * TILE_M, Cfg::MASK_BYTES, &full[stage]);
+        bulk_load_1d(dst + Cfg::SLAB_BYTES, p.mask + (size_t)tile * TILE_M, Cfg::MASK_BYTES, fbar);
         if (has_res) {
           uint8_t* rdst = dst + Cfg::SLAB_BYTES + Cfg::MASK_BYTES;
           const int rc0 = p.res_chunk0 + group * (NT / 8);
           if (p.res_blocked) {
             bulk_load_1d(rdst, p.res + ((size_t)tile * p.res_planes + rc0) * (TILE_M * 8), Cfg::RES_BYTES,
-                         &full[stage]);
+                         fbar);
           } else {
 #pragma unroll 1
             for (int c = 0; c < NT / 8; c++)
               bulk_load_1d(rdst + c * TILE_M * 16, p.res + ((size_t)(rc0 + c) * p.rows_alloc + row0) * 8,
-                           TILE_M * 16, &full[stage]);
+                           TILE_M * 16, fbar);
           }
         }
       }
@@ -249,12 +258,12 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       const int acc = it & 1;                       // == mw
       const uint32_t acc_phase = (it >> 1) & 1;
       const int stage = it % STAGES;
-      const uint32_t phase = (it / STAGES) & 1;
+      const uint32_t phase = (it / full_period) & 1;
       long long* tr = (p.trace && blockIdx.y == 0 && it < TRACE_TILES)
                           ? p.trace + ((size_t)blockIdx.x * TRACE_TILES + it) * TRACE_SLOTS : nullptr;
       if (tr && lane == 0) tr[2] = clock64();
       mbar_wait(&tempty[acc], acc_phase ^ 1);
-      mbar_wait(&full[stage], phase);
+      mbar_wait(&full[mw * MAXS + stage], phase);
       if (tl && lane == 0 && it == 0) tl[3] = globaltimer_ns();
       if (tr && lane == 0) tr[3] = clock64();
       tc_fence_after();
@@ -327,7 +336,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       long long* tr = (p.trace && blockIdx.y == 0 && it < TRACE_TILES && warp == 2 && lane == 0)
                           ? p.trace + ((size_t)blockIdx.x * TRACE_TILES + it) * TRACE_SLOTS : nullptr;
       if (tr) tr[5] = clock64();
-      mbar_wait(&full[stage], phase);                        // mask landed with the slab
+      mbar_wait(&full[acc * MAXS + stage], (it / full_period) & 1);   // mask landed with the slab
       const bool on = valid && (s_mask[trow] != 0);
       mbar_wait(&tfull[acc], acc_phase);
       if (tl && it == 0 && warp == 2 && lane == 0) tl[4] = globaltimer_ns();
