@@ -213,6 +213,15 @@ typedef struct maru_queue_stats {
 } maru_queue_stats;
 int  maru_queue_get_stats(maru_queue* q, maru_queue_stats* st);
 
+/* ---- host-side helper: exact ladder flags without the reference's Board copies ------------------ */
+/* colors: [height*width] raster, 0 empty / +1 black / -1 white. (ko_x, ko_y, ko_color): the point the
+ * side ko_color may not retake (Board::_koIndex/_koColor, Board.cpp:140-205), or ko_x < 0 for none.
+ * flags[y*width+x] = 1 for every stone Board::isShicho(x, y) reports (Board::_updateShicho /
+ * _isShichoRen, Board.cpp:1045-1153) — same decision procedure on a flat board, ~20x cheaper
+ * (maru_b200/dropin/lean_ladder.h). Pure host code, no GPU involved. */
+int  maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
+                       uint8_t* flags);
+
 /* ---- errors ---------------------------------------------------------------------------------- */
 const char* maru_last_error(void);      /* thread-local text of the last failing call              */
 int  maru_abi_version(void);

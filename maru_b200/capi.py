@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
     'maru_eval_debug_set', 'maru_eval_debug_trace', 'maru_eval_debug_timeline', 'maru_eval_debug_stamps', 'maru_eval_profile_states',
     'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
-    'maru_queue_get_stats', 'maru_last_error', 'maru_abi_version',
+    'maru_queue_get_stats', 'maru_ladder_flags', 'maru_last_error', 'maru_abi_version',
 ]
 
 
@@ -108,6 +108,7 @@ def load_library():
     lib.maru_queue_execute.argtypes = [vp, vp, vp, ci]
     lib.maru_queue_execute_states.argtypes = [vp, vp, vp, ci]
     lib.maru_queue_get_stats.argtypes = [vp, C.POINTER(QueueStats)]
+    lib.maru_ladder_flags.argtypes = [vp, ci, ci, ci, ci, ci, vp]
     lib.maru_last_error.restype = C.c_char_p
     lib.maru_abi_version.restype = ci
     _lib = lib
@@ -117,6 +118,18 @@ def load_library():
 def _check(lib, rc: int, what: str) -> None:
     if rc != 0:
         raise MaruB200Error(f'{what}: {lib.maru_last_error().decode(errors="replace")}')
+
+
+def ladder_flags(colors: np.ndarray, ko: Optional[tuple] = None) -> np.ndarray:
+    """Exact Board::isShicho flags of a position (host code). colors: [h, w] int8, 0 / +1 black / -1 white;
+    ko = (x, y, color) if `color` may not retake at (x, y). Returns uint8 [h, w]."""
+    lib = load_library()
+    col = np.ascontiguousarray(colors, np.int8)
+    h, w = col.shape
+    out = np.zeros((h, w), np.uint8)
+    kx, ky, kc = ko if ko is not None else (-1, -1, 0)
+    _check(lib, lib.maru_ladder_flags(col.ctypes.data, w, h, kx, ky, kc, out.ctypes.data), 'maru_ladder_flags')
+    return out
 
 
 def ensure_pack(model: str | Path) -> Path:

@@ -1,4 +1,5 @@
 // capi.cpp — extern "C" surface of libmaru_b200.so (declared in include/maru_b200.h).
+#include "../dropin/lean_ladder.h"
 #include <cstring>
 #include <new>
 
@@ -212,6 +213,28 @@ int maru_eval_debug_stamps(maru_eval* ev, long long* out) {
   CKC(cudaSetDevice(e->gpu_id));
   CKC(cudaStreamSynchronize(e->stream));
   CKC(cudaMemcpy(out, e->d_stamps, 512 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
+                      uint8_t* flags) {
+  if (colors == nullptr || flags == nullptr || width < 1 || height < 1 || width > 19 || height > 19) {
+    maru::set_error("maru_ladder_flags: bad argument");
+    return 1;
+  }
+  maru_b200::LeanBoard b;
+  b.init(width, height);
+  for (int y = 0; y < height; y++)
+    for (int x = 0; x < width; x++) {
+      const int8_t v = colors[y * width + x];
+      b.c[b.index(x, y)] = v > 0 ? maru_b200::LeanBoard::kBlack : v < 0 ? maru_b200::LeanBoard::kWhite
+                                                                    : maru_b200::LeanBoard::kEmpty;
+    }
+  if (ko_x >= 0 && ko_y >= 0 && ko_x < width && ko_y < height && ko_color != 0) {
+    b.ko_index = b.index(ko_x, ko_y);
+    b.ko_color = ko_color > 0 ? 1 : -1;
+  }
+  b.ladder_flags(flags);
   return 0;
 }
 

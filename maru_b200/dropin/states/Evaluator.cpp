@@ -10,9 +10,21 @@
 // (priors of the candidate cells + value) instead of the 2169-float row.
 #include "Evaluator.h"
 
+#include <cstdlib>
+
 #include "state_from_board.h"
 
 namespace deepgo {
+
+// MARU_LEAN_LADDER=0 falls back to Board::isShicho (A/B measurements); the default is the flat-board
+// read-out of lean_ladder.h, bit-identical and 20-45x cheaper.
+static bool lean_ladder_enabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("MARU_LEAN_LADDER");
+    return v == nullptr || v[0] != '0';
+  }();
+  return on;
+}
 
 Evaluator::Evaluator(Processor* processor, float komi, int32_t rule, bool superko)
     : _processor(processor), _komi(komi), _rule(rule), _superko(superko), _policies(), _value(0.0f),
@@ -34,7 +46,8 @@ void Evaluator::evaluate(Board* board, int32_t color) {
   if (_evaluated) return;
 
   maru_state state;
-  maru_b200::state_from_board(board, color, _komi, _rule, _superko, /*with_move_mask=*/true, &state);
+  maru_b200::state_from_board(board, color, _komi, _rule, _superko, /*with_move_mask=*/true, &state,
+                              lean_ladder_enabled());
   // The legal / non-territory filter (Evaluator.cpp:60-68) does not depend on the network, so it is
   // taken BEFORE the evaluation and travels in the record; the heads kernel gathers the priors of
   // exactly those cells (board order) next to the value scalars: 1456 B back instead of 8676 B.

@@ -59,6 +59,8 @@ def _bind_board(lib) -> None:
     lib.ref_board_get_inputs.argtypes = [C.c_void_p, _f32p, C.c_int, C.c_float, C.c_int, C.c_int]
     lib.ref_board_get_state.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_float, C.c_int, C.c_int,
                                         C.c_int]
+    lib.ref_board_get_state_lean.argtypes = [C.c_void_p, _u8p, C.c_int, C.c_float, C.c_int, C.c_int,
+                                        C.c_int]
 
 
 def _bind_nn(lib) -> None:
@@ -159,11 +161,13 @@ class RefBoard:
         self.lib.ref_board_get_inputs(self.ptr, out, color, float(komi), rule, int(superko))
         return out
 
-    def get_state(self, color, komi=7.5, rule=RULE_CH, superko=False, with_mask=False) -> np.ndarray:
-        """Compact maru_state (448 bytes) via the Board's public getters (state_from_board.h)."""
+    def get_state(self, color, komi=7.5, rule=RULE_CH, superko=False, with_mask=False,
+                  lean_ladder=False) -> np.ndarray:
+        """Compact maru_state (448 bytes) via the Board's public getters (state_from_board.h).
+        lean_ladder: ladder flags from maru_b200/dropin/lean_ladder.h instead of Board::isShicho."""
         out = np.zeros(STATE_SIZE, np.uint8)
-        self.lib.ref_board_get_state(self.ptr, out, color, float(komi), rule, int(superko),
-                                     int(with_mask))
+        fn = self.lib.ref_board_get_state_lean if lean_ladder else self.lib.ref_board_get_state
+        fn(self.ptr, out, color, float(komi), rule, int(superko), int(with_mask))
         return out
 
 

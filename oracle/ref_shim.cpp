@@ -61,6 +61,12 @@ void ref_board_get_state(void* b, maru_state* st, int color, float komi, int rul
                          int with_mask) {
   maru_b200::state_from_board((Board*)b, color, komi, rule, superko != 0, with_mask != 0, st);
 }
+// Same record with the ladder flags taken from the flat-board read-out (lean_ladder.h) instead of
+// Board::isShicho: the two must be byte-identical (tests/test_lean_ladder.py).
+void ref_board_get_state_lean(void* b, maru_state* st, int color, float komi, int rule, int superko,
+                              int with_mask) {
+  maru_b200::state_from_board((Board*)b, color, komi, rule, superko != 0, with_mask != 0, st, true);
+}
 int ref_model_input_size() { return MODEL_INPUT_SIZE; }
 int ref_model_output_size() { return MODEL_OUTPUT_SIZE; }
 

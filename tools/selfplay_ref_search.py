@@ -35,6 +35,7 @@ def main():
     ap.add_argument('--root', default='pucb', choices=['pucb', 'gumbel'])
     ap.add_argument('--width', type=int, default=16)
     ap.add_argument('--noise', type=float, default=1.0)
+    ap.add_argument('--opening', type=int, default=0, help='random legal moves played before the timed search (mid-game positions)')
     args = ap.parse_args()
 
     import torch
@@ -59,13 +60,53 @@ def main():
     proc = ref.RefProcessor(str(model), gpus=gpus, batch_size=256, kind=kind)
     made = []
 
-    def make_player(_g):
-        p = ref.RefPlayer(proc, args.threads, args.size, args.size)
+    import numpy as np
+
+    class Opened:
+        """A reference player that replays a seeded random legal opening when it is initialised."""
+
+        def __init__(self, g):
+            self.p = ref.RefPlayer(proc, args.threads, args.size, args.size)
+            self.g = g
+            self.ready = False
+
+        def initialize(self):
+            if self.ready:               # the opening is replayed once, outside the timed region
+                return
+            self.ready = True
+            self.p.initialize()
+            if args.opening > 0:
+                rng = np.random.default_rng(1000 + self.g)
+                b = ref.RefBoard(args.size, args.size)
+                color = ref.BLACK
+                for _ in range(args.opening):
+                    en = np.flatnonzero(b.get_enableds(color, True))
+                    if len(en) == 0:
+                        break
+                    i = int(rng.choice(en))
+                    x, y = i % args.size, i // args.size
+                    b.play(x, y, color)
+                    self.p.play(x, y)
+                    color = -color
+
+        def evaluate(self, **kw):
+            return self.p.evaluate(**kw)
+
+        def play(self, x, y):
+            return self.p.play(x, y)
+
+        def close(self):
+            self.p.close()
+
+    def make_player(g):
+        p = Opened(g)
         made.append(p)
         return p
     sched = selfplay.SelfPlayScheduler(make_player, args.games, args.visits, max_moves=args.moves,
                                        root=args.root, width=args.width, noise=args.noise,
                                        rank=rank, world=world)
+    for p in sched.players:
+        p.initialize()
     if dist is not None:
         dist.barrier()
     st = sched.run()
@@ -75,6 +116,7 @@ def main():
                               unit='visits/s', n_gpus=world if args.impl == 'b200' else 0, impl=args.impl,
                               games=args.games, board=args.size, visits_per_move=args.visits,
                               moves_per_game=args.moves, threads_per_game=args.threads, root=args.root,
+                              opening_moves=args.opening, lean_ladder=os.environ.get('MARU_LEAN_LADDER', '1') != '0',
                               total_visits=agg['visits'], moves=agg['batches'], wall_s=agg['wall_s'],
                               host_cores=os.cpu_count(), model=args.model)), flush=True)
     for p in made:
