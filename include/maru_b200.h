@@ -222,6 +222,13 @@ int  maru_queue_get_stats(maru_queue* q, maru_queue_stats* st);
 int  maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
                        uint8_t* flags);
 
+/* Candidate-move filter of Evaluator::evaluate on the same flat board (Evaluator.cpp:60-68):
+ * enableds[y*width+x] = Board::getEnableds(color, checkSeki=true) (Board.cpp:333-343, 1177-1631),
+ * territories[y*width+x] = Board::getTerritories(color) in {-1, 0, +1} (Board.cpp:350-378, 872-1040);
+ * a move is kept iff enableds != 0 && territories == 0 (maru_state::move_mask). Either output may be NULL. */
+int  maru_rules_eval(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
+                     int color, uint8_t* enableds, int8_t* territories);
+
 /* ---- errors ---------------------------------------------------------------------------------- */
 const char* maru_last_error(void);      /* thread-local text of the last failing call              */
 int  maru_abi_version(void);

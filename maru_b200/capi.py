@@ -55,7 +55,7 @@ ABI_SYMBOLS = [
     'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
     'maru_eval_debug_set', 'maru_eval_debug_trace', 'maru_eval_debug_timeline', 'maru_eval_debug_stamps', 'maru_eval_profile_states',
     'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
-    'maru_queue_get_stats', 'maru_ladder_flags', 'maru_last_error', 'maru_abi_version',
+    'maru_queue_get_stats', 'maru_ladder_flags', 'maru_rules_eval', 'maru_last_error', 'maru_abi_version',
 ]
 
 
@@ -109,6 +109,7 @@ def load_library():
     lib.maru_queue_execute_states.argtypes = [vp, vp, vp, ci]
     lib.maru_queue_get_stats.argtypes = [vp, C.POINTER(QueueStats)]
     lib.maru_ladder_flags.argtypes = [vp, ci, ci, ci, ci, ci, vp]
+    lib.maru_rules_eval.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp]
     lib.maru_last_error.restype = C.c_char_p
     lib.maru_abi_version.restype = ci
     _lib = lib
@@ -130,6 +131,20 @@ def ladder_flags(colors: np.ndarray, ko: Optional[tuple] = None) -> np.ndarray:
     kx, ky, kc = ko if ko is not None else (-1, -1, 0)
     _check(lib, lib.maru_ladder_flags(col.ctypes.data, w, h, kx, ky, kc, out.ctypes.data), 'maru_ladder_flags')
     return out
+
+
+def rules_eval(colors: np.ndarray, color: int, ko: Optional[tuple] = None):
+    """(enableds uint8 [h, w] = Board::getEnableds(color, checkSeki=True), territories int8 [h, w] =
+    Board::getTerritories(color)) of a position, on the flat board (host code)."""
+    lib = load_library()
+    col = np.ascontiguousarray(colors, np.int8)
+    h, w = col.shape
+    en = np.zeros((h, w), np.uint8)
+    te = np.zeros((h, w), np.int8)
+    kx, ky, kc = ko if ko is not None else (-1, -1, 0)
+    _check(lib, lib.maru_rules_eval(col.ctypes.data, w, h, kx, ky, kc, color, en.ctypes.data, te.ctypes.data),
+           'maru_rules_eval')
+    return en, te
 
 
 def ensure_pack(model: str | Path) -> Path:

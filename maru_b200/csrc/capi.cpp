@@ -1,5 +1,5 @@
 // capi.cpp — extern "C" surface of libmaru_b200.so (declared in include/maru_b200.h).
-#include "../dropin/lean_ladder.h"
+#include "../dropin/lean_rules.h"
 #include <cstring>
 #include <new>
 
@@ -216,13 +216,27 @@ int maru_eval_debug_stamps(maru_eval* ev, long long* out) {
   return 0;
 }
 
-int maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
-                      uint8_t* flags) {
-  if (colors == nullptr || flags == nullptr || width < 1 || height < 1 || width > 19 || height > 19) {
-    maru::set_error("maru_ladder_flags: bad argument");
+static void fill_lean_board(maru_b200::LeanBoard& b, const int8_t* colors, int width, int height, int ko_x,
+                            int ko_y, int ko_color);
+
+int maru_rules_eval(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color, int color,
+                    uint8_t* enableds, int8_t* territories) {
+  if (colors == nullptr || width < 1 || height < 1 || width > 19 || height > 19 || (color != 1 && color != -1)) {
+    maru::set_error("maru_rules_eval: bad argument");
     return 1;
   }
   maru_b200::LeanBoard b;
+  fill_lean_board(b, colors, width, height, ko_x, ko_y, ko_color);
+  maru_b200::LeanRules r(b);
+  if (enableds != nullptr)
+    for (int y = 0; y < height; y++)
+      for (int x = 0; x < width; x++) enableds[y * width + x] = r.enabled(b.index(x, y), color, true) ? 1 : 0;
+  if (territories != nullptr) r.territories(color, territories);
+  return 0;
+}
+
+static void fill_lean_board(maru_b200::LeanBoard& b, const int8_t* colors, int width, int height, int ko_x,
+                            int ko_y, int ko_color) {
   b.init(width, height);
   for (int y = 0; y < height; y++)
     for (int x = 0; x < width; x++) {
@@ -234,6 +248,16 @@ int maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int
     b.ko_index = b.index(ko_x, ko_y);
     b.ko_color = ko_color > 0 ? 1 : -1;
   }
+}
+
+int maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
+                      uint8_t* flags) {
+  if (colors == nullptr || flags == nullptr || width < 1 || height < 1 || width > 19 || height > 19) {
+    maru::set_error("maru_ladder_flags: bad argument");
+    return 1;
+  }
+  maru_b200::LeanBoard b;
+  fill_lean_board(b, colors, width, height, ko_x, ko_y, ko_color);
   b.ladder_flags(flags);
   return 0;
 }

@@ -1,0 +1,444 @@
+// lean_rules.h — the reference's candidate-move filter on a flat board.
+//
+// Evaluator::evaluate keeps a move only if it is legal under the reference's seki-aware legality test
+// AND does not lie in territory that is already unconditionally decided (reference
+// src/deepgo/native/cpp/Evaluator.cpp:60-68):
+//     Board::getEnableds(enableds, color, checkSeki=true)     Board.cpp:333-343, 1177-1220
+//       -> Board::_isSeki / _isSekiRen / _isSekiArea           Board.cpp:1228-1465
+//       -> Board::_isNakade / _isSingleArea                    Board.cpp:1480-1631
+//     Board::getTerritories(territories, color)                Board.cpp:350-378
+//       -> Board::_updateArea                                  Board.cpp:872-1040
+// On the reference's Board (three std::set per group, Ren objects copied BY VALUE inside _isEnabled)
+// these two calls cost 0.1 ms (9x9) to 0.4 ms (19x19) per leaf — what is left of the host time once the
+// ladder read-out is lean.  This header restates them over LeanBoard (lean_ladder.h): groups are labelled
+// once per position, sets are small sorted arrays.  The result must be IDENTICAL on every cell (it decides
+// which moves the search may expand), so every quirk is kept: the 9-cell cut-offs, the exact nakade
+// vital-point count with its corner rule, "an area is decided only if EVERY cell of it touches exactly the
+// own groups its first cell touches", and the iteration that un-decides groups with fewer than two
+// decided areas.  tests/test_lean_rules.py compares against the compiled reference.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+
+#include "lean_ladder.h"
+
+namespace maru_b200 {
+
+// sorted unique small set of cell / group indices (the reference uses std::set<int32_t>).  Every set these
+// rules build is small by construction: the reference itself gives up at 9 cells / 7 stones, opponent groups
+// that matter have exactly 2 liberties, and own groups with >= 9 liberties / >= 6 stones are cut off before
+// their cells are inserted.  The largest reachable size is 4 + 4*8 = 36 (liberties of four groups).
+struct IdxSet {
+  static constexpr int CAP = 96;
+  int n = 0;
+  int16_t v[CAP];
+  IdxSet() = default;
+  IdxSet(const IdxSet& o) : n(o.n) { std::memcpy(v, o.v, (size_t)o.n * sizeof(int16_t)); }   // only the live part
+  IdxSet& operator=(const IdxSet& o) {
+    n = o.n;
+    std::memcpy(v, o.v, (size_t)o.n * sizeof(int16_t));
+    return *this;
+  }
+  void clear() { n = 0; }
+  bool has(int x) const {
+    for (int i = 0; i < n; i++)
+      if (v[i] >= x) return v[i] == x;
+    return false;
+  }
+  bool insert(int x) {
+    int i = 0;
+    while (i < n && v[i] < x) i++;
+    if (i < n && v[i] == x) return false;
+    if (n >= CAP) return false;                    // unreachable by the bounds above; never write past the array
+    for (int j = n; j > i; j--) v[j] = v[j - 1];
+    v[i] = (int16_t)x;
+    n++;
+    return true;
+  }
+  void erase(int x) {
+    for (int i = 0; i < n; i++) {
+      if (v[i] == x) {
+        for (int j = i; j + 1 < n; j++) v[j] = v[j + 1];
+        n--;
+        return;
+      }
+    }
+  }
+  bool operator==(const IdxSet& o) const { return n == o.n && std::memcmp(v, o.v, (size_t)n * sizeof(int16_t)) == 0; }
+  bool operator!=(const IdxSet& o) const { return !(*this == o); }
+};
+
+// the (at most four) own groups around one cell, sorted
+struct Ids4 {
+  int16_t v[4];
+  int n = 0;
+  void insert(int x) {
+    int i = 0;
+    while (i < n && v[i] < x) i++;
+    if (i < n && v[i] == x) return;
+    for (int j = n; j > i; j--) v[j] = v[j - 1];
+    v[i] = (int16_t)x;
+    n++;
+  }
+  bool operator!=(const Ids4& o) const {
+    if (n != o.n) return true;
+    for (int i = 0; i < n; i++)
+      if (v[i] != o.v[i]) return true;
+    return false;
+  }
+};
+
+struct LeanRules {
+  const LeanBoard& b;
+  int d[4];
+  // group labelling: gid[cell] = smallest cell index of the stone's group, -1 for empty, -2 for the border
+  int16_t gid[LeanBoard::MAXN];
+  int16_t n_libs[LeanBoard::MAXN];       // per group id
+  int16_t n_stones[LeanBoard::MAXN];
+  int32_t lib_off[LeanBoard::MAXN];      // per group id: offset of its sorted liberty list in lib_pool
+  int32_t stone_off[LeanBoard::MAXN];
+  int16_t lib_pool[4 * 361 + 8];
+  int16_t stone_pool[361 + 8];
+
+  explicit LeanRules(const LeanBoard& board) : b(board) {
+    d[0] = -1;
+    d[1] = -b.W;
+    d[2] = 1;
+    d[3] = b.W;
+    for (int i = 0; i < b.N; i++) gid[i] = (b.c[i] == LeanBoard::kEdge) ? -2 : -1;
+    int lp = 0, sp = 0;
+    LeanBoard::Group g;
+    for (int i = 0; i < b.N; i++) {
+      if ((b.c[i] != LeanBoard::kBlack && b.c[i] != LeanBoard::kWhite) || gid[i] >= 0) continue;
+      b.group(i, g);
+      int id = g.stones[0];
+      for (int k = 1; k < g.n_stones; k++) id = std::min<int>(id, g.stones[k]);
+      for (int k = 0; k < g.n_stones; k++) gid[g.stones[k]] = (int16_t)id;
+      n_libs[id] = (int16_t)g.n_libs;
+      n_stones[id] = (int16_t)g.n_stones;
+      lib_off[id] = lp;
+      stone_off[id] = sp;
+      for (int k = 0; k < g.n_libs; k++) lib_pool[lp++] = g.libs[k];
+      for (int k = 0; k < g.n_stones; k++) stone_pool[sp++] = g.stones[k];
+    }
+  }
+  int color_of(int cell) const { return b.c[cell]; }     // kEmpty / kBlack / kWhite / kEdge
+
+  // ---------------------------------------------------------------- Board::_isNakade (Board.cpp:1480-1591)
+  bool is_nakade(const IdxSet& positions) const {
+    const int length = 5;
+    const int arounds[4] = {1, -1, length, -length};
+    const int horizontals[4] = {1, -1, 1, -1};
+    const int verticals[4] = {length, length, -length, -length};
+    if (positions.n == 0 || positions.n >= 7) return false;
+    int start_x = b.w, start_y = b.h, end_x = 0, end_y = 0;
+    for (int k = 0; k < positions.n; k++) {
+      const int x = positions.v[k] % b.W - 1, y = positions.v[k] / b.W - 1;
+      start_x = std::min(x, start_x);
+      start_y = std::min(y, start_y);
+      end_x = std::max(x, end_x);
+      end_y = std::max(y, end_y);
+    }
+    if (end_x - start_x > 3 || end_y - start_y > 3) return false;
+    int board[length * length] = {0};
+    int corner[length * length] = {0};
+    for (int k = 0; k < positions.n; k++) {
+      const int sx = positions.v[k] % b.W - 1, sy = positions.v[k] / b.W - 1;
+      const int dx = sx - start_x + 1, dy = sy - start_y + 1;
+      // the reference writes board[dy*5+dx] with dx, dy up to 4: inside its 25-cell scratch board
+      board[dy * length + dx] = 1;
+      if ((sx == 0 || sx == b.w - 1) && (sy == 0 || sy == b.h - 1)) corner[dy * length + dx] = 1;
+    }
+    for (int y = 1; y < length - 1; y++) {
+      for (int x = 1; x < length - 1; x++) {
+        const int p = y * length + x;
+        if (board[p] != 1) continue;
+        int direct = 0;
+        for (int a : arounds) direct += board[p + a];
+        int skew = 0, corner_conn = 0;
+        for (int i = 0; i < 4; i++) {
+          const int v = verticals[i], h = horizontals[i];
+          if (board[p + v + h] != 1) continue;
+          if (corner_conn == 0 && corner[p + v] == 1 && board[p + v] == 1) {
+            corner_conn = 1;
+          } else if (corner_conn == 0 && corner[p + h] == 1 && board[p + h] == 1) {
+            corner_conn = 1;
+          } else if (skew == 0 && board[p + v] == 1 && board[p + h] == 1) {
+            skew = 1;
+          }
+        }
+        if (direct + skew + corner_conn >= positions.n - 1) return true;
+      }
+    }
+    return false;
+  }
+
+  // ---------------------------------------------------------------- Board::_isSingleArea (Board.cpp:1599-1631)
+  bool is_single_area(const IdxSet& positions, int color, int excluded) const {
+    const int op = -color;
+    IdxSet areas;
+    int16_t stack[LeanBoard::MAXN];
+    int sp = 0;
+    stack[sp++] = positions.v[0];
+    areas.insert(positions.v[0]);
+    while (sp > 0) {
+      const int pos = stack[--sp];
+      for (int a : d) {
+        const int t = pos + a;
+        if (t < 0 || t >= b.N) continue;                       // (the flood never leaves the bordered board)
+        if ((gid[t] == -1 || (gid[t] >= 0 && b.c[t] == op)) && t != excluded && !areas.has(t)) {
+          stack[sp++] = (int16_t)t;
+          areas.insert(t);
+        }
+      }
+    }
+    for (int k = 0; k < positions.n; k++)
+      if (!areas.has(positions.v[k])) return false;
+    return true;
+  }
+
+  // ---------------------------------------------------------------- Board::_isSekiRen (Board.cpp:1301-1376)
+  bool is_seki_ren(int index, int color, const IdxSet& ren_ids, int space_index) const {
+    const int op = -color;
+    IdxSet op_ids;
+    for (int a : d) {
+      const int targets[2] = {index + a, space_index + a};
+      for (int t : targets) {
+        const int id = gid[t];
+        if (t != index && t != space_index && id == -1) return false;
+        if (id >= 0 && b.c[t] == op) op_ids.insert(id);
+      }
+    }
+    if (op_ids.n == 0) return false;
+    for (int k = 0; k < op_ids.n; k++)
+      if (n_libs[op_ids.v[k]] != 2) return false;
+    // (a group of >= 6 stones plus the new stone is always "7 or more": same early exit as below)
+    for (int k = 0; k < ren_ids.n; k++)
+      if (n_stones[ren_ids.v[k]] >= 6) return true;
+    IdxSet positions;
+    positions.insert(index);
+    for (int k = 0; k < ren_ids.n; k++) {
+      const int id = ren_ids.v[k];
+      for (int i = 0; i < n_stones[id]; i++) positions.insert(stone_pool[stone_off[id] + i]);
+      if (positions.n >= 7) return true;
+    }
+    if (positions.n >= 4 && !is_nakade(positions)) return true;
+    IdxSet op_spaces;
+    for (int k = 0; k < op_ids.n; k++) {
+      const int id = op_ids.v[k];
+      for (int i = 0; i < n_libs[id]; i++) op_spaces.insert(lib_pool[lib_off[id] + i]);
+    }
+    op_spaces.erase(index);
+    op_spaces.erase(space_index);
+    return op_spaces.n != 0;
+  }
+
+  // ---------------------------------------------------------------- Board::_isSekiArea (Board.cpp:1386-1465)
+  bool is_seki_area(int index, int color, const IdxSet& ren_ids_in, const IdxSet& spaces) const {
+    const int op = -color;
+    IdxSet positions, ren_ids;
+    int16_t stack[LeanBoard::MAXN];
+    int sp = 0;
+    positions.insert(index);
+    stack[sp++] = (int16_t)index;
+    for (int k = 0; k < spaces.n; k++) {
+      positions.insert(spaces.v[k]);
+      stack[sp++] = spaces.v[k];
+    }
+    while (sp > 0) {
+      const int pos = stack[--sp];
+      for (int a : d) {
+        const int t = pos + a;
+        const int id = gid[t];
+        if ((id == -1 || (id >= 0 && b.c[t] == op)) && !positions.has(t)) {
+          stack[sp++] = (int16_t)t;
+          positions.insert(t);
+        }
+        if (id >= 0 && b.c[t] == color) ren_ids.insert(id);
+      }
+      if (positions.n >= 9) return false;
+    }
+    if (ren_ids != ren_ids_in) return false;
+    if (is_single_area(positions, color, -1)) {
+      for (int k = 0; k < positions.n; k++) {
+        const int pos = positions.v[k];
+        if (gid[pos] != -1) continue;
+        IdxSet tmp = positions;
+        tmp.erase(pos);
+        if (is_nakade(tmp)) return false;
+      }
+    }
+    positions.erase(index);
+    if (!is_single_area(positions, color, index)) return false;
+    for (int k = 0; k < positions.n; k++) {
+      const int pos = positions.v[k];
+      if (gid[pos] != -1) continue;
+      IdxSet tmp = positions;
+      tmp.erase(pos);
+      if (is_nakade(tmp)) return true;
+    }
+    return false;
+  }
+
+  // ---------------------------------------------------------------- Board::_isSeki (Board.cpp:1228-1291)
+  bool is_seki(int index, int color) const {
+    const int op = -color;
+    for (int a : d) {
+      const int id = gid[index + a];
+      if (id >= 0 && b.c[index + a] == op && n_libs[id] == 1) return false;
+    }
+    IdxSet ren_ids;
+    for (int a : d) {
+      const int id = gid[index + a];
+      if (id >= 0 && b.c[index + a] == color) ren_ids.insert(id);
+    }
+    if (ren_ids.n == 0) return false;
+    // the reference inserts every group's liberties and gives up once the union holds >= 9 cells (checked
+    // after each group): a group with >= 9 liberties of its own always ends there — skip the insertion work
+    for (int k = 0; k < ren_ids.n; k++)
+      if (n_libs[ren_ids.v[k]] >= 9) return false;
+    IdxSet spaces;
+    for (int a : d)
+      if (gid[index + a] == -1) spaces.insert(index + a);
+    for (int k = 0; k < ren_ids.n; k++) {
+      const int id = ren_ids.v[k];
+      for (int i = 0; i < n_libs[id]; i++) spaces.insert(lib_pool[lib_off[id] + i]);
+      if (spaces.n >= 9) return false;
+    }
+    spaces.erase(index);
+    if (spaces.n == 0) return false;
+    if (spaces.n == 1) return is_seki_ren(index, color, ren_ids, spaces.v[0]);
+    return is_seki_area(index, color, ren_ids, spaces);
+  }
+
+  // ---------------------------------------------------------------- Board::_isEnabled (Board.cpp:1177-1220)
+  bool enabled(int index, int color, bool check_seki) const {
+    if (gid[index] != -1) return false;
+    if (index == b.ko_index && color == b.ko_color) return false;
+    if (check_seki && is_seki(index, color)) return false;
+    const int op = -color;
+    for (int a : d) {
+      const int t = index + a;
+      if (gid[t] == -1) return true;
+      if (gid[t] < 0) continue;                                  // border
+      if (b.c[t] == color && n_libs[gid[t]] > 1) return true;
+      if (b.c[t] == op && n_libs[gid[t]] == 1) return true;
+    }
+    return false;
+  }
+
+  // ---------------------------------------------------------------- Board::_updateArea + getTerritories
+  // territories[y*w + x] = owner * color in {-1, 0, +1} (Board.cpp:350-378)
+  void territories(int color, int8_t* out) const {
+    bool fixed[LeanBoard::MAXN];                                 // per group id
+    std::memset(fixed, 0, sizeof fixed);
+    int16_t area_id[2][LeanBoard::MAXN];
+    bool area_flag[2][LeanBoard::MAXN];
+    for (int c = 0; c < 2; c++) {
+      const int col = (c == 0) ? LeanBoard::kBlack : LeanBoard::kWhite;
+      const int op = -col;
+      int16_t ids_v[LeanBoard::MAXN];                            // groups of this colour (their smallest cells)
+      int ids_n = 0;
+      for (int i = 0; i < b.N; i++)
+        if (gid[i] == i && b.c[i] == col) ids_v[ids_n++] = (int16_t)i;
+      // (group, decided area) registrations of this colour: Ren::areas of the reference, as a flat pair list
+      int16_t pair_group[4 * LeanBoard::MAXN], pair_area[4 * LeanBoard::MAXN];
+      int n_pairs = 0;
+      for (int k = 0; k < ids_n; k++) fixed[ids_v[k]] = true;
+      bool checks[LeanBoard::MAXN];
+      std::memset(checks, 0, sizeof checks);
+      std::memset(area_flag[c], 0, sizeof area_flag[c]);
+      for (int index = 0; index < b.N; index++) {
+        if (checks[index]) continue;
+        const int ic = b.c[index];
+        if (ic != LeanBoard::kEmpty && ic != op) {
+          area_id[c][index] = -1;
+          continue;
+        }
+        Ids4 connected;
+        for (int a : d) {
+          const int t = index + a;
+          if (t >= 0 && t < b.N && b.c[t] == col) connected.insert(gid[t]);
+        }
+        int16_t stack[4 * LeanBoard::MAXN];
+        int sp = 0;
+        stack[sp++] = (int16_t)index;
+        area_flag[c][index] = true;
+        while (sp > 0) {
+          const int pos = stack[--sp];
+          if (checks[pos]) continue;
+          checks[pos] = true;
+          area_id[c][pos] = (int16_t)index;
+          Ids4 around;
+          for (int a : d) {
+            const int t = pos + a;
+            if (gid[t] >= 0 && b.c[t] == col) around.insert(gid[t]);
+          }
+          if (around.n == 0) area_flag[c][pos] = false;
+          if (around != connected) area_flag[c][index] = false;
+          for (int a : d) {
+            const int t = pos + a;
+            const int tc = b.c[t];
+            if (tc == LeanBoard::kEmpty || tc == op) stack[sp++] = (int16_t)t;
+          }
+        }
+        if (area_flag[c][index]) {
+          for (int k = 0; k < connected.n; k++) {
+            pair_group[n_pairs] = connected.v[k];
+            pair_area[n_pairs++] = (int16_t)index;
+          }
+        }
+      }
+      // Greatest fixed point of "a group stays decided while >= 2 of its areas are decided; an area of an
+      // undecided group is undecided" (Board.cpp:988-1032). Flags only ever fall, so the order in which the
+      // reference visits the groups does not change the result: count per sweep instead of per group.
+      bool updated = true;
+      int16_t cnt[LeanBoard::MAXN];
+      while (updated) {
+        updated = false;
+        for (int k = 0; k < ids_n; k++) cnt[ids_v[k]] = 0;
+        for (int i = 0; i < n_pairs; i++)
+          if (area_flag[c][pair_area[i]]) cnt[pair_group[i]]++;
+        for (int k = 0; k < ids_n; k++)
+          if (fixed[ids_v[k]] && cnt[ids_v[k]] < 2) fixed[ids_v[k]] = false;
+        for (int i = 0; i < n_pairs; i++) {
+          if (!fixed[pair_group[i]] && area_flag[c][pair_area[i]]) {
+            area_flag[c][pair_area[i]] = false;
+            updated = true;
+          }
+        }
+      }
+    }
+    for (int y = 0; y < b.h; y++) {
+      for (int x = 0; x < b.w; x++) {
+        const int index = b.index(x, y);
+        const int id = gid[index];
+        int8_t t = 0;
+        if (id >= 0 && fixed[id]) {
+          t = (int8_t)(b.c[index] * color);
+        } else if (area_id[0][index] != -1 && area_flag[0][area_id[0][index]]) {
+          t = (int8_t)(LeanBoard::kBlack * color);
+        } else if (area_id[1][index] != -1 && area_flag[1][area_id[1][index]]) {
+          t = (int8_t)(LeanBoard::kWhite * color);
+        }
+        out[y * b.w + x] = t;
+      }
+    }
+  }
+
+  // bit (y*w + x) of mask = legal (seki-checked) AND not decided territory (Evaluator.cpp:60-68)
+  void move_mask(int color, uint8_t* mask48) const {
+    int8_t terr[361];
+    territories(color, terr);
+    std::memset(mask48, 0, 48);
+    for (int y = 0; y < b.h; y++)
+      for (int x = 0; x < b.w; x++) {
+        const int i = y * b.w + x;
+        if (terr[i] == 0 && enabled(b.index(x, y), color, true)) mask48[i >> 3] |= (uint8_t)(1u << (i & 7));
+      }
+  }
+};
+
+}  // namespace maru_b200

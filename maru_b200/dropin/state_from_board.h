@@ -18,14 +18,16 @@
 #include <utility>
 #include <vector>
 
-#include "lean_ladder.h"
+#include "lean_rules.h"
 #include "maru_b200.h"
 
 namespace maru_b200 {
 
 // lean_ladder: take the ladder flags from the flat-board read-out of lean_ladder.h (bit-identical to
 // Board::isShicho, 20-45x cheaper: the reference copies a whole std::set-based Board per search step)
-// instead of calling Board::isShicho, which triggers Board::_updateShicho (Board.cpp:303-313, 1045-1067).
+// instead of calling Board::isShicho, which triggers Board::_updateShicho (Board.cpp:303-313, 1045-1067),
+// and the move mask from lean_rules.h instead of Board::getEnableds(checkSeki) / getTerritories
+// (identical on every cell, tests/test_lean_rules.py).
 template <class BoardT>
 inline void state_from_board(BoardT* board, int32_t color, float komi, int32_t rule, bool superko,
                              bool with_move_mask, maru_state* st, bool lean_ladder = false) {
@@ -40,8 +42,8 @@ inline void state_from_board(BoardT* board, int32_t color, float komi, int32_t r
   st->komi = komi;
 
   uint8_t ladder[361];
+  LeanBoard lb;
   if (lean_ladder) {
-    LeanBoard lb;
     lb.init(w, h);
     for (int32_t y = 0; y < h; y++)
       for (int32_t x = 0; x < w; x++) {
@@ -94,7 +96,11 @@ inline void state_from_board(BoardT* board, int32_t color, float komi, int32_t r
     st->ko_y = MARU_NONE;
   }
 
-  if (with_move_mask) {
+  if (with_move_mask && lean_ladder) {
+    LeanRules rules(lb);
+    rules.move_mask(color, st->move_mask);
+    st->flags |= MARU_STATE_HAS_MASK;
+  } else if (with_move_mask) {
     std::unique_ptr<int32_t[]> enableds(new int32_t[w * h]);
     std::unique_ptr<int32_t[]> territories(new int32_t[w * h]);
     board->getEnableds(enableds.get(), color, true);
