@@ -95,7 +95,33 @@ class ClockSampler:
         self.gpu, self.samples, self.stop = gpu, [], threading.Event()
         self.th = threading.Thread(target=self.run, daemon=True)
 
+    def run_nvml(self) -> bool:
+        """Fast path: poll NVML directly (~1 ms per sample) so that even a 20 ms timed region is covered by
+        many samples; nvidia-smi (one process per sample, ~50 ms) is the fallback."""
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons', None) or \
+                nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception:
+            return False
+        bits = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.samples.append([str(sm), str(mx), '0'] +
+                                    ['Active' if r & b else 'Not Active' for b in (0x8, 0x40, 0x20, 0x4)])
+            except Exception:
+                pass
+            self.stop.wait(0.001)
+        return True
+
     def run(self):
+        if self.run_nvml():
+            return
         while not self.stop.is_set():
             try:
                 out = subprocess.run(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.QUERY}',
