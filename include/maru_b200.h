@@ -229,6 +229,17 @@ int  maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, in
 int  maru_rules_eval(const int8_t* colors, int width, int height, int ko_x, int ko_y, int ko_color,
                      int color, uint8_t* enableds, int8_t* territories);
 
+/* A whole position on the flat board (maru_b200/dropin/lean_game.h): Board::play semantics (captures, ko,
+ * pass = off-board coordinates, 3-move history per colour, Board.cpp:140-205) and the compact record built
+ * without a reference Board — byte-identical to state_from_board() over the reference Board. Host code. */
+typedef struct maru_game maru_game;
+maru_game* maru_game_create(int width, int height);
+maru_game* maru_game_clone(const maru_game* g);
+void maru_game_destroy(maru_game* g);
+int  maru_game_play(maru_game* g, int x, int y, int color);      /* captured stones, 0 = pass, -1 = illegal */
+int  maru_game_state(const maru_game* g, int color, float komi, int rule, int superko, int with_move_mask,
+                     maru_state* out);
+
 /* ---- errors ---------------------------------------------------------------------------------- */
 const char* maru_last_error(void);      /* thread-local text of the last failing call              */
 int  maru_abi_version(void);

@@ -55,7 +55,8 @@ ABI_SYMBOLS = [
     'maru_encode_planes_device', 'maru_eval_debug_planes', 'maru_eval_debug_policy_logits',
     'maru_eval_debug_set', 'maru_eval_debug_trace', 'maru_eval_debug_timeline', 'maru_eval_debug_stamps', 'maru_eval_profile_states',
     'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
-    'maru_queue_get_stats', 'maru_ladder_flags', 'maru_rules_eval', 'maru_last_error', 'maru_abi_version',
+    'maru_queue_get_stats', 'maru_ladder_flags', 'maru_rules_eval', 'maru_game_create', 'maru_game_clone',
+    'maru_game_destroy', 'maru_game_play', 'maru_game_state', 'maru_last_error', 'maru_abi_version',
 ]
 
 
@@ -110,6 +111,14 @@ def load_library():
     lib.maru_queue_get_stats.argtypes = [vp, C.POINTER(QueueStats)]
     lib.maru_ladder_flags.argtypes = [vp, ci, ci, ci, ci, ci, vp]
     lib.maru_rules_eval.argtypes = [vp, ci, ci, ci, ci, ci, ci, vp, vp]
+    lib.maru_game_create.argtypes = [ci, ci]
+    lib.maru_game_create.restype = vp
+    lib.maru_game_clone.argtypes = [vp]
+    lib.maru_game_clone.restype = vp
+    lib.maru_game_destroy.argtypes = [vp]
+    lib.maru_game_destroy.restype = None
+    lib.maru_game_play.argtypes = [vp, ci, ci, ci]
+    lib.maru_game_state.argtypes = [vp, ci, C.c_float, ci, ci, ci, vp]
     lib.maru_last_error.restype = C.c_char_p
     lib.maru_abi_version.restype = ci
     _lib = lib
@@ -145,6 +154,39 @@ def rules_eval(colors: np.ndarray, color: int, ko: Optional[tuple] = None):
     _check(lib, lib.maru_rules_eval(col.ctypes.data, w, h, kx, ky, kc, color, en.ctypes.data, te.ctypes.data),
            'maru_rules_eval')
     return en, te
+
+
+class LeanGame:
+    """A position on the flat host board (maru_game_*): Board::play semantics and the compact record,
+    byte-identical to the reference Board + state_from_board, without building a reference Board."""
+
+    def __init__(self, width: int = 19, height: int = 19, _handle=None):
+        self.lib = load_library()
+        self.width, self.height = width, height
+        self.handle = _handle if _handle is not None else self.lib.maru_game_create(width, height)
+        if not self.handle:
+            raise MaruB200Error(self.lib.maru_last_error().decode(errors='replace') or 'maru_game_create failed')
+
+    def copy(self) -> 'LeanGame':
+        return LeanGame(self.width, self.height, self.lib.maru_game_clone(self.handle))
+
+    def play(self, x: int, y: int, color: int) -> int:
+        return self.lib.maru_game_play(self.handle, x, y, color)
+
+    def state(self, color: int, komi: float = 7.5, rule: int = 0, superko: bool = False,
+              with_mask: bool = False) -> np.ndarray:
+        out = np.zeros(STATE_SIZE, np.uint8)
+        _check(self.lib, self.lib.maru_game_state(self.handle, color, float(komi), rule, int(superko),
+                                                  int(with_mask), out.ctypes.data), 'maru_game_state')
+        return out
+
+    def close(self) -> None:
+        if getattr(self, 'handle', None):
+            self.lib.maru_game_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
 
 
 def ensure_pack(model: str | Path) -> Path:

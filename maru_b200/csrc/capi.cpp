@@ -1,5 +1,5 @@
 // capi.cpp — extern "C" surface of libmaru_b200.so (declared in include/maru_b200.h).
-#include "../dropin/lean_rules.h"
+#include "../dropin/lean_game.h"
 #include <cstring>
 #include <new>
 
@@ -213,6 +213,35 @@ int maru_eval_debug_stamps(maru_eval* ev, long long* out) {
   CKC(cudaSetDevice(e->gpu_id));
   CKC(cudaStreamSynchronize(e->stream));
   CKC(cudaMemcpy(out, e->d_stamps, 512 * sizeof(long long), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+struct maru_game {
+  maru_b200::LeanGame g;
+};
+
+maru_game* maru_game_create(int width, int height) {
+  if (width < 1 || height < 1 || width > 19 || height > 19) {
+    maru::set_error("maru_game_create: bad board size");
+    return nullptr;
+  }
+  maru_game* p = new (std::nothrow) maru_game();
+  if (p != nullptr) p->g.init(width, height);
+  return p;
+}
+maru_game* maru_game_clone(const maru_game* g) { return g ? new (std::nothrow) maru_game(*g) : nullptr; }
+void maru_game_destroy(maru_game* g) { delete g; }
+int maru_game_play(maru_game* g, int x, int y, int color) {
+  if (g == nullptr || (color != 1 && color != -1)) return -1;
+  return g->g.play(x, y, color);
+}
+int maru_game_state(const maru_game* g, int color, float komi, int rule, int superko, int with_move_mask,
+                    maru_state* out) {
+  if (g == nullptr || out == nullptr || (color != 1 && color != -1)) {
+    maru::set_error("maru_game_state: bad argument");
+    return 1;
+  }
+  g->g.to_state(color, komi, rule, superko != 0, with_move_mask != 0, out);
   return 0;
 }
 
