@@ -408,7 +408,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   if (tl && threadIdx.x == 0) tl[5] = globaltimer_ns();
   if (warp == 1) {
     tc_fence_after();
+    if (tl && threadIdx.x == 32) tl[7] = globaltimer_ns();
     tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    if (tl && threadIdx.x == 32) tl[6] = globaltimer_ns();     // after the TMEM release: the CTA's last instruction
   }
 }
 

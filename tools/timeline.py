@@ -22,6 +22,7 @@ for i in range(64):
     if tl[i, 0, 0] == 0: continue
     a = (tl[i, 0, :6] - t0) / 1e3
     b = (tl[i, 1, :6] - t0) / 1e3
-    print(f'{i:3d} {a[0]:7.1f} {a[1]:7.1f} {a[2]:7.1f} {a[3]:7.1f} {a[4]:7.1f} {a[5]:7.1f} | {b[0]:7.1f} {b[2]:7.1f} {b[5]:7.1f}   dur {a[5]-a[0]:5.1f}  gap-from-prev-exit {a[0]-prev_exit:5.1f}')
+    dealloc = (tl[i, 0, 6] - tl[i, 0, 5]) / 1e3 if tl[i, 0, 6] else float('nan')
+    print(f'{i:3d} {a[0]:7.1f} {a[1]:7.1f} {a[2]:7.1f} {a[3]:7.1f} {a[4]:7.1f} {a[5]:7.1f} | {b[0]:7.1f} {b[2]:7.1f} {b[5]:7.1f}   dur {a[5]-a[0]:5.1f}  gap-from-prev-exit {a[0]-prev_exit:5.1f}  tmem-dealloc {dealloc:5.2f} (fence {(tl[i,0,7]-tl[i,0,5])/1e3:5.2f})')
     prev_exit = max(a[5], b[5])
 ev.close()
