@@ -331,7 +331,7 @@ def run_b200(args):
     prof = {}
     for rep in range(max(3, min(args.steps, 10))):
         for l in ev.profile_states_device(d_states.data_ptr(), d_out.data_ptr(), B):
-            key = (l['kind'], l['cin'], l['cout'], l['taps'])
+            key = (l['kind'], l['cin'], l['cout'], l['taps'], l['name'] if l['kind'] == 5 else '')
             a = prof.setdefault(key, dict(ms=0.0, flops=0.0, bytes=0.0, launches=0, name=l['name']))
             if rep > 0:                                            # first rep = warm-up
                 a['ms'] += l['ms']; a['flops'] += l['flops']; a['bytes'] += l['bytes']; a['launches'] += 1
@@ -350,29 +350,37 @@ def run_b200(args):
 
     if rank == 0:
         peaks = load_peaks()
-        kinds = {0: 'encode', 1: 'conv3x3', 2: 'conv1x1', 3: 'attention', 4: 'heads'}
+        kinds = {0: 'encode', 1: 'conv3x3', 2: 'conv1x1', 3: 'attention', 4: 'heads', 5: 'conv flow'}
         table = []
         tot_ms = sum(a['ms'] for a in prof.values()) or 1.0
         for key, a in sorted(prof.items(), key=lambda kv: -kv[1]['ms']):
             if a['launches'] == 0:
                 continue
-            table.append(dict(kernel=f"{kinds[key[0]]} {key[1]}->{key[2]}", example=a['name'],
+            table.append(dict(kernel=f"{kinds[key[0]]} {key[1]}->{key[2]}" if key[0] != 5 else 'conv_flow (persistent multi-layer)',
+                              example=a['name'],
                               launches_per_step=a['launches'] // max(1, (max(3, min(args.steps, 10)) - 1)),
                               us_per_launch=a['ms'] / a['launches'] * 1e3, share=a['ms'] / tot_ms,
                               tflops=a['flops'] / (a['ms'] / 1e3) / 1e12 if a['flops'] else None,
                               gbs=a['bytes'] / (a['ms'] / 1e3) / 1e9))
-        dom_key = max((k for k in prof if k[0] == 1 and prof[k]['launches']), key=lambda k: prof[k]['ms'])
+        # dominant kernel: the persistent conv kernel (a whole chain of 3x3 / 1x1 layers per launch) when the
+        # forward uses it, else the busiest one-layer 3x3 conv
+        dom_key = max((k for k in prof if k[0] in (1, 5) and prof[k]['launches']), key=lambda k: prof[k]['ms'])
         dom = prof[dom_key]
         achieved = dom['flops'] / (dom['ms'] / 1e3) / 1e12
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
-            cap = json.loads((ROOT / 'profiles' / 'r1_conv3x3_ncu_full.json').read_text())
-            traffic = cap['_traffic_bytes_per_launch']['blk0.in0.c1']
+            if dom_key[0] == 5:
+                cap = json.loads((ROOT / 'profiles' / 'r1_conv_flow_ncu_full.json').read_text())
+                traffic = cap['_traffic_bytes_per_launch'][dom['name'].split('[')[0]]
+            else:
+                cap = json.loads((ROOT / 'profiles' / 'r1_conv3x3_ncu_full.json').read_text())
+                traffic = cap['_traffic_bytes_per_launch']['blk0.in0.c1']
         except Exception:
             pass
         roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16_burst'], unit='TFLOP/s',
                         frac=achieved / peaks['bf16_burst'], traffic=traffic,
-                        kernel=f'conv_gemm 3x3 {dom_key[1]}->{dom_key[2]} ({dom["launches"]} timed launches)',
+                        kernel=(f'conv_flow {dom["name"]} ({dom["launches"]} timed launches)' if dom_key[0] == 5 else
+                                f'conv_gemm 3x3 {dom_key[1]}->{dom_key[2]} ({dom["launches"]} timed launches)'),
                         peak_source=peaks['source'] + ' (burst, kernel timed alone)',
                         flops_per_launch=dom['flops'] / dom['launches'],
                         us_per_launch=dom['ms'] / dom['launches'] * 1e3,

@@ -158,20 +158,23 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * the heads then do not run). key 1: bit0 = disable programmatic dependent launch (A/B timing), bit2 = use the legacy
  * mma.sync attention kernel instead of the tcgen05 one (A/B), bit3 = enable the experimental
  * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower),
- * bit5 = run consecutive conv layers as persistent multi-layer chain kernels with grid barriers
- * (conv_chain.cu; correct, measured slower than one PDL launch per layer), bit6 = with bit5: record
- * per-layer stamps (maru_eval_debug_stamps). */
+ * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
+ * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
+ * (maru_eval_debug_stamps), bits 8-9 = timing experiments that drop the flow epilogue's fences (results
+ * may be wrong). */
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
 #define MARU_DBG_TRACE_LAUNCH 2       /* index of the trunk launch whose pipeline is traced (-1: off) */
 #define MARU_DBG_TIMELINE 3           /* 1: every conv launch stamps %globaltimer (see debug_timeline)  */
+#define MARU_DBG_FLOW_TRACE_CTA 4     /* >= 0: that CTA of a flow kernel stamps every item (debug_trace, [256][8]) */
+#define MARU_DBG_FLOW_TRACE_LAUNCH 5  /* which flow launch of the forward is traced (default 0)          */
 int  maru_eval_debug_set(maru_eval* e, int key, int value);
 /* [64 launches][first CTA, last CTA][8] ns stamps: entry, prologue done, dependency resolved, first
  * operands landed, first accumulator ready, exit. */
 int  maru_eval_debug_timeline(maru_eval* e, long long* out);
-/* Persistent chain kernels (debug key 1 bit6 set): [128 layers][4] ns stamps of CTA 0 — layer start,
- * first operands landed, CTA done with the layer, weights landed — chains back to back, each followed
- * by one [end, 0, 0, 0] row. */
+/* Persistent flow kernels (debug key 1 bit6 set): [128 layers][4] ns stamps of CTA 0 — producer enters
+ * the layer, weights landed, epilogue done with the layer — chains back to back, each followed by one
+ * [end, 0, 0, 0] row. */
 int  maru_eval_debug_stamps(maru_eval* e, long long* out);
 /* clock64 stamps of the traced conv launch: [n_ctas][32 tiles][8] = producer {wait,issue}, MMA warp
  * {wait start, operands ready, issued}, epilogue warp {wait start, accumulator ready, done}. */

@@ -301,6 +301,8 @@ int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   else if (key == MARU_DBG_DESC_BITS) e->dbg_desc = value;
   else if (key == MARU_DBG_TRACE_LAUNCH) e->dbg_trace_launch = value;
   else if (key == MARU_DBG_TIMELINE) e->dbg_timeline = value;
+  else if (key == MARU_DBG_FLOW_TRACE_CTA) e->dbg_flow_trace_cta = value;
+  else if (key == MARU_DBG_FLOW_TRACE_LAUNCH) e->dbg_flow_trace_chain = value;
   else {
     maru::set_error("maru_eval_debug_set: unknown key");
     return 1;

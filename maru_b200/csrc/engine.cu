@@ -166,17 +166,17 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
   allocs.push_back(L.w);
   allocs.push_back(L.b);
 
-  // chain blob: per channel group [TAPS][KCH][nt][8] weights followed by the bias operand of the bias
+  // flow blob: per channel group [TAPS][KCH][nt][8] weights followed by the bias operand of the bias
   // MMA ([2 k-chunks][nt rows][8]: (hi, lo, 0...) in chunk 0) -> one bulk copy per CTA and layer
   const int cands[4] = {L.nt, 128, 64, 32};
   for (int nt : cands) {
-    if (cout % nt == 0 && conv_chain_supports(cin, nt, taps)) {
-      L.nt_chain = nt;
+    if (cout % nt == 0 && conv_flow_supports(cin, nt, taps)) {
+      L.nt_flow = nt;
       break;
     }
   }
-  if (L.nt_chain > 0) {
-    const int nt = L.nt_chain, groups = cout / nt;
+  if (L.nt_flow > 0) {
+    const int nt = L.nt_flow, groups = cout / nt;
     const size_t wb = (size_t)taps * cin * nt * 2, bb = (size_t)2 * nt * 16;
     std::vector<uint8_t> blob((wb + bb) * groups, 0);
     const float* bias = reinterpret_cast<const float*>(pk.data.data() + b->offset);
@@ -252,6 +252,8 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     return 1;
   }
   gpu_id = gpu;
+  device_ref(+1);
+  dev_counted = true;
   max_batch = max_batch_ > 0 ? max_batch_ : 256;
   flags = flags_;
   CK(cudaSetDevice(gpu_id));
@@ -263,7 +265,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   }
   sm_count = prop.multiProcessorCount;
   CK(configure_conv_gemm());
-  CK(configure_conv_chain());
+  CK(configure_conv_flow());
   CK(configure_attention());
   CK(configure_misc_kernels());
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -329,8 +331,8 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     CK(cudaMalloc(&d_flags, flags_bytes));
     CK(cudaMemset(d_flags, 0, flags_bytes));
     allocs.push_back(d_flags);
-    CK(cudaMalloc(&d_sync, 256 * sizeof(unsigned)));
-    CK(cudaMemset(d_sync, 0, 256 * sizeof(unsigned)));
+    CK(cudaMalloc(&d_sync, 2 * 256 * sizeof(unsigned)));
+    CK(cudaMemset(d_sync, 0, 2 * 256 * sizeof(unsigned)));
     allocs.push_back(d_sync);
     CK(cudaMalloc(&d_stamps, 512 * sizeof(long long)));
     CK(cudaMemset(d_stamps, 0, 512 * sizeof(long long)));
@@ -383,6 +385,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
 }
 
 Engine::~Engine() {
+  if (dev_counted) device_ref(-1);
   if (gpu_id >= 0) cudaSetDevice(gpu_id);
   if (stream) cudaStreamSynchronize(stream);
   for (auto& kv : graphs)
@@ -451,6 +454,65 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   p.seq = launches_done;
   if (dbg_stop_after >= 0 && launches_done >= dbg_stop_after) return 0;
   launches_done++;
+  // Flow mode (default): consecutive conv layers are collected and launched as ONE persistent kernel by
+  // flush_chain() (conv_flow.cu). Layers whose weights or slabs do not fit next to the chain's (e.g. the
+  // 147 KB stem) run as one PDL launch each, and so does everything when a debug knob asks for per-layer
+  // behaviour (stop-after, traces, timeline, tile flags) or another engine shares the device.
+  const bool flowable = flow_enabled() && !use_flags && p.trace == nullptr && p.timeline == nullptr && L.nt_flow > 0;
+  if (flowable) {
+    const int groups = L.cout / L.nt_flow;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      const int blob = (conv_flow_blob_bytes(L.cin, L.nt_flow, L.taps) + 1023) & ~1023;
+      const int w_new = blob > pending_w ? blob : pending_w;
+      bool fits = pending.n_layers + groups <= FLOW_MAX && conv_flow_fits(L.cin, L.nt_flow, L.taps, w_new);
+      for (int k = 0; fits && k < pending.n_layers; k++) {
+        const FlowLayer& Q = pending.layer[k];
+        fits = conv_flow_fits(Q.cin, Q.nt, Q.taps, w_new);
+      }
+      if (fits) {
+        for (int grp = 0; grp < groups; grp++) {
+          FlowLayer& Q = pending.layer[pending.n_layers + grp];
+          Q.in = p.in;
+          Q.res = p.res;
+          Q.out = p.out;
+          Q.blob = L.blob + (size_t)grp * conv_flow_blob_bytes(L.cin, L.nt_flow, L.taps);
+          Q.in_blocked = p.in_blocked;
+          Q.in_planes = p.in_planes;
+          Q.res_blocked = p.res_blocked;
+          Q.res_planes = p.res_planes;
+          Q.out_blocked = p.out_blocked;
+          Q.out_planes = p.out_planes;
+          Q.out_chunk0 = grp * (L.nt_flow / 8);
+          Q.cin = L.cin;
+          Q.nt = L.nt_flow;
+          Q.taps = L.taps;
+          Q.relu = relu;
+        }
+        if (pending.n_layers == 0) {
+          pending_single = p;
+          pending_first = &L;
+          pending.m_rows = p.m_rows;
+          pending.n_dev = n_dev;
+          pending.pdl = p.pdl;
+          pending_flops = pending_bytes = 0.0;
+          pending_convs = 0;
+        }
+        pending.n_layers += groups;
+        pending_convs++;
+        pending_w = w_new;
+        {
+          const double T = (double)CELLS * n;
+          pending_flops += 2.0 * T * L.cin * L.cout * L.taps;
+          pending_bytes += T * (L.cin + L.cout + (res ? L.cout : 0)) * 2.0 + (double)L.taps * L.cin * L.cout * 2.0;
+        }
+        out.flagged = false;
+        return 0;
+      }
+      if (pending.n_layers == 0) break;       // does not fit even alone: one-layer launch below
+      if (flush_chain(st)) return 1;
+    }
+  }
+  if (flush_chain(st)) return 1;
   {
     // algorithmic figures at T = 361 on-board tokens per position (stem: 33 planes + 7 infos)
     const double T = (double)CELLS * n;
@@ -460,56 +522,6 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
     const double by = T * (cin_alg + L.cout + (res ? L.cout : 0)) * 2.0 + (double)L.taps * L.cin * L.cout * 2.0;
     prof_begin(L.name.c_str(), L.taps == 9 ? 1 : 2, L.cin, L.cout, L.taps, fl, by, st);
   }
-  // Chain mode (EXPERIMENT, debug bit 5; measured slower, DESIGN.md "what did not work"): consecutive
-  // conv layers are collected and launched as ONE persistent kernel by flush_chain(). The default is one
-  // PDL launch per layer; layers whose weights leave no room for two pipeline stages next to the
-  // chain's always run that way.
-  const bool chainable = prof == nullptr && !use_flags && (dbg_desc & 32) && p.trace == nullptr &&
-                         p.timeline == nullptr && L.nt_chain > 0;
-  if (chainable) {
-    for (int attempt = 0; attempt < 2; attempt++) {
-      const int blob = (conv_chain_blob_bytes(L.cin, L.nt_chain, L.taps) + 1023) & ~1023;
-      const int w_new = blob > pending_w ? blob : pending_w;
-      bool fits = pending.n_layers < CHAIN_MAX && conv_chain_stages(L.cin, L.nt_chain, L.taps, res != nullptr, w_new) >= 2;
-      for (int k = 0; fits && k < pending.n_layers; k++) {
-        const ChainLayer& Q = pending.layer[k];
-        fits = conv_chain_stages(Q.cin, Q.nt, Q.taps, Q.res != nullptr, w_new) >= 2;
-      }
-      if (fits) {
-        ChainLayer& Q = pending.layer[pending.n_layers];
-        Q.in = p.in;
-        Q.res = p.res;
-        Q.out = p.out;
-        Q.blob = L.blob;
-        Q.in_blocked = p.in_blocked;
-        Q.in_planes = p.in_planes;
-        Q.res_blocked = p.res_blocked;
-        Q.res_planes = p.res_planes;
-        Q.out_blocked = p.out_blocked;
-        Q.out_planes = p.out_planes;
-        Q.cin = L.cin;
-        Q.nt = L.nt_chain;
-        Q.taps = L.taps;
-        Q.cout_total = L.cout;
-        Q.relu = relu;
-        Q.stages = 0;
-        if (pending.n_layers == 0) {
-          pending_single = p;
-          pending_first = &L;
-          pending.m_rows = p.m_rows;
-          pending.n_dev = n_dev;
-          pending.pdl = p.pdl;
-        }
-        pending.n_layers++;
-        pending_w = w_new;
-        out.flagged = false;
-        return 0;
-      }
-      if (pending.n_layers == 0) break;       // does not fit even alone: one-layer launch below
-      if (flush_chain(st)) return 1;
-    }
-  }
-  if (flush_chain(st)) return 1;
   n_launched++;
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
     CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
@@ -601,27 +613,52 @@ int Engine::flush_chain(cudaStream_t st) {
   const int nl = pending.n_layers;
   pending.n_layers = 0;
   pending_w = 0;
-  if (nl == 1) {
-    CK(launch_conv_gemm(pending_single, pending_first->cin, pending_first->nt, pending_first->taps, sm_count, st));
+  if (pending_convs == 1 && nl == 1) {
+    // a chain of one layer: the one-layer kernel (its launch boundary overlaps the neighbours' through PDL)
+    prof_begin(pending_first->name.c_str(), pending_first->taps == 9 ? 1 : 2, pending_first->cin, pending_first->cout,
+               pending_first->taps, pending_flops, pending_bytes, st);
+    for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
+      CK(launch_conv_gemm(pending_single, pending_first->cin, pending_first->nt, pending_first->taps, sm_count, st));
+    prof_end(st);
     return 0;
-  }
-  if (sync_used + nl > 256) {
-    set_error("internal: too many chained layers in one forward");
-    return 1;
   }
   pending.n_layers = nl;
   pending.mask = mask;
   pending.rows_alloc = rows_alloc;
-  pending.sync = d_sync + sync_used;
-  pending.stamps = (dbg_desc & 64) ? d_stamps + stamps_used : nullptr;
-  pending.trace = (dbg_desc & 64) && stamps_used == 0 && dbg_trace_launch >= 0 ? d_stamps + 256 : nullptr;   // first chain only
-  pending.trace_layer = dbg_trace_launch;
-  sync_used += nl;
+  pending.flags = d_sync;
+  pending.stamps = (dbg_desc & 64) && stamps_used + 4 * nl + 4 <= 512 ? d_stamps + stamps_used : nullptr;
   stamps_used += 4 * nl + 4;
-  const cudaError_t e = launch_conv_chain(pending, sm_count, st);
+  // bring-up: debug key 2 (trace launch) = -(1 + cta) traces that CTA of the FIRST flow kernel of the forward
+  pending.trace = (dbg_flow_trace_cta >= 0 && n_flow_launches == dbg_flow_trace_chain) ? d_trace : nullptr;
+  pending.trace_cta = dbg_flow_trace_cta;
+  pending.dbg = (dbg_desc >> 8) & 15;
+  char name[48];
+  snprintf(name, sizeof name, "flow%d[%s..%d layers]", n_flow_launches++, pending_first->name.c_str(), pending_convs);
+  prof_begin(name, 5, 0, 0, 0, pending_flops, pending_bytes, st);
+  cudaError_t e = cudaSuccess;
+  for (int rep = 0; rep < (prof ? prof_reps : 1) && e == cudaSuccess; rep++) {
+    pending.flag_base = flag_next;      // flags only grow: every launch of a forward gets its own value range
+    flag_next += (unsigned)nl;
+    e = launch_conv_flow(pending, sm_count, st);
+  }
+  prof_end(st);
   pending.n_layers = 0;
   CK(e);
   return 0;
+}
+
+// The flow kernel spins on flags written by the other CTAs of its grid: every CTA must become resident,
+// which holds when the engine has the device to itself (one stream, kernels of a forward in order).
+static std::mutex g_dev_mu;
+static int g_engines_on_device[64] = {0};
+void Engine::device_ref(int delta) {
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  if (gpu_id >= 0 && gpu_id < 64) g_engines_on_device[gpu_id] += delta;
+}
+bool Engine::flow_enabled() {
+  if ((dbg_desc & 32) || dbg_stop_after >= 0 || dbg_timeline || dbg_trace_launch >= 0) return false;
+  std::lock_guard<std::mutex> lock(g_dev_mu);
+  return gpu_id >= 0 && gpu_id < 64 && g_engines_on_device[gpu_id] == 1;
 }
 
 void Engine::clear_graphs() {
@@ -635,8 +672,9 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
   {
     // per-tile completion counters start from zero in every forward (also under graph replay)
     CK(cudaMemsetAsync(d_flags, 0, flags_bytes, st));
-    CK(cudaMemsetAsync(d_sync, 0, 256 * sizeof(unsigned), st));
-    sync_used = 0;
+    CK(cudaMemsetAsync(d_sync, 0, 2 * 256 * sizeof(unsigned), st));
+    flag_next = 0;
+    n_flow_launches = 0;
     stamps_used = 0;
     pending.n_layers = 0;
     pending_w = 0;
@@ -753,7 +791,7 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
   } else {
     // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
     const int bucket = bucket_for(n, max_batch);
-    GraphKey key{kind, bucket, d_in, d_out};
+    GraphKey key{kind, bucket, d_in, d_out, flow_enabled()};
     auto it = graphs.find(key);
     if (it == graphs.end()) {
       cudaGraph_t gr = nullptr;

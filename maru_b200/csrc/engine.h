@@ -23,10 +23,10 @@ struct ConvLayer {
   int cin = 0, cout = 0, taps = 0, nt = 0;
   __nv_bfloat16* w = nullptr;
   float* b = nullptr;
-  // persistent chain kernel (conv_chain.cu): per channel group [W image | bias image], and the
+  // persistent flow kernel (conv_flow.cu): per channel group [W image | bias image], and the
   // channels-per-tile it was packed for (0: this layer cannot run inside a chain)
   uint8_t* blob = nullptr;
-  int nt_chain = 0;
+  int nt_flow = 0;
 };
 struct Block {
   ConvLayer reduce, c[4], expand;
@@ -66,12 +66,14 @@ struct GraphKey {
   int kind, bucket;
   const void* in;
   const void* out;
+  bool flow;   // captured with the persistent flow kernels (only while the engine has the device to itself)
   bool operator<(const GraphKey& o) const {
-    return std::tie(kind, bucket, in, out) < std::tie(o.kind, o.bucket, o.in, o.out);
+    return std::tie(kind, bucket, in, out, flow) < std::tie(o.kind, o.bucket, o.in, o.out, o.flow);
   }
 };
 
 struct Engine {
+  bool dev_counted = false;
   int gpu_id = -1, max_batch = 0, sm_count = 0, rows_alloc = 0;
   unsigned flags = 0;
   int blocks = 0, C = 0, attn_every = 0, head_dim = 0, Ch = 0, Cv = 0, n_attn = 0;
@@ -102,6 +104,8 @@ struct Engine {
   int dbg_trace_launch = -1;
   long long* d_timeline = nullptr;   // [64 launches][2][8] globaltimer stamps (debug key 3 = on/off)
   int dbg_timeline = 0;
+  int dbg_flow_trace_cta = -1;     // debug key 4: CTA of the flow kernel to trace per item; key 5: which flow launch
+  int dbg_flow_trace_chain = 0;
   void clear_graphs();
 
   // per-launch profiling (maru_eval_profile_states): when prof != nullptr every launch is bracketed
@@ -133,12 +137,17 @@ struct Engine {
   int conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int n, const int* n_dev,
            cudaStream_t st);
   // consecutive conv layers are collected here and launched as ONE persistent kernel by flush_chain()
-  ChainParams pending;
+  FlowParams pending;
   ConvParams pending_single;        // the same layer as a one-layer launch (a chain of one falls back to it)
   const ConvLayer* pending_first = nullptr;
   int pending_w = 0;                // weight-blob region of the pending chain
-  unsigned* d_sync = nullptr;       // grid-barrier counters of all chains of one forward (zeroed per forward)
-  int sync_used = 0;
+  unsigned* d_sync = nullptr;       // neighbour flags of the flow kernels, [2][256] (zeroed per forward)
+  unsigned flag_next = 0;           // next unused flag value of the forward being enqueued
+  int n_flow_launches = 0;
+  int pending_convs = 0;            // conv layers (not channel groups) in the pending chain
+  double pending_flops = 0, pending_bytes = 0;
+  bool flow_enabled();
+  void device_ref(int delta);
   long long* d_stamps = nullptr;    // per-layer %globaltimer stamps of the chains (profiling)
   int stamps_used = 0;
   int n_launched = 0;               // kernels launched by the forward being enqueued

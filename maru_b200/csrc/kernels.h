@@ -57,40 +57,47 @@ struct ConvParams {
 };
 constexpr int TRACE_TILES = 32, TRACE_SLOTS = 8;
 
-// ---- persistent multi-layer conv kernel (conv_chain.cu) ---------------------------------------
-// A CHAIN of consecutive conv layers runs in ONE kernel (one CTA per SM, all co-resident) with a
-// grid-wide barrier between layers: a kernel boundary costs ~4.6 us before the first dependent load
-// (tools/timeline.py), a barrier + the first slab load ~2 us.
-struct ChainLayer {
+// ---- persistent multi-layer conv kernel (conv_flow.cu) ----------------------------------------
+// A CHAIN of consecutive conv layers runs in ONE kernel, one CTA per SM.  Every CTA owns a contiguous
+// range of M tiles for all layers; dependencies between layers are tracked per tile inside the CTA
+// (shared-memory counters) and, for the two range ends, by gpu-scope flags between neighbouring CTAs.
+// No grid barrier, no kernel boundary: a launch boundary costs ~3.5 of the ~10 us of a batch-256 layer.
+struct FlowLayer {
   const __nv_bfloat16* in;
-  const __nv_bfloat16* res;    // optional residual (may alias out)
+  const __nv_bfloat16* res;    // optional residual, same channels as the output (may alias out)
   __nv_bfloat16* out;
-  const uint8_t* blob;         // [groups][W image of the group | bias image 2*NT*16 B]: one bulk copy per CTA
+  const uint8_t* blob;         // [W image of the nt output channels | bias image 2*nt*16 B]: one bulk copy
   int in_blocked, in_planes, res_blocked, res_planes, out_blocked, out_planes;
-  int cin, nt, taps, cout_total, relu, stages;
+  int out_chunk0;              // first output plane (channel / 8) this layer writes
+  int cin, nt, taps, relu;
 };
-constexpr int CHAIN_MAX = 16;
-struct ChainParams {
-  ChainLayer layer[CHAIN_MAX];
+constexpr int FLOW_MAX = 24;           // layers per chain
+constexpr int FLOW_MAX_TILES = 48;     // M tiles per CTA
+struct FlowParams {
+  FlowLayer layer[FLOW_MAX];
   int n_layers;
   const uint8_t* mask;
   int rows_alloc;
   int m_rows;
   const int* n_dev;
-  int w_region;                // shared-memory bytes reserved for the weight blob (max over the layers)
-  unsigned* sync;              // [n_layers] grid-barrier arrival counters, zero when the kernel starts
-  long long* stamps;           // optional [n_layers + 1][4] %globaltimer of CTA 0: layer start, first operands, done, weights
-  long long* trace;            // optional [32 tiles][8] per-tile stamps of CTA 0 in layer `trace_layer` (bring-up)
-  int trace_layer;
+  int w_region;                // shared-memory bytes of ONE weight region (two regions, double-buffered)
+  int area;                    // bytes of the slab ring
+  unsigned* flags;             // [2 * grid] first / last tile of CTA b finished layers < value - flag_base
+  unsigned flag_base;          // flag value before the first layer of this launch (flags only ever grow)
+  long long* stamps;           // optional [n_layers + 1][4] %globaltimer of CTA 0: layer start, weights landed, done
+  long long* trace;            // optional [256 items][8] %globaltimer stamps of CTA trace_cta (bring-up, conv_flow.cu)
+  int trace_cta;
+  int dbg;                     // timing experiments only: bit0 skip the epilogue's proxy fence, bit1 its gpu fence
   int pdl;
 };
-cudaError_t configure_conv_chain();
-bool conv_chain_supports(int cin, int nt, int taps);
-int conv_chain_blob_bytes(int cin, int nt, int taps);     // bytes of one group's blob
-// pipeline stages a layer gets inside a chain whose weight-blob region is w_region bytes (< 2: does not fit)
-int conv_chain_stages(int cin, int nt, int taps, bool has_res, int w_region);
-// fills stages / w_region; returns cudaErrorInvalidConfiguration when a layer does not fit
-cudaError_t launch_conv_chain(ChainParams& cp, int sm_count, cudaStream_t stream);
+cudaError_t configure_conv_flow();
+bool conv_flow_supports(int cin, int nt, int taps);
+int conv_flow_blob_bytes(int cin, int nt, int taps);
+int conv_flow_area(int w_region);
+// does a layer fit a chain whose weight regions are w_region bytes each (blob fits, two slabs fit the ring)?
+bool conv_flow_fits(int cin, int nt, int taps, int w_region);
+// fills w_region / area; returns cudaErrorInvalidConfiguration when a layer does not fit
+cudaError_t launch_conv_flow(FlowParams& fp, int sm_count, cudaStream_t stream);
 
 cudaError_t configure_conv_gemm();
 cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,

@@ -17,6 +17,9 @@ def test_queue_matches_direct_and_batches(built_lib, model_dir):
     rows = np.concatenate([rows, load_positions('9')[0]])
     states = np.concatenate([states, load_positions('9')[1]])
     direct = maru_b200.Evaluator(path, gpu=0, max_batch=64)
+    # two evaluators share the GPU below, which turns the persistent flow kernels off (their CTAs spin on each
+    # other and need the device to themselves): compare bit for bit against the same one-launch-per-layer path
+    direct.debug_set(1, 32)
     want = direct.forward(rows)
     direct.close()
     proc = maru_b200.Processor(path, gpus=[0], batch_size=32, threads_par_gpu=2)
