@@ -177,6 +177,7 @@ __device__ __noinline__ void flow_producer(const FlowParams& fp, const FlowCta c
     const __nv_bfloat16* const in = fp.layer[l].in;
     const size_t in_tile_stride = (size_t)fp.layer[l].in_planes * (TILE_M * 8);
     const bool blocked = (taps == 1) && fp.layer[l].in_blocked;
+    const int dep_back = fp.layer[l].dep_back;
     const int lead = (taps == 9) ? 24 : 0;
     const uint32_t slab_rows = TILE_M + 2 * lead;
     const uint32_t slab_bytes = slab_rows * cin * 2;
@@ -185,17 +186,19 @@ __device__ __noinline__ void flow_producer(const FlowParams& fp, const FlowCta c
     for (int i = 0; i < k; i++, g++) {
       const int j = flow_tile_of(i, k);
       const int tile = c.t0 + j;
-      if (l > 0 && !(dbg & 4)) {
-        // this tile (and for a 3x3 its two neighbours) of the previous layer must be stored and published
-        const uint32_t need = 8u * (uint32_t)l;
+      if (dep_back > 0 && !(dbg & 4)) {
+        // this tile (and for a 3x3 its two neighbours) of the layer that wrote the input must be stored and
+        // published. Usually that is the previous layer; the channel groups of one convolution (q, k, v; the two
+        // halves of the stem) all read the same input and do not wait for each other.
+        const uint32_t need = 8u * (uint32_t)(l - dep_back + 1);
         const uint32_t done = c.ctrl + CB_DONE;
         if (c.tr != nullptr && lane == 0 && g < 256) c.tr[g * 8 + 7] = globaltimer_ns();
         flow_wait_done(done + 4 * i, need, l, i);
         if (taps == 9) {
           if (j > 0) flow_wait_done(done + 4 * flow_item_of(j - 1, k), need, l, i);
-          else if (tile > 0) flow_wait_flag(flags + 2 * (c.cta - 1) + 1, flag_base + (unsigned)l, l, i);
+          else if (tile > 0 && !(dbg & 16)) flow_wait_flag(flags + 2 * (c.cta - 1) + 1, flag_base + (unsigned)(l - dep_back + 1), l, i);
           if (j < k - 1) flow_wait_done(done + 4 * flow_item_of(j + 1, k), need, l, i);
-          else if (tile + 1 < c.n_tiles) flow_wait_flag(flags + 2 * (c.cta + 1), flag_base + (unsigned)l, l, i);
+          else if (tile + 1 < c.n_tiles && !(dbg & 16)) flow_wait_flag(flags + 2 * (c.cta + 1), flag_base + (unsigned)(l - dep_back + 1), l, i);
         }
         if (c.tr != nullptr && lane == 0 && g < 192) c.tr[(320 + g) * 8 + 3] = globaltimer_ns();
         fence_acq_rel_cta();
@@ -387,7 +390,8 @@ template <int CW>
 __device__ __forceinline__ void flow_epilogue_tile(const int relu, const uint32_t t_addr, __nv_bfloat16* out_row,
                                                    const size_t pstride, const __nv_bfloat16* res_row,
                                                    const size_t rstride, const bool valid, const bool on,
-                                                   const uint32_t tfull, const uint32_t parity, long long* trs) {
+                                                   const uint32_t tfull, const uint32_t tempty, const uint32_t parity,
+                                                   long long* trs) {
   const bool has_res = res_row != nullptr;
   // residual (same channel range as the output): prefetched before the accumulator is ready
   uint4 rv[CW / 8];
@@ -399,36 +403,43 @@ __device__ __forceinline__ void flow_epilogue_tile(const int relu, const uint32_
   mbar_wait_a(tfull, parity);
   if (trs != nullptr) trs[4] = globaltimer_ns();
   tc_fence_after();
+  // all of this thread's accumulator columns in one go (one wait), then the accumulator is handed back to the
+  // MMA warps before the conversion and the stores
+  uint32_t v[CW];
+  if constexpr (CW == 16) {
+    tmem_ld16(t_addr, v);
+  } else if constexpr (CW == 32) {
+    tmem_ld32(t_addr, v);
+  } else {
+    tmem_ld32(t_addr, v);
+    tmem_ld32(t_addr + 32, v + 32);
+  }
+  tmem_ld_wait();
+  tc_fence_before();
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive_a(tempty);
 #pragma unroll
-  for (int c0 = 0; c0 < CW; c0 += 16) {
-    uint32_t v[16];
-    tmem_ld16(t_addr + c0, v);
-    tmem_ld_wait();
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-      uint32_t o[4];
-      uint32_t rw[4] = {0u, 0u, 0u, 0u};
-      if (has_res) {
-        const uint4 r4 = rv[c0 / 8 + q];
-        rw[0] = r4.x;
-        rw[1] = r4.y;
-        rw[2] = r4.z;
-        rw[3] = r4.w;
-      }
-#pragma unroll
-      for (int e = 0; e < 4; e++) {
-        float lo = __uint_as_float(v[q * 8 + 2 * e]), hi = __uint_as_float(v[q * 8 + 2 * e + 1]);
-        if (has_res) {
-          lo += bf16_lo(rw[e]);
-          hi += bf16_hi(rw[e]);
-        }
-        uint32_t pk = pack_bf16x2(lo, hi);
-        if (relu) pk = relu_bf16x2(pk);
-        o[e] = on ? pk : 0u;
-      }
-      if (valid)
-        *reinterpret_cast<uint4*>(out_row + (size_t)(c0 / 8 + q) * pstride) = make_uint4(o[0], o[1], o[2], o[3]);
+  for (int q = 0; q < CW / 8; q++) {
+    uint32_t o[4];
+    uint32_t rw[4] = {0u, 0u, 0u, 0u};
+    if (has_res) {
+      rw[0] = rv[q].x;
+      rw[1] = rv[q].y;
+      rw[2] = rv[q].z;
+      rw[3] = rv[q].w;
     }
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      float lo = __uint_as_float(v[q * 8 + 2 * e]), hi = __uint_as_float(v[q * 8 + 2 * e + 1]);
+      if (has_res) {
+        lo += bf16_lo(rw[e]);
+        hi += bf16_hi(rw[e]);
+      }
+      uint32_t pk = pack_bf16x2(lo, hi);
+      if (relu) pk = relu_bf16x2(pk);
+      o[e] = on ? pk : 0u;
+    }
+    if (valid) *reinterpret_cast<uint4*>(out_row + (size_t)q * pstride) = make_uint4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -472,19 +483,17 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, const FlowCta c
         res_row = res_blocked ? res + (((size_t)tile * res_planes + chunk0) * TILE_M + trow) * 8
                               : res + ((size_t)chunk0 * rows_alloc + grow) * 8;
       const uint32_t t_addr = c.tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 128u + half * cw;
-      const uint32_t tfull = c.ctrl + CB_TFULL + 8 * acc;
+      const uint32_t tfull = c.ctrl + CB_TFULL + 8 * acc, tempty = c.ctrl + CB_TEMPTY + 8 * acc;
       long long* trs = (c.tr != nullptr && warp == 2 && lane == 0 && g < 256) ? c.tr + g * 8 : nullptr;
       if (cw == 64)
-        flow_epilogue_tile<64>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, (g >> 2) & 1u, trs);
+        flow_epilogue_tile<64>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
       else if (cw == 32)
-        flow_epilogue_tile<32>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, (g >> 2) & 1u, trs);
+        flow_epilogue_tile<32>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
       else
-        flow_epilogue_tile<16>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, (g >> 2) & 1u, trs);
+        flow_epilogue_tile<16>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
       if (trs != nullptr) trs[5] = globaltimer_ns();
-      tc_fence_before();
       __syncwarp();
       if (lane == 0) {
-        mbar_arrive_a(c.ctrl + CB_TEMPTY + 8 * acc);
         if (dbg & 1) {                         // A/B: fence in the storing warp (slow, the first version)
           fence_proxy_async_all();
           __threadfence();
@@ -505,6 +514,9 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) conv_flow_kernel(const __grid
   uint8_t* ctrl_p = smem + 2 * fp.w_region;
 
   const int warp = threadIdx.x >> 5;
+  // bring-up: [cta][8] %globaltimer stamps of every CTA: entry, dependency resolved + mask loaded, roles done, exit
+  long long* const tc = (fp.trace != nullptr) ? fp.trace + 8192 + (size_t)blockIdx.x * 8 : nullptr;
+  if (tc != nullptr && threadIdx.x == 0) tc[0] = globaltimer_ns();
   if (threadIdx.x == 0) {
     for (int i = 0; i < FLOW_SLOTS; i++) {
       mbar_init_a(c.ctrl + CB_FULL + 8 * i, 1);
@@ -566,6 +578,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) conv_flow_kernel(const __grid
     reinterpret_cast<uint4*>(ctrl_p + FLOW_CTRL_BYTES + FLOW_ONES_BYTES)[i] =
         reinterpret_cast<const uint4*>(fp.mask + (size_t)c.t0 * TILE_M)[i];
   __syncthreads();
+  if (tc != nullptr && threadIdx.x == 0) tc[1] = globaltimer_ns();
 
   if (c.k > 0) {
     if (warp == 0) flow_producer(fp, c);
@@ -580,11 +593,16 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) conv_flow_kernel(const __grid
   // grid to complete). Triggering any earlier could let them occupy an SM that a CTA of this grid needs.
   pdl_launch_dependents();
   if (fp.stamps != nullptr && c.cta == 0 && threadIdx.x == 64) fp.stamps[4 * fp.n_layers] = globaltimer_ns();
+  if (tc != nullptr && threadIdx.x == 64) tc[2] = globaltimer_ns();     // an epilogue thread: last stores issued
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(c.tmem_base, 512);
+    if (tc != nullptr && threadIdx.x == 32) {
+      tc[3] = globaltimer_ns();
+      tc[4] = c.k;
+    }
   }
 }
 

@@ -487,6 +487,8 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
           Q.nt = L.nt_flow;
           Q.taps = L.taps;
           Q.relu = relu;
+          // every channel group reads the output of the conv before this one (none for the first conv of a chain)
+          Q.dep_back = (pending.n_layers == 0) ? 0 : 1 + grp;
         }
         if (pending.n_layers == 0) {
           pending_single = p;
@@ -502,8 +504,9 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
         pending_w = w_new;
         {
           const double T = (double)CELLS * n;
-          pending_flops += 2.0 * T * L.cin * L.cout * L.taps;
-          pending_bytes += T * (L.cin + L.cout + (res ? L.cout : 0)) * 2.0 + (double)L.taps * L.cin * L.cout * 2.0;
+          const double cin_alg = (L.name == "stem") ? IN_PLANES : L.cin;     // 33 planes (+ 7 infos) are algorithmic
+          pending_flops += 2.0 * T * cin_alg * L.cout * L.taps + ((L.name == "stem") ? 2.0 * IN_INFOS * L.cout * n : 0.0);
+          pending_bytes += T * (cin_alg + L.cout + (res ? L.cout : 0)) * 2.0 + (double)L.taps * L.cin * L.cout * 2.0;
         }
         out.flagged = false;
         return 0;
@@ -631,7 +634,7 @@ int Engine::flush_chain(cudaStream_t st) {
   // bring-up: debug key 2 (trace launch) = -(1 + cta) traces that CTA of the FIRST flow kernel of the forward
   pending.trace = (dbg_flow_trace_cta >= 0 && n_flow_launches == dbg_flow_trace_chain) ? d_trace : nullptr;
   pending.trace_cta = dbg_flow_trace_cta;
-  pending.dbg = (dbg_desc >> 8) & 15;
+  pending.dbg = (dbg_desc >> 8) & 31;
   char name[48];
   snprintf(name, sizeof name, "flow%d[%s..%d layers]", n_flow_launches++, pending_first->name.c_str(), pending_convs);
   prof_begin(name, 5, 0, 0, 0, pending_flops, pending_bytes, st);

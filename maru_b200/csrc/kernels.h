@@ -70,6 +70,7 @@ struct FlowLayer {
   int in_blocked, in_planes, res_blocked, res_planes, out_blocked, out_planes;
   int out_chunk0;              // first output plane (channel / 8) this layer writes
   int cin, nt, taps, relu;
+  int dep_back;                // the input was written by layer l - dep_back of this launch (0: by an earlier kernel)
 };
 constexpr int FLOW_MAX = 24;           // layers per chain
 constexpr int FLOW_MAX_TILES = 48;     // M tiles per CTA
