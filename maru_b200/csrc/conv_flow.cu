@@ -157,7 +157,11 @@ struct FlowCta {
 };
 
 // ------------------------------------------------------------------------------------------ producer (warp 0)
-__device__ __noinline__ void flow_producer(const FlowParams& fp, const FlowCta c) {
+__device__ __noinline__ void flow_producer(const FlowParams& fp, uint32_t c_smem, uint32_t c_ctrl, uint32_t c_area, uint32_t c_tmem, int c_cta, int c_t0, int c_k, int c_n_tiles, int c_m_rows, long long* c_tr) {
+  // scalars, not a struct: a by-value struct argument of a non-inlined function lives on the local-memory stack
+  FlowCta c;
+  c.smem = c_smem; c.ctrl = c_ctrl; c.area = c_area; c.tmem_base = c_tmem; c.cta = c_cta; c.t0 = c_t0; c.k = c_k;
+  c.n_tiles = c_n_tiles; c.m_rows = c_m_rows; c.tr = c_tr;
   const int lane = threadIdx.x & 31;
   const int k = c.k;
   // Everything read from the kernel parameters is copied into locals first: the asm statements below clobber
@@ -172,12 +176,24 @@ __device__ __noinline__ void flow_producer(const FlowParams& fp, const FlowCta c
   long long* const stamps = (c.cta == 0) ? fp.stamps : nullptr;
   uint32_t g = 0, head = 0;
   uint32_t o1 = 0, e1 = 0, o2 = 0, e2 = 0, o3 = 0, e3 = 0;
+  // the fields of layer l+1 are fetched while layer l is being requested (see flow_mma)
+  int nx_taps = fp.layer[0].taps, nx_cin = fp.layer[0].cin, nx_planes = fp.layer[0].in_planes;
+  int nx_blocked = fp.layer[0].in_blocked, nx_dep = fp.layer[0].dep_back;
+  const __nv_bfloat16* nx_in = fp.layer[0].in;
   for (int l = 0; l < n_layers; l++) {
-    const int taps = fp.layer[l].taps, cin = fp.layer[l].cin;
-    const __nv_bfloat16* const in = fp.layer[l].in;
-    const size_t in_tile_stride = (size_t)fp.layer[l].in_planes * (TILE_M * 8);
-    const bool blocked = (taps == 1) && fp.layer[l].in_blocked;
-    const int dep_back = fp.layer[l].dep_back;
+    const int taps = nx_taps, cin = nx_cin;
+    const __nv_bfloat16* const in = nx_in;
+    const size_t in_tile_stride = (size_t)nx_planes * (TILE_M * 8);
+    const bool blocked = (taps == 1) && nx_blocked;
+    const int dep_back = nx_dep;
+    if (l + 1 < n_layers) {
+      nx_taps = fp.layer[l + 1].taps;
+      nx_cin = fp.layer[l + 1].cin;
+      nx_planes = fp.layer[l + 1].in_planes;
+      nx_blocked = fp.layer[l + 1].in_blocked;
+      nx_dep = fp.layer[l + 1].dep_back;
+      nx_in = fp.layer[l + 1].in;
+    }
     const int lead = (taps == 9) ? 24 : 0;
     const uint32_t slab_rows = TILE_M + 2 * lead;
     const uint32_t slab_bytes = slab_rows * cin * 2;
@@ -262,7 +278,11 @@ __device__ __forceinline__ void flow_issue(uint32_t d_tmem, uint32_t a_lo, uint3
   }
 }
 
-__device__ __noinline__ void flow_mma(const FlowParams& fp, const FlowCta c, const uint32_t mw) {
+__device__ __noinline__ void flow_mma(const FlowParams& fp, uint32_t c_smem, uint32_t c_ctrl, uint32_t c_area, uint32_t c_tmem, int c_cta, int c_t0, int c_k, int c_n_tiles, int c_m_rows, long long* c_tr, const uint32_t mw) {
+  // scalars, not a struct: a by-value struct argument of a non-inlined function lives on the local-memory stack
+  FlowCta c;
+  c.smem = c_smem; c.ctrl = c_ctrl; c.area = c_area; c.tmem_base = c_tmem; c.cta = c_cta; c.t0 = c_t0; c.k = c_k;
+  c.n_tiles = c_n_tiles; c.m_rows = c_m_rows; c.tr = c_tr;
   const int lane = threadIdx.x & 31;
   const int k = c.k;
   const uint32_t ones = c.ctrl + FLOW_CTRL_BYTES;
@@ -273,8 +293,16 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, const FlowCta c, con
   const uint32_t w_region = (uint32_t)fp.w_region;
   long long* const stamps = (c.cta == 0 && mw == 0) ? fp.stamps : nullptr;
   uint32_t g = 0;
+  // the shape of layer l+1 is fetched while layer l runs: reached through the parameter reference these are generic
+  // loads (~0.7 us), and at a layer boundary they would sit between two tiles' MMAs
+  int nx_taps = fp.layer[0].taps, nx_cin = fp.layer[0].cin, nx_nt = fp.layer[0].nt;
   for (int l = 0; l < n_layers; l++) {
-    const int taps = fp.layer[l].taps, cin = fp.layer[l].cin, nt = fp.layer[l].nt;
+    const int taps = nx_taps, cin = nx_cin, nt = nx_nt;
+    if (l + 1 < n_layers) {
+      nx_taps = fp.layer[l + 1].taps;
+      nx_cin = fp.layer[l + 1].cin;
+      nx_nt = fp.layer[l + 1].nt;
+    }
     const uint32_t slab_rows = (taps == 9) ? TILE_M + 48 : TILE_M;
     const uint64_t a_d = umma_desc(0, slab_rows * 16, 128);        // slab:  LBO = slab plane
     const uint64_t b_d = umma_desc(0, nt * 16, 128);               // W, biasB: LBO = NT rows
@@ -316,7 +344,11 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, const FlowCta c, con
 }
 
 // ------------------------------------------------------------------------------------------ weights + neighbour flags (warp 11)
-__device__ __noinline__ void flow_aux(const FlowParams& fp, const FlowCta c) {
+__device__ __noinline__ void flow_aux(const FlowParams& fp, uint32_t c_smem, uint32_t c_ctrl, uint32_t c_area, uint32_t c_tmem, int c_cta, int c_t0, int c_k, int c_n_tiles, int c_m_rows, long long* c_tr) {
+  // scalars, not a struct: a by-value struct argument of a non-inlined function lives on the local-memory stack
+  FlowCta c;
+  c.smem = c_smem; c.ctrl = c_ctrl; c.area = c_area; c.tmem_base = c_tmem; c.cta = c_cta; c.t0 = c_t0; c.k = c_k;
+  c.n_tiles = c_n_tiles; c.m_rows = c_m_rows; c.tr = c_tr;
   const int lane = threadIdx.x & 31;
   const int k = c.k;
   const int n_layers = fp.n_layers;
@@ -360,7 +392,11 @@ __device__ __noinline__ void flow_aux(const FlowParams& fp, const FlowCta c) {
 // 8 counts of an item, runs the generic -> async proxy fence ONCE on behalf of the 256 storing threads (a proxy
 // fence anywhere on the causality path from the writes to the bulk-copy reads is sufficient; it costs ~0.7 us,
 // which used to stall every epilogue warp after every tile), and re-publishes the count for the producer warp.
-__device__ __noinline__ void flow_publisher(const FlowParams& fp, const FlowCta c, const uint32_t pw) {
+__device__ __noinline__ void flow_publisher(const FlowParams& fp, uint32_t c_smem, uint32_t c_ctrl, uint32_t c_area, uint32_t c_tmem, int c_cta, int c_t0, int c_k, int c_n_tiles, int c_m_rows, long long* c_tr, const uint32_t pw) {
+  // scalars, not a struct: a by-value struct argument of a non-inlined function lives on the local-memory stack
+  FlowCta c;
+  c.smem = c_smem; c.ctrl = c_ctrl; c.area = c_area; c.tmem_base = c_tmem; c.cta = c_cta; c.t0 = c_t0; c.k = c_k;
+  c.n_tiles = c_n_tiles; c.m_rows = c_m_rows; c.tr = c_tr;
   const int lane = threadIdx.x & 31;
   const int k = c.k;
   const int n_layers = fp.n_layers;
@@ -443,7 +479,11 @@ __device__ __forceinline__ void flow_epilogue_tile(const int relu, const uint32_
   }
 }
 
-__device__ __noinline__ void flow_epilogue(const FlowParams& fp, const FlowCta c) {
+__device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem, uint32_t c_ctrl, uint32_t c_area, uint32_t c_tmem, int c_cta, int c_t0, int c_k, int c_n_tiles, int c_m_rows, long long* c_tr) {
+  // scalars, not a struct: a by-value struct argument of a non-inlined function lives on the local-memory stack
+  FlowCta c;
+  c.smem = c_smem; c.ctrl = c_ctrl; c.area = c_area; c.tmem_base = c_tmem; c.cta = c_cta; c.t0 = c_t0; c.k = c_k;
+  c.n_tiles = c_n_tiles; c.m_rows = c_m_rows; c.tr = c_tr;
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int k = c.k;
@@ -581,13 +621,13 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) conv_flow_kernel(const __grid
   if (tc != nullptr && threadIdx.x == 0) tc[1] = globaltimer_ns();
 
   if (c.k > 0) {
-    if (warp == 0) flow_producer(fp, c);
-    else if (warp == 1) flow_mma(fp, c, 0u);
-    else if (warp == 10) flow_mma(fp, c, 1u);
-    else if (warp == 11) flow_aux(fp, c);
-    else if (warp == 12) flow_publisher(fp, c, 0u);
-    else if (warp == 13) flow_publisher(fp, c, 1u);
-    else flow_epilogue(fp, c);
+    if (warp == 0) flow_producer(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr);
+    else if (warp == 1) flow_mma(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr, 0u);
+    else if (warp == 10) flow_mma(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr, 1u);
+    else if (warp == 11) flow_aux(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr);
+    else if (warp == 12) flow_publisher(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr, 0u);
+    else if (warp == 13) flow_publisher(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr, 1u);
+    else flow_epilogue(fp, c.smem, c.ctrl, c.area, c.tmem_base, c.cta, c.t0, c.k, c.n_tiles, c.m_rows, c.tr);
   }
   // Every role is past its last layer: the next kernel's CTAs may become resident (they still wait for this
   // grid to complete). Triggering any earlier could let them occupy an SM that a CTA of this grid needs.
