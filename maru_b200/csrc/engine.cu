@@ -458,7 +458,8 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   // flush_chain() (conv_flow.cu). Layers whose weights or slabs do not fit next to the chain's (e.g. the
   // 147 KB stem) run as one PDL launch each, and so does everything when a debug knob asks for per-layer
   // behaviour (stop-after, traces, timeline, tile flags) or another engine shares the device.
-  const bool flowable = flow_enabled() && !use_flags && p.trace == nullptr && p.timeline == nullptr && L.nt_flow > 0;
+  const bool flowable = flow_enabled() && !use_flags && p.trace == nullptr && p.timeline == nullptr && L.nt_flow > 0 &&
+                        ((p.m_rows + TILE_M - 1) / TILE_M + sm_count - 1) / sm_count <= FLOW_MAX_TILES;
   if (flowable) {
     const int groups = L.cout / L.nt_flow;
     for (int attempt = 0; attempt < 2; attempt++) {
