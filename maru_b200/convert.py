@@ -5,7 +5,7 @@ reference does in C++ at src/deepgo/native/cpp/Model.cpp:77) -> BatchNorm foldin
 a flat binary pack that `maru_eval_create` maps into device buffers (maru_b200/csrc/engine.cu).
 No forward pass is ever run here.
 
-usage:  python -m maru_b200.convert <file>.model [<out>.b200]
+usage:  python -m maru_b200.convert <file>.model [<out>.b200] [--name-map=<map>.json]
 
 Pack layout (little endian):
   header  : magic "MARUB200", u32 version=1, u32 n_tensors, i32 arch[8]
@@ -133,21 +133,108 @@ def write_pack(arch: list, tensors: Dict[str, torch.Tensor], path: str) -> None:
         f.truncate(off)
 
 
-def convert(model_path: str, out_path: str | None = None) -> str:
+def apply_name_map(sd: Dict[str, torch.Tensor], name_map: dict) -> Dict[str, torch.Tensor]:
+    """a TorchScript archive whose parameters are named differently from netspec.MaruNet
+    (a released Maru `.model`; the reference loads it opaquely, Model.cpp:77) is converted through a name
+    map, a JSON object written from the template `python -m maru_b200.inspect_model <file>.model` prints:
+
+      {"arch": [blocks, channels, attn_every, head_dim, head_channels, value_channels],
+       "rename": {"<their key>": "<netspec key>", ...}}
+
+    Every netspec key must be produced exactly once; tensors are checked against the shapes `arch` implies
+    by fold_state_dict (a wrong map fails loudly, it never produces a silently different network)."""
+    rename = name_map.get('rename', {})
+    out: Dict[str, torch.Tensor] = {}
+    for k, v in sd.items():
+        nk = rename.get(k, k)
+        if nk is None or nk == '':
+            continue                      # explicitly dropped (e.g. num_batches_tracked)
+        if nk in out:
+            raise ValueError(f'name map sends two tensors to {nk!r}')
+        out[nk] = v
+    if 'arch' in name_map:
+        a = [int(x) for x in name_map['arch']]
+        out['arch'] = torch.tensor(a + [0] * (8 - len(a)), dtype=torch.int32)
+    return out
+
+
+def expected_keys(arch: list) -> Dict[str, tuple]:
+    """netspec.MaruNet state_dict keys (those the loader reads) -> shapes implied by `arch`."""
+    blocks, C, attn_every, head_dim, Ch, Cv = [int(v) for v in arch[:6]]
+    n_attn = blocks // attn_every if attn_every > 0 else 0
+    keys: Dict[str, tuple] = {}
+
+    def bn(prefix, c):
+        for f in ('weight', 'bias', 'running_mean', 'running_var'):
+            keys[f'{prefix}.{f}'] = (c,)
+
+    def convbn(prefix, cout, cin, k):
+        keys[f'{prefix}.conv.weight'] = (cout, cin, k, k)
+        bn(f'{prefix}.bn', cout)
+
+    keys['stem_conv.weight'] = (C, 33, 3, 3)
+    keys['stem_info.weight'] = (C, 7)
+    bn('stem_bn', C)
+    for i in range(blocks):
+        convbn(f'blocks.{i}.reduce', C // 2, C, 1)
+        for j in range(2):
+            convbn(f'blocks.{i}.inner{j}.c1', C // 2, C // 2, 3)
+            convbn(f'blocks.{i}.inner{j}.c2', C // 2, C // 2, 3)
+        convbn(f'blocks.{i}.expand', C, C // 2, 1)
+    for k in range(n_attn):
+        bn(f'attn.{k}.norm', C)
+        keys[f'attn.{k}.qkv.weight'] = (3 * C, C, 1, 1)
+        keys[f'attn.{k}.qkv.bias'] = (3 * C,)
+        keys[f'attn.{k}.proj.weight'] = (C, C, 1, 1)
+        keys[f'attn.{k}.proj.bias'] = (C,)
+    convbn('heads.g', Ch, C, 1)
+    keys['heads.planes.weight'] = (6, Ch, 1, 1)
+    keys['heads.planes.bias'] = (6,)
+    keys['heads.fc1.weight'] = (Cv, 2 * Ch)
+    keys['heads.fc1.bias'] = (Cv,)
+    keys['heads.fc2.weight'] = (3, Cv)
+    keys['heads.fc2.bias'] = (3,)
+    return keys
+
+
+def check_state_dict(sd: Dict[str, torch.Tensor]) -> None:
+    """Raises ValueError listing every missing key / wrong shape (numel must match; conv weights may be
+    stored with or without the trailing 1x1 dimensions)."""
+    if 'arch' not in sd:
+        raise ValueError('no `arch` buffer')
+    problems = []
+    for k, shape in expected_keys([int(v) for v in sd['arch'].tolist()]).items():
+        if k not in sd:
+            problems.append(f'missing {k} {shape}')
+        elif int(sd[k].numel()) != int(np.prod(shape)):
+            problems.append(f'{k}: shape {tuple(sd[k].shape)}, expected {shape}')
+    if problems:
+        raise ValueError('state_dict does not match the architecture in `arch`:\n  ' + '\n  '.join(problems))
+
+
+def convert(model_path: str, out_path: str | None = None, name_map: dict | None = None) -> str:
     """`.model` (TorchScript archive) -> `<model_path>.b200`. Returns the pack path."""
     mod = torch.jit.load(model_path, map_location='cpu')
     sd = {k: v.detach().cpu() for k, v in mod.state_dict().items()}
+    if name_map is not None:
+        sd = apply_name_map(sd, name_map)
     if 'arch' not in sd:
         raise ValueError(f'{model_path}: no `arch` buffer - not a netspec.MaruNet export; '
-                         'released Maru weights need a name map (SURVEY f4)')
+                         'released Maru weights need a name map (SURVEY f4): '
+                         'python -m maru_b200.inspect_model <file>.model prints a template')
+    check_state_dict(sd)
     arch, tensors = fold_state_dict(sd)
     out_path = out_path or (model_path + '.b200')
     write_pack(arch, tensors, out_path)
     return out_path
 
 
-def convert_state_dict(sd: Dict[str, torch.Tensor], out_path: str) -> str:
-    arch, tensors = fold_state_dict({k: v.detach().cpu() for k, v in sd.items()})
+def convert_state_dict(sd: Dict[str, torch.Tensor], out_path: str, name_map: dict | None = None) -> str:
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    if name_map is not None:
+        sd = apply_name_map(sd, name_map)
+    check_state_dict(sd)
+    arch, tensors = fold_state_dict(sd)
     write_pack(arch, tensors, out_path)
     return out_path
 
@@ -156,4 +243,11 @@ if __name__ == '__main__':
     if len(sys.argv) < 2:
         print(__doc__)
         sys.exit(2)
-    print(convert(sys.argv[1], sys.argv[2] if len(sys.argv) > 2 else None))
+    args = [a for a in sys.argv[1:] if not a.startswith('--name-map=')]
+    maps = [a.split('=', 1)[1] for a in sys.argv[1:] if a.startswith('--name-map=')]
+    nm = None
+    if maps:
+        import json
+        with open(maps[0]) as fh:
+            nm = json.load(fh)
+    print(convert(args[0], args[1] if len(args) > 1 else None, nm))
