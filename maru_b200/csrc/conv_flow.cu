@@ -290,6 +290,7 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, uint32_t c_smem, uin
   const uint32_t r_hi = (uint32_t)(r_d >> 32);
   const uint32_t ones_lo = (uint32_t)r_d + (ones >> 4);
   const int n_layers = fp.n_layers;
+  const int dbg = fp.dbg;
   const uint32_t w_region = (uint32_t)fp.w_region;
   long long* const stamps = (c.cta == 0 && mw == 0) ? fp.stamps : nullptr;
   uint32_t g = 0;
@@ -325,10 +326,16 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, uint32_t c_smem, uin
       if (elect_one()) {
         const uint32_t a_lo = (uint32_t)a_d + ((c.area + off) >> 4);
         const uint32_t d_tmem = c.tmem_base + acc * 128u;
+        // The weight descriptors are the same for every tile of a layer; left alone, the compiler hoists all 37
+        // of them out of the tile loop into vector registers and feeds every UTCHMMA through R2UR moves and
+        // uniform-register spills (~65 cycles per MMA). Made opaque here, they are one base register plus an
+        // immediate per MMA, like the slab descriptors.
+        uint32_t w_lo_i = w_lo, biasb_lo_i = biasb_lo, ones_lo_i = ones_lo;
+        asm volatile("" : "+r"(w_lo_i), "+r"(biasb_lo_i), "+r"(ones_lo_i));
 #define X(CIN_, NT_, TAPS_)                                \
         else if (cin == CIN_ && nt == NT_ && taps == TAPS_) \
-          flow_issue<CIN_, NT_, TAPS_>(d_tmem, a_lo, a_hi, w_lo, b_hi, ones_lo, r_hi, biasb_lo);
-        if (false) {}
+          flow_issue<CIN_, NT_, TAPS_>(d_tmem, a_lo, a_hi, w_lo_i, b_hi, ones_lo_i, r_hi, biasb_lo_i);
+        if (dbg & 32) {}      // timing experiment: no MMAs at all
         MARU_FLOW_CASES(X)
 #undef X
         umma_commit_a(c.ctrl + CB_EMPTY + 8 * (g & 3));   // slab reusable once these MMAs retire
@@ -511,7 +518,7 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
       const int j = flow_tile_of(i, k);
       const int tile = c.t0 + j;
       const int row = tile * TILE_M + trow;
-      const bool valid = row < c.m_rows;
+      const bool valid = row < c.m_rows && !(dbg & 64);
       const size_t grow = (size_t)GUARD_ROWS + row;
       uint32_t mv;
       asm volatile("ld.shared::cta.u8 %0, [%1];\n" : "=r"(mv) : "r"(mask + j * TILE_M + trow));
@@ -525,7 +532,13 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
       const uint32_t t_addr = c.tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 128u + half * cw;
       const uint32_t tfull = c.ctrl + CB_TFULL + 8 * acc, tempty = c.ctrl + CB_TEMPTY + 8 * acc;
       long long* trs = (c.tr != nullptr && warp == 2 && lane == 0 && g < 256) ? c.tr + g * 8 : nullptr;
-      if (cw == 64)
+      if (dbg & 128) {            // timing experiment: the epilogue only hands the accumulator back
+        mbar_wait_a(tfull, (g >> 2) & 1u);
+        tc_fence_after();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_a(tempty);
+      } else if (cw == 64)
         flow_epilogue_tile<64>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
       else if (cw == 32)
         flow_epilogue_tile<32>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
@@ -538,7 +551,8 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
           fence_proxy_async_all();
           __threadfence();
         }
-        red_release_inc(c.ctrl + CB_RAW + 4 * i);
+        if (dbg & 2) asm volatile("red.relaxed.cta.shared::cta.add.u32 [%0], 1;\n" ::"r"(c.ctrl + CB_RAW + 4 * i) : "memory");
+        else red_release_inc(c.ctrl + CB_RAW + 4 * i);
       }
     }
     if (stamps != nullptr) stamps[4 * l + 2] = globaltimer_ns();

@@ -635,7 +635,7 @@ int Engine::flush_chain(cudaStream_t st) {
   // bring-up: debug key 2 (trace launch) = -(1 + cta) traces that CTA of the FIRST flow kernel of the forward
   pending.trace = (dbg_flow_trace_cta >= 0 && n_flow_launches == dbg_flow_trace_chain) ? d_trace : nullptr;
   pending.trace_cta = dbg_flow_trace_cta;
-  pending.dbg = (dbg_desc >> 8) & 31;
+  pending.dbg = (dbg_desc >> 8) & 255;
   char name[48];
   snprintf(name, sizeof name, "flow%d[%s..%d layers]", n_flow_launches++, pending_first->name.c_str(), pending_convs);
   prof_begin(name, 5, 0, 0, 0, pending_flops, pending_bytes, st);
