@@ -46,3 +46,31 @@ def test_queue_matches_direct_and_batches(built_lib, model_dir):
         assert np.array_equal(big[:len(rows)], want)
     finally:
         proc.close()
+
+
+def test_queue_on_the_flow_kernels(built_lib, model_dir):
+    """One evaluator per GPU (the default): the queue's batches of every size replay graphs built from the
+    persistent conv_flow kernels (live batch size read on the device). Results must equal the direct call on the
+    same path bit for bit, whatever batch a position happened to travel in."""
+    import maru_b200
+    path = model_dir('b4c128')
+    rows, states = load_positions('19')
+    direct = maru_b200.Evaluator(path, gpu=0, max_batch=64)
+    want = direct.forward_states(states)
+    assert direct.info().launches_per_forward <= 8            # encode, 3 flow launches, 2 attention, heads
+    direct.close()
+    proc = maru_b200.Processor(path, gpus=[0], batch_size=48, threads_par_gpu=1)
+    try:
+        assert np.array_equal(proc.execute_states(states), want)
+        got = np.zeros_like(want)
+        def worker(tid):
+            for i in range(tid, len(states), 12):
+                k = 1 + (i % 3)                                # jobs of 1..3 positions
+                got[i:i + k] = proc.execute_states(states[i:i + k])[:k]
+        ts = [threading.Thread(target=worker, args=(t,)) for t in range(12)]
+        [t.start() for t in ts]
+        [t.join() for t in ts]
+        assert np.array_equal(got, want)
+        assert proc.queue.stats().batches >= 3
+    finally:
+        proc.close()
