@@ -160,7 +160,7 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower),
  * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
  * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
- * (maru_eval_debug_stamps), bits 8-15 = timing experiments inside the flow kernels (tools/flow_ab.py; results are WRONG with any of
+ * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on 148 SMs), bits 8-15 = timing experiments inside the flow kernels (tools/flow_ab.py; results are WRONG with any of
  * them set): 8 fence in the storing warps, 10 no dependency waits, 11 no slab loads, 12 no neighbour-flag waits,
  * 13 no MMAs, 14 no stores, 15 no epilogue work at all. */
 #define MARU_DBG_STOP_AFTER 0

@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "engine.h"
+#include <stdlib.h>
 
 namespace maru {
 
@@ -252,6 +253,11 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     return 1;
   }
   gpu_id = gpu;
+  if (const char* ff = getenv("MARU_B200_FLOW")) {
+    // "1": the persistent flow kernels at every batch size, "0": never (default: for 249..354 positions on 148 SMs)
+    if (ff[0] == '1') dbg_desc |= 128;
+    if (ff[0] == '0') dbg_desc |= 32;
+  }
   device_ref(+1);
   dev_counted = true;
   max_batch = max_batch_ > 0 ? max_batch_ : 256;
@@ -582,6 +588,7 @@ int Engine::profile_states(const maru_state* d_states, float* d_out, int n, maru
     set_error("maru_eval_profile_states: n out of range");
     return 1;
   }
+  flow_live = flow_pays(n);
   std::vector<maru_launch_time> rec;
   rec.reserve(256);
   while ((int)prof_ev.size() < 512) {
@@ -635,7 +642,7 @@ int Engine::flush_chain(cudaStream_t st) {
   // bring-up: debug key 2 (trace launch) = -(1 + cta) traces that CTA of the FIRST flow kernel of the forward
   pending.trace = (dbg_flow_trace_cta >= 0 && n_flow_launches == dbg_flow_trace_chain) ? d_trace : nullptr;
   pending.trace_cta = dbg_flow_trace_cta;
-  pending.dbg = (dbg_desc >> 8) & 255;
+  pending.dbg = (dbg_desc >> 8) & 1023;
   char name[48];
   snprintf(name, sizeof name, "flow%d[%s..%d layers]", n_flow_launches++, pending_first->name.c_str(), pending_convs);
   prof_begin(name, 5, 0, 0, 0, pending_flops, pending_bytes, st);
@@ -659,7 +666,21 @@ void Engine::device_ref(int delta) {
   std::lock_guard<std::mutex> lock(g_dev_mu);
   if (gpu_id >= 0 && gpu_id < 64) g_engines_on_device[gpu_id] += delta;
 }
+// The persistent flow kernels win in a window around 5-7 tiles per CTA. Below it a layer inside the flow kernel is one
+// serial store -> publish -> load -> MMA chain per tile and the three big launches lose the prologue overlap that PDL
+// gives 34 small ones; above it the per-layer kernels amortise their launch boundary over 10+ tiles and their lighter
+// epilogue (residual by identity MMA instead of L2 loads in the epilogue, ~7 % at batch 1024) wins.
+// Measured (b4c128, forward in us, flow / per-layer): batch 1: 186 / 159, 64: 246 / 222, 128: 323 / 305, 192: 415 / 401,
+// 224: 444 / 433, 256: 448-458 / 466, 320: 544 / 562, 384: 666 / 659, 512: 838 / 824, 1024: 1710 / 1617.
+bool Engine::flow_pays(int n) const {
+  const int n_tiles = (total_rows(n) + TILE_M - 1) / TILE_M;
+  return 4 * n_tiles >= 21 * sm_count && 2 * n_tiles < 15 * sm_count;     // 5.25 <= tiles per CTA < 7.5: batch 249..354
+}
 bool Engine::flow_enabled() {
+  if (dbg_desc & 128) return flow_device_ok();      // debug: force the flow kernels at any batch size
+  return flow_live && flow_device_ok();
+}
+bool Engine::flow_device_ok() {
   if ((dbg_desc & 32) || dbg_stop_after >= 0 || dbg_timeline || dbg_trace_launch >= 0) return false;
   std::lock_guard<std::mutex> lock(g_dev_mu);
   return gpu_id >= 0 && gpu_id < 64 && g_engines_on_device[gpu_id] == 1;
@@ -791,10 +812,12 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
     return 1;
   }
   if (flags & MARU_FLAG_NO_GRAPH) {
+    flow_live = flow_pays(n);
     if (launch_all(kind, d_in, d_out, n, nullptr, stream)) return 1;
   } else {
     // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
     const int bucket = bucket_for(n, max_batch);
+    flow_live = flow_pays(n);             // by the LIVE batch size: a bucket has a flow graph and a per-layer graph
     GraphKey key{kind, bucket, d_in, d_out, flow_enabled()};
     auto it = graphs.find(key);
     if (it == graphs.end()) {

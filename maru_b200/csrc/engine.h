@@ -147,6 +147,9 @@ struct Engine {
   int pending_convs = 0;            // conv layers (not channel groups) in the pending chain
   double pending_flops = 0, pending_bytes = 0;
   bool flow_enabled();
+  bool flow_device_ok();
+  bool flow_pays(int n) const;      // enough tiles per CTA for the persistent kernels to win
+  bool flow_live = true;            // flow_pays(live batch size) of the forward being enqueued
   void device_ref(int delta);
   long long* d_stamps = nullptr;    // per-layer %globaltimer stamps of the chains (profiling)
   int stamps_used = 0;

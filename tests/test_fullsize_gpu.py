@@ -27,12 +27,20 @@ def test_full_size_properties(built_lib, model_dir, name, batch):
     try:
         st = mixed_states(batch, seed=11)
         out = ev.forward_states(st)
+        launches = ev.info().launches_per_forward
         assert out.shape == (batch, 2169) and np.isfinite(out).all()
         assert np.array_equal(ev.forward_states(st), out)                     # run-to-run deterministic
         perm = np.random.default_rng(3).permutation(batch)
         assert np.array_equal(ev.forward_states(st[perm]), out[perm])         # slot / neighbour independent
         for n in (1, 7, batch - 1):
-            assert np.array_equal(ev.forward_states(st[:n]), out[:n])         # ragged prefix of the same bucket
+            got = ev.forward_states(st[:n])                                   # ragged prefix of the same bucket
+            if ev.info().launches_per_forward == launches:
+                assert np.array_equal(got, out[:n])
+            else:
+                # The engine picks the persistent multi-layer conv kernels or one launch per layer by the LIVE batch
+                # size (Engine::flow_pays). Same MMAs in the same order, but the residual is added in the epilogue
+                # (fp32) instead of by an identity MMA: one bf16 rounding may differ per residual layer.
+                assert np.abs(got - out[:n]).max() < 2e-3
         # on-board mask from the records: width x height centred in the 19x19 frame
         w, h = st[:, 368].astype(int), st[:, 369].astype(int)
         yy, xx = np.mgrid[0:19, 0:19]

@@ -52,14 +52,19 @@ def test_queue_on_the_flow_kernels(built_lib, model_dir):
     """One evaluator per GPU (the default): the queue's batches of every size replay graphs built from the
     persistent conv_flow kernels (live batch size read on the device). Results must equal the direct call on the
     same path bit for bit, whatever batch a position happened to travel in."""
+    import os
     import maru_b200
     path = model_dir('b4c128')
     rows, states = load_positions('19')
-    direct = maru_b200.Evaluator(path, gpu=0, max_batch=64)
-    want = direct.forward_states(states)
-    assert direct.info().launches_per_forward <= 8            # encode, 3 flow launches, 2 attention, heads
-    direct.close()
-    proc = maru_b200.Processor(path, gpus=[0], batch_size=48, threads_par_gpu=1)
+    os.environ['MARU_B200_FLOW'] = '1'        # the flow kernels at every batch size (default: for 249..354 positions on 148 SMs)
+    try:
+        direct = maru_b200.Evaluator(path, gpu=0, max_batch=64)
+        want = direct.forward_states(states)
+        assert direct.info().launches_per_forward <= 8            # encode, 3 flow launches, 2 attention, heads
+        direct.close()
+        proc = maru_b200.Processor(path, gpus=[0], batch_size=48, threads_par_gpu=1)
+    finally:
+        del os.environ['MARU_B200_FLOW']
     try:
         assert np.array_equal(proc.execute_states(states), want)
         got = np.zeros_like(want)

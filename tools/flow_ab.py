@@ -19,7 +19,7 @@ d_states = torch.from_numpy(st).to(dev)
 d_out = torch.empty((B, maru_b200.OUTPUT_SIZE), dtype=torch.float32, device=dev)
 stream = torch.cuda.ExternalStream(ev.stream(), device=dev)
 for bits in variants:
-    ev.debug_set(1, bits | 64)
+    ev.debug_set(1, bits | 64 | 128)
     best = None
     for _ in range(6):
         ev.forward_states(st)
@@ -31,7 +31,7 @@ for bits in variants:
             if s[i, 2] == 0:
                 chains.append((s[i, 0] - start) / 1e3); start = None
         best = chains if best is None else [min(a, b) for a, b in zip(best, chains)]
-    ev.debug_set(1, bits)
+    ev.debug_set(1, bits | (0 if bits & 32 else 128))
     for _ in range(3): ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), B)
     ev.sync()
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)

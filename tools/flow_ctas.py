@@ -12,6 +12,7 @@ chain = int(sys.argv[2]) if len(sys.argv) > 2 else 0
 model, _ = model_files('b4c128')
 ev = maru_b200.Evaluator(model, gpu=0, max_batch=B)
 st = synth.random_states(B, 19, seed=7)
+ev.debug_set(1, 128)
 ev.debug_set(4, 1000)      # trace buffer on, no per-item CTA
 ev.debug_set(5, chain)
 for _ in range(3): ev.forward_states(st)

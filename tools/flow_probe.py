@@ -16,7 +16,7 @@ for name, n in cases:
     ev.debug_set(1, 32)
     want = ev.forward_states(st)
     l0 = ev.info().launches_per_forward
-    ev.debug_set(1, 0)
+    ev.debug_set(1, 128)
     print(name, n, 'per-layer ok, launches', l0, flush=True)
     got = ev.forward_states(st)
     print(name, n, 'flow launches', ev.info().launches_per_forward, 'max err', float(np.abs(got - want).max()), flush=True)

@@ -12,7 +12,7 @@ name = sys.argv[2] if len(sys.argv) > 2 else 'b4c128'
 model, _ = model_files(name)
 ev = maru_b200.Evaluator(model, gpu=0, max_batch=B, flags=maru_b200.capi.FLAG_NO_GRAPH)
 st = synth.random_states(B, 19, seed=7)
-ev.debug_set(1, 64 | (int(sys.argv[3]) if len(sys.argv) > 3 else 0))
+ev.debug_set(1, 64 | 128 | (int(sys.argv[3]) if len(sys.argv) > 3 else 0))
 for _ in range(3): ev.forward_states(st)
 s = ev.debug_stamps().astype(np.float64).reshape(-1, 4)
 t0 = s[0, 0]

@@ -15,7 +15,7 @@ bits = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 model, _ = model_files('b4c128')
 ev = maru_b200.Evaluator(model, gpu=0, max_batch=B, flags=maru_b200.capi.FLAG_NO_GRAPH)
 st = synth.random_states(B, 19, seed=7)
-ev.debug_set(1, bits)
+ev.debug_set(1, bits | 128)
 ev.debug_set(4, cta)
 ev.debug_set(5, chain)
 for _ in range(3): ev.forward_states(st)
