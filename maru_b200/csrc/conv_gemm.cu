@@ -41,9 +41,9 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
   const int STAGES = p.stages;
   const int STAGE_BYTES = Cfg::SLAB_BYTES + Cfg::MASK_BYTES + (has_res ? Cfg::RES_BYTES : 0);
   uint8_t* s_w = smem;
-  uint8_t* s_ones = s_w + Cfg::W_BYTES;
-  uint8_t* s_biasb = s_ones + Cfg::ONES_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_biasb + Cfg::BIASB_BYTES);
+  uint8_t* s_biasb = s_w + Cfg::W_BYTES;               // directly behind the weights: [W | bias image] is one blob
+  uint8_t* s_ones = s_biasb + Cfg::BIASB_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + Cfg::ONES_BYTES);
   uint8_t* s_ident = reinterpret_cast<uint8_t*>(bars) + Cfg::BAR_BYTES;   // keeps stages 128-B aligned (TMA)
   uint8_t* s_stage = s_ident + (has_res ? Cfg::IDENT_BYTES : 0);
   // "stage landed" barriers come in TWO sets, one per MMA-issuing warp (tiles alternate between the two
@@ -82,6 +82,13 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
     // wait and the first slab load (tools/timeline.py).
     mbar_init(wbar, 1);
     fence_mbar_init();
+    if (p.blob != nullptr) {
+      // weights AND the bias operand of the bias MMA, prepared at load time (engine.cu): one request, and no
+      // dependent global load of the bias (~0.7 us) on the prologue's critical path. The CTAs of a layer only start
+      // when the previous layer's CTA has left the SM, so the prologue is fully exposed at every layer boundary.
+      mbar_expect_tx(wbar, Cfg::W_BYTES + Cfg::BIASB_BYTES);
+      bulk_load_1d(s_w, p.blob + (size_t)group * (Cfg::W_BYTES + Cfg::BIASB_BYTES), Cfg::W_BYTES + Cfg::BIASB_BYTES, wbar);
+    } else {
     mbar_expect_tx(wbar, Cfg::W_BYTES);
     if (p.cout_total == NT) {
       bulk_load_1d(s_w, p.w, Cfg::W_BYTES, wbar);            // whole image is contiguous: one request
@@ -91,6 +98,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
         const __nv_bfloat16* src = p.w + ((size_t)tc * p.cout_total + (size_t)group * NT) * 8;
         bulk_load_1d(s_w + (size_t)tc * NT * 16, src, NT * 16, wbar);
       }
+    }
     }
     for (int i = 0; i < MAXS; i++) {
       mbar_init(&full[i], 1);
@@ -117,7 +125,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
       const uint32_t w0 = (i < TILE_M) ? 0x3F803F80u : 0u;
       *reinterpret_cast<uint4*>(s_ones + i * 16) = make_uint4(w0, 0u, 0u, 0u);
     }
-    for (int i = t; i < 2 * NT; i += 256) {                   // bias: (hi, lo, 0, ...) in chunk 0
+    for (int i = t; p.blob == nullptr && i < 2 * NT; i += 256) {   // bias: (hi, lo, 0, ...) in chunk 0
       uint32_t w0 = 0u;
       if (i < NT) {
         const float bv = p.bias[group * NT + i];

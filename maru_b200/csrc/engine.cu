@@ -436,6 +436,7 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   p.in_chunk0 = 0;
   p.w = L.w;
   p.bias = L.b;
+  p.blob = (L.nt_flow == L.nt) ? L.blob : nullptr;      // packed for this channel-group width
   p.res = res ? res->p : nullptr;
   p.res_chunk0 = 0;
   p.out = out.p;

@@ -24,6 +24,7 @@ struct ConvParams {
   int in_chunk0;             // first input plane (channel/8)
   const __nv_bfloat16* w;    // [taps][cin/8][cout_total][8]  (UMMA K-major SWIZZLE_NONE image)
   const float* bias;         // [cout_total]
+  const uint8_t* blob;       // optional [groups][W image of the group | bias operand image]: one bulk copy per CTA
   const __nv_bfloat16* res;  // optional residual planes (may alias out)
   int res_chunk0;
   __nv_bfloat16* out;
