@@ -336,6 +336,20 @@ def run_b200(args):
             if rep > 0:                                            # first rep = warm-up
                 a['ms'] += l['ms']; a['flops'] += l['flops']; a['bytes'] += l['bytes']; a['launches'] += 1
 
+    # the same trunk with one launch per conv layer (debug bit 5): the 3x3 layer alone, for continuity with earlier
+    # rounds and to show what the chain launch averages over (its 1x1 layers are epilogue- / latency-bound)
+    per_layer = None
+    if any(k[0] == 5 for k in prof):
+        ev.debug_set(1, 32)
+        acc = dict(ms=0.0, flops=0.0, launches=0)
+        for rep in range(3):
+            for l in ev.profile_states_device(d_states.data_ptr(), d_out.data_ptr(), B):
+                if rep > 0 and l['kind'] == 1 and l['cin'] == l['cout'] and l['taps'] == 9:
+                    acc['ms'] += l['ms']; acc['flops'] += l['flops']; acc['launches'] += 1
+        ev.debug_set(1, int(os.environ.get('MARU_DBG_BITS', '0')))
+        if acc['launches']:
+            per_layer = acc
+
     # ---------------- reduce over ranks ----------------------------------------------------------
     from maru_b200 import shard
     agg = shard.reduce_stats(shard.RankStats(positions=B * args.steps, batches=args.steps,
@@ -384,6 +398,11 @@ def run_b200(args):
                         peak_source=peaks['source'] + ' (burst, kernel timed alone)',
                         flops_per_launch=dom['flops'] / dom['launches'],
                         us_per_launch=dom['ms'] / dom['launches'] * 1e3,
+                        conv3x3_one_launch_per_layer=(None if per_layer is None else dict(
+                            achieved=per_layer['flops'] / (per_layer['ms'] / 1e3) / 1e12,
+                            frac=per_layer['flops'] / (per_layer['ms'] / 1e3) / 1e12 / peaks['bf16_burst'],
+                            us_per_launch=per_layer['ms'] / per_layer['launches'] * 1e3,
+                            note='same 3x3 C/2->C/2 layer timed alone on the one-launch-per-layer path (debug bit 5)')),
                         whole_net_tflops=value * info.flops_per_eval / 1e12,
                         whole_net_frac_of_sustained=value * info.flops_per_eval / 1e12 / peaks['bf16_sustained'])
         cpu = None
