@@ -286,6 +286,7 @@ def run_b200(args):
         sync_all()
         t_wall = time.perf_counter() - t_wall0
     step_ms = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    info = ev.info()                                   # launches_per_forward of the path that actually ran
     dev_ms = float(sum(step_ms))
     clock = clocks.summary()
 
