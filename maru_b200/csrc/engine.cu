@@ -176,8 +176,9 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
       break;
     }
   }
-  if (L.nt_flow > 0) {
-    const int nt = L.nt_flow, groups = cout / nt;
+  L.nt_blob = L.nt_flow > 0 ? L.nt_flow : (conv_ksplit_supports(cin, L.nt, taps) ? L.nt : 0);
+  if (L.nt_blob > 0) {
+    const int nt = L.nt_blob, groups = cout / nt;
     const size_t wb = (size_t)taps * cin * nt * 2, bb = (size_t)2 * nt * 16;
     std::vector<uint8_t> blob((wb + bb) * groups, 0);
     const float* bias = reinterpret_cast<const float*>(pk.data.data() + b->offset);
@@ -272,6 +273,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   sm_count = prop.multiProcessorCount;
   CK(configure_conv_gemm());
   CK(configure_conv_flow());
+  CK(configure_conv_ksplit());
   CK(configure_attention());
   CK(configure_misc_kernels());
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -436,7 +438,7 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   p.in_chunk0 = 0;
   p.w = L.w;
   p.bias = L.b;
-  p.blob = (L.nt_flow == L.nt) ? L.blob : nullptr;      // packed for this channel-group width
+  p.blob = (L.nt_blob == L.nt) ? L.blob : nullptr;      // packed for this channel-group width
   p.res = res ? res->p : nullptr;
   p.res_chunk0 = 0;
   p.out = out.p;
@@ -534,8 +536,14 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
     prof_begin(L.name.c_str(), L.taps == 9 ? 1 : 2, L.cin, L.cout, L.taps, fl, by, st);
   }
   n_launched++;
-  for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
-    CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
+  // 128 input channels, 3x3 (the C = 256 nets): the K-split kernel pipelines half-slabs where conv_gemm has room for one
+  // stage only (debug bit 4: conv_gemm, A/B)
+  const bool ksplit = conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked && !(dbg_desc & 16) &&
+                      p.trace == nullptr && p.timeline == nullptr && !use_flags;
+  for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) {
+    if (ksplit) CK(launch_conv_ksplit(p, sm_count, st));
+    else CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
+  }
   prof_end(st);
   if (use_flags) {
     out.version += 8u * (unsigned)(L.cout / L.nt);   // 8 epilogue warps per CTA, one CTA per channel group

@@ -101,6 +101,11 @@ bool conv_flow_fits(int cin, int nt, int taps, int w_region);
 // fills w_region / area; returns cudaErrorInvalidConfiguration when a layer does not fit
 cudaError_t launch_conv_flow(FlowParams& fp, int sm_count, cudaStream_t stream);
 
+// ---- 3x3, 128 input channels, half-slab pipeline (conv_ksplit.cu) -----------------------------------
+cudaError_t configure_conv_ksplit();
+bool conv_ksplit_supports(int cin, int nt, int taps);
+cudaError_t launch_conv_ksplit(ConvParams p, int sm_count, cudaStream_t stream);
+
 cudaError_t configure_conv_gemm();
 cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,
                              cudaStream_t stream);
