@@ -108,3 +108,27 @@ def test_flow_kernel_matches_per_layer_launches(built_lib, model_dir):
                 assert np.abs(got - want).max() < 2e-3, (name, n, float(np.abs(got - want).max()))
         finally:
             ev.close()
+
+
+def test_ksplit_kernel_matches_conv_gemm(built_lib, model_dir):
+    """3x3 layers with 128 input channels (C = 256 nets): the half-slab pipeline of conv_ksplit.cu against
+    conv_gemm<128,64,9> (debug bit 4). Same MMAs, but channels 0-63 of all taps are accumulated before 64-127:
+    equal to fp32 rounding of the accumulator, i.e. at most a bf16 ulp per layer; deterministic run to run."""
+    import maru_b200
+    from maru_b200 import synth
+    ev = maru_b200.Evaluator(model_dir('b10c256'), gpu=0, max_batch=64, flags=maru_b200.capi.FLAG_NO_GRAPH)
+    try:
+        for n in (1, 37):
+            st = synth.random_states(n, 19, seed=40 + n)
+            ev.debug_set(1, 16)
+            want = ev.forward_states(st)
+            wbuf = ev.debug_planes(2, n, 128)
+            ev.debug_set(1, 0)
+            got = ev.forward_states(st)
+            gbuf = ev.debug_planes(2, n, 128)
+            assert np.array_equal(got, ev.forward_states(st))
+            scale = np.abs(wbuf).max() + 1e-6
+            assert np.abs(gbuf - wbuf).max() <= 0.02 * scale + 1e-3
+            assert np.abs(got - want).max() < 2e-3, float(np.abs(got - want).max())
+    finally:
+        ev.close()
