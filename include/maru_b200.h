@@ -158,7 +158,7 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * the heads then do not run). key 1: bit0 = disable programmatic dependent launch (A/B timing), bit2 = use the legacy
  * mma.sync attention kernel instead of the tcgen05 one (A/B), bit3 = enable the experimental
  * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower),
- * bit4 = conv_gemm instead of the K-split kernel for 3x3 layers with 128 input channels (A/B),
+ * bit4 = conv_gemm instead of the K-split (3x3, 128 input channels) and wide (1x1, 256 -> k*256) kernels (A/B),
  * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
  * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
  * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on 148 SMs), bits 8-15 = timing experiments inside the flow kernels (tools/flow_ab.py; results are WRONG with any of

@@ -177,24 +177,25 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
     }
   }
   L.nt_blob = L.nt_flow > 0 ? L.nt_flow : (conv_ksplit_supports(cin, L.nt, taps) ? L.nt : 0);
-  if (L.nt_blob > 0) {
-    const int nt = L.nt_blob, groups = cout / nt;
+  const float* bias = reinterpret_cast<const float*>(pk.data.data() + b->offset);
+  auto bf16_rn = [](float f) -> uint16_t {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);     // inf / nan
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+  };
+  auto bf16_to_f = [](uint16_t h) -> float {
+    uint32_t u = (uint32_t)h << 16;
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+  };
+  // per group of nt output channels: [TAPS][KCH][nt][8] weights | bias operand image ([2 k-chunks][nt][8]: (hi, lo, 0...))
+  auto make_blob = [&](int nt, uint8_t** dst) -> int {
+    const int groups = cout / nt;
     const size_t wb = (size_t)taps * cin * nt * 2, bb = (size_t)2 * nt * 16;
     std::vector<uint8_t> blob((wb + bb) * groups, 0);
-    const float* bias = reinterpret_cast<const float*>(pk.data.data() + b->offset);
-    auto bf16_rn = [](float f) -> uint16_t {
-      uint32_t u;
-      memcpy(&u, &f, 4);
-      if ((u & 0x7F800000u) == 0x7F800000u) return (uint16_t)(u >> 16);     // inf / nan
-      u += 0x7FFFu + ((u >> 16) & 1u);
-      return (uint16_t)(u >> 16);
-    };
-    auto bf16_to_f = [](uint16_t h) -> float {
-      uint32_t u = (uint32_t)h << 16;
-      float f;
-      memcpy(&f, &u, 4);
-      return f;
-    };
     for (int g = 0; g < groups; g++) {
       uint16_t* wdst = reinterpret_cast<uint16_t*>(blob.data() + (wb + bb) * g);
       for (int t = 0; t < taps; t++)
@@ -212,10 +213,13 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
         bdst[(size_t)r * 8 + 1] = lo;
       }
     }
-    CK(cudaMalloc(&L.blob, blob.size()));
-    CK(cudaMemcpy(L.blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
-    allocs.push_back(L.blob);
-  }
+    CK(cudaMalloc(dst, blob.size()));
+    CK(cudaMemcpy(*dst, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    allocs.push_back(*dst);
+    return 0;
+  };
+  if (L.nt_blob > 0 && make_blob(L.nt_blob, &L.blob)) return 1;
+  if (conv_wide_supports(cin, cout, taps) && make_blob(256, &L.blob_wide)) return 1;
   return 0;
 }
 
@@ -274,6 +278,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   CK(configure_conv_gemm());
   CK(configure_conv_flow());
   CK(configure_conv_ksplit());
+  CK(configure_conv_wide());
   CK(configure_attention());
   CK(configure_misc_kernels());
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -538,10 +543,16 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   n_launched++;
   // 128 input channels, 3x3 (the C = 256 nets): the K-split kernel pipelines half-slabs where conv_gemm has room for one
   // stage only (debug bit 4: conv_gemm, A/B)
-  const bool ksplit = conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked && !(dbg_desc & 16) &&
-                      p.trace == nullptr && p.timeline == nullptr && !use_flags;
+  const bool plain = !(dbg_desc & 16) && p.trace == nullptr && p.timeline == nullptr && !use_flags;
+  const bool ksplit = plain && conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked;
+  // 256 -> k * 256 channels, 1x1, no residual (qkv of the C = 256 nets): 256 output channels per CTA, half the
+  // redundant input-tile loads of the 128-channel groups
+  const bool wide = plain && conv_wide_supports(L.cin, L.cout, L.taps) && L.blob_wide != nullptr && res == nullptr && in.blocked;
+  ConvParams pw = p;
+  pw.blob = L.blob_wide;
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) {
     if (ksplit) CK(launch_conv_ksplit(p, sm_count, st));
+    else if (wide) CK(launch_conv_wide(pw, sm_count, st));
     else CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
   }
   prof_end(st);

@@ -27,6 +27,7 @@ struct ConvLayer {
   // channels-per-tile it was packed for (0: this layer cannot run inside a chain)
   uint8_t* blob = nullptr;
   int nt_flow = 0;
+  uint8_t* blob_wide = nullptr;   // the same per group of 256 output channels (conv_wide.cu), when the shape allows
   int nt_blob = 0;     // channels per group the blob was packed for (nt_flow, or nt for the K-split kernel)
 };
 struct Block {

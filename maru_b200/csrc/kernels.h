@@ -106,6 +106,11 @@ cudaError_t configure_conv_ksplit();
 bool conv_ksplit_supports(int cin, int nt, int taps);
 cudaError_t launch_conv_ksplit(ConvParams p, int sm_count, cudaStream_t stream);
 
+// ---- 1x1, 256 input channels, 256 output channels per CTA (conv_wide.cu) ------------------------------
+cudaError_t configure_conv_wide();
+bool conv_wide_supports(int cin, int cout, int taps);
+cudaError_t launch_conv_wide(ConvParams p, int sm_count, cudaStream_t stream);
+
 cudaError_t configure_conv_gemm();
 cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,
                              cudaStream_t stream);

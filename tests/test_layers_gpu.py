@@ -112,7 +112,8 @@ def test_flow_kernel_matches_per_layer_launches(built_lib, model_dir):
 
 def test_ksplit_kernel_matches_conv_gemm(built_lib, model_dir):
     """3x3 layers with 128 input channels (C = 256 nets): the half-slab pipeline of conv_ksplit.cu against
-    conv_gemm<128,64,9> (debug bit 4). Same MMAs, but channels 0-63 of all taps are accumulated before 64-127:
+    conv_gemm<128,64,9>, and the 256-channel-per-CTA qkv projection of conv_wide.cu against conv_gemm<256,128,1>
+    (debug bit 4 selects conv_gemm for both). Same MMAs, but channels 0-63 of all taps are accumulated before 64-127:
     equal to fp32 rounding of the accumulator, i.e. at most a bf16 ulp per layer; deterministic run to run."""
     import maru_b200
     from maru_b200 import synth
