@@ -1,5 +1,5 @@
-// conv_wide.cu — 1x1 convolution with 256 input channels and 256 output channels per CTA, no residual (the qkv
-// projection of the C = 256 nets: 256 -> 768 = three groups), sm_100a.
+// conv_wide.cu — 1x1 convolution with 256 input channels and 256 output channels per CTA (the C = 256 nets: the
+// 256 -> 768 qkv projection = three groups, and the 256 -> 256 output projection with its residual), sm_100a.
 //
 // conv_gemm<256, 128, 1> runs this layer as six groups of 128 output channels; every group loads the same 64 KB
 // input tile again, 616 MB of L2 -> SM traffic per layer at batch 512 (~100 us at 6 TB/s; measured 120 us).  Here a
@@ -12,7 +12,8 @@
 //   warp 0   : producer — weights + bias operand (one blob), then two half-tiles per tile
 //   warp 1   : MMA issue (one elected lane): bias, then 8 K-steps per half into one of two 256-column accumulators
 //   warps 2-9: epilogue — 128 columns per thread in four tcgen05.ld of 32, bf16 pack, ReLU, mask, 16-byte stores
-// Same accumulation order as conv_gemm (K ascending), so the outputs are bit-identical to the six-group path.
+// Same accumulation order as conv_gemm (K ascending); a residual is added by the epilogue in fp32 (conv_gemm adds it
+// with an identity MMA before the K loop), so residual layers agree with conv_gemm to one bf16 rounding.
 #include "conv_cfg.cuh"
 
 namespace maru {
@@ -137,7 +138,8 @@ __global__ void __launch_bounds__(CW_THREADS, 1) conv_wide_kernel(const ConvPara
     const int lg = warp & 3;
     const int hcol = (warp - 2) >> 2;
     const int trow = lg * 32 + lane;
-    pdl_wait();                                            // the mask is read from global memory
+    pdl_wait();                                            // the mask (and the residual) are read from global memory
+    const bool has_res = p.res != nullptr;
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
       const int acc = it & 1;
@@ -151,9 +153,22 @@ __global__ void __launch_bounds__(CW_THREADS, 1) conv_wide_kernel(const ConvPara
       __nv_bfloat16* out_row = p.out_blocked
                                    ? p.out + (((size_t)tile * p.out_planes + chunk0) * TILE_M + trow) * 8
                                    : p.out + ((size_t)chunk0 * p.rows_alloc + grow) * 8;
+      // residual (same tensor geometry as the output, e.g. h = h + proj(o) in place): all 128 columns of this
+      // thread's row are requested before the accumulator is waited for
+      uint4 rv[CW / 8];
+      if (has_res) {
+        const size_t rstride = p.res_blocked ? (size_t)TILE_M * 8 : (size_t)p.rows_alloc * 8;
+        const int rc0 = p.res_chunk0 + group * (CW_NT / 8) + hcol * (CW / 8);
+        const __nv_bfloat16* res_row = p.res_blocked
+                                           ? p.res + (((size_t)tile * p.res_planes + rc0) * TILE_M + trow) * 8
+                                           : p.res + ((size_t)rc0 * p.rows_alloc + grow) * 8;
+#pragma unroll
+        for (int q = 0; q < CW / 8; q++)
+          rv[q] = on ? *reinterpret_cast<const uint4*>(res_row + (size_t)q * rstride) : make_uint4(0u, 0u, 0u, 0u);
+      }
       mbar_wait(&tfull[acc], (uint32_t)((it >> 1) & 1));
       tc_fence_after();
-#pragma unroll 1
+#pragma unroll
       for (int c0 = 0; c0 < CW; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(t_addr + c0, v);
@@ -166,9 +181,21 @@ __global__ void __launch_bounds__(CW_THREADS, 1) conv_wide_kernel(const ConvPara
 #pragma unroll
         for (int q = 0; q < 4; q++) {
           uint32_t o[4];
+          uint32_t rw[4] = {0u, 0u, 0u, 0u};
+          if (has_res) {
+            rw[0] = rv[c0 / 8 + q].x;
+            rw[1] = rv[c0 / 8 + q].y;
+            rw[2] = rv[c0 / 8 + q].z;
+            rw[3] = rv[c0 / 8 + q].w;
+          }
 #pragma unroll
           for (int e = 0; e < 4; e++) {
-            uint32_t pk = pack_bf16x2(__uint_as_float(v[q * 8 + 2 * e]), __uint_as_float(v[q * 8 + 2 * e + 1]));
+            float lo = __uint_as_float(v[q * 8 + 2 * e]), hi = __uint_as_float(v[q * 8 + 2 * e + 1]);
+            if (has_res) {
+              lo += bf16_lo(rw[e]);
+              hi += bf16_hi(rw[e]);
+            }
+            uint32_t pk = pack_bf16x2(lo, hi);
             if (p.relu) pk = relu_bf16x2(pk);
             o[e] = on ? pk : 0u;
           }
@@ -199,7 +226,7 @@ int conv_wide_blob_bytes() { return CW_W_BYTES + CW_BIASB_BYTES; }
 
 // p.blob: [groups of 256 output channels][W image [32 k-chunks][256][8] | bias operand image]
 cudaError_t launch_conv_wide(ConvParams p, int sm_count, cudaStream_t stream) {
-  if (p.blob == nullptr || !p.in_blocked || p.res != nullptr || (p.cout_total % CW_NT) != 0) return cudaErrorInvalidValue;
+  if (p.blob == nullptr || !p.in_blocked || (p.cout_total % CW_NT) != 0) return cudaErrorInvalidValue;
   const int groups = p.cout_total / CW_NT;
   const int n_tiles = (p.m_rows + TILE_M - 1) / TILE_M;
   int gx = sm_count / groups;

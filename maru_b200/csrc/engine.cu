@@ -545,9 +545,10 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   // stage only (debug bit 4: conv_gemm, A/B)
   const bool plain = !(dbg_desc & 16) && p.trace == nullptr && p.timeline == nullptr && !use_flags;
   const bool ksplit = plain && conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked;
-  // 256 -> k * 256 channels, 1x1, no residual (qkv of the C = 256 nets): 256 output channels per CTA, half the
+  // 256 -> k * 256 channels, 1x1 (qkv and the output projection of the C = 256 nets): 256 output channels per CTA, half the
   // redundant input-tile loads of the 128-channel groups
-  const bool wide = plain && conv_wide_supports(L.cin, L.cout, L.taps) && L.blob_wide != nullptr && res == nullptr && in.blocked;
+  const bool wide = plain && conv_wide_supports(L.cin, L.cout, L.taps) && L.blob_wide != nullptr && in.blocked &&
+                    (res == nullptr || res->blocked == out.blocked);
   ConvParams pw = p;
   pw.blob = L.blob_wide;
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) {
