@@ -395,7 +395,7 @@ def run_b200(args):
         roofline = dict(bound='tensor', achieved=achieved, peak=peaks['bf16_burst'], unit='TFLOP/s',
                         frac=achieved / peaks['bf16_burst'], traffic=traffic,
                         kernel=(f'conv_flow {dom["name"]} ({dom["launches"]} timed launches)' if dom_key[0] == 5 else
-                                f'conv_gemm 3x3 {dom_key[1]}->{dom_key[2]} ({dom["launches"]} timed launches)'),
+                                f'conv 3x3 {dom_key[1]}->{dom_key[2]} ({dom["launches"]} timed launches; conv_gemm / conv_ksplit / conv_pair by shape)'),
                         peak_source=peaks['source'] + ' (burst, kernel timed alone)',
                         flops_per_launch=dom['flops'] / dom['launches'],
                         us_per_launch=dom['ms'] / dom['launches'] * 1e3,

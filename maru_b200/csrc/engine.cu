@@ -279,6 +279,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   CK(configure_conv_flow());
   CK(configure_conv_ksplit());
   CK(configure_conv_wide());
+  CK(configure_conv_pair());
   CK(configure_attention());
   CK(configure_misc_kernels());
   CK(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
@@ -545,6 +546,10 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   // stage only (debug bit 4: conv_gemm, A/B)
   const bool plain = !(dbg_desc & 16) && p.trace == nullptr && p.timeline == nullptr && !use_flags;
   const bool ksplit = plain && conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked;
+  // 128 -> 128 3x3 on CTA pairs (cta_group::2): N = 128 per SM in 64 cycles per K step instead of two N = 64 MMAs of 48
+  static const bool pair_off = getenv("MARU_B200_PAIR") != nullptr && getenv("MARU_B200_PAIR")[0] == '0';
+  const bool pair = ksplit && !pair_off && conv_pair_supports(L.cin, L.cout, L.taps) && L.nt == 64 &&
+                    (res == nullptr || res->blocked == out.blocked);
   // 256 -> k * 256 channels, 1x1 (qkv and the output projection of the C = 256 nets): 256 output channels per CTA, half the
   // redundant input-tile loads of the 128-channel groups
   const bool wide = plain && conv_wide_supports(L.cin, L.cout, L.taps) && L.blob_wide != nullptr && in.blocked &&
@@ -552,7 +557,8 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   ConvParams pw = p;
   pw.blob = L.blob_wide;
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) {
-    if (ksplit) CK(launch_conv_ksplit(p, sm_count, st));
+    if (pair) CK(launch_conv_pair(p, sm_count, st));
+    else if (ksplit) CK(launch_conv_ksplit(p, sm_count, st));
     else if (wide) CK(launch_conv_wide(pw, sm_count, st));
     else CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
   }
