@@ -161,7 +161,8 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * bit4 = conv_gemm instead of the K-split (3x3, 128 input channels) and wide (1x1, 256 -> k*256) kernels (A/B),
  * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
  * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
- * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on 148 SMs), bits 8-15 = timing experiments inside the flow kernels (tools/flow_ab.py; results are WRONG with any of
+ * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on 148 SMs), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B),
+ * bits 8-17 = timing experiments inside the flow kernels (tools/flow_ab.py; results are WRONG with any of
  * them set): 8 fence in the storing warps, 10 no dependency waits, 11 no slab loads, 12 no neighbour-flag waits,
  * 13 no MMAs, 14 no stores, 15 no epilogue work at all. */
 #define MARU_DBG_STOP_AFTER 0

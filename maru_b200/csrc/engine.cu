@@ -547,8 +547,7 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   const bool plain = !(dbg_desc & 16) && p.trace == nullptr && p.timeline == nullptr && !use_flags;
   const bool ksplit = plain && conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked;
   // 128 -> 128 3x3 on CTA pairs (cta_group::2): N = 128 per SM in 64 cycles per K step instead of two N = 64 MMAs of 48
-  static const bool pair_off = getenv("MARU_B200_PAIR") != nullptr && getenv("MARU_B200_PAIR")[0] == '0';
-  const bool pair = ksplit && !pair_off && conv_pair_supports(L.cin, L.cout, L.taps) && L.nt == 64 &&
+  const bool pair = ksplit && !(dbg_desc & (1 << 20)) && conv_pair_supports(L.cin, L.cout, L.taps) && L.nt == 64 &&
                     (res == nullptr || res->blocked == out.blocked);
   // 256 -> k * 256 channels, 1x1 (qkv and the output projection of the C = 256 nets): 256 output channels per CTA, half the
   // redundant input-tile loads of the 128-channel groups

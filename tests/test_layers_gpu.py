@@ -111,9 +111,8 @@ def test_flow_kernel_matches_per_layer_launches(built_lib, model_dir):
 
 
 def test_ksplit_kernel_matches_conv_gemm(built_lib, model_dir):
-    """3x3 layers with 128 input channels (C = 256 nets): the half-slab pipeline of conv_ksplit.cu against
-    conv_gemm<128,64,9>, and the 256-channel-per-CTA qkv projection of conv_wide.cu against conv_gemm<256,128,1>
-    (debug bit 4 selects conv_gemm for both). Same MMAs, but channels 0-63 of all taps are accumulated before 64-127:
+    """C = 256 nets: the CTA-pair kernel conv_pair.cu (3x3 128 -> 128, cta_group::2), its fallback conv_ksplit.cu (half-slab
+    pipeline) and the 256-channel-per-CTA projections of conv_wide.cu, all against conv_gemm (debug bit 4). Same MMAs, but channels 0-63 of all taps are accumulated before 64-127:
     equal to fp32 rounding of the accumulator, i.e. at most a bf16 ulp per layer; deterministic run to run."""
     import maru_b200
     from maru_b200 import synth
@@ -124,7 +123,10 @@ def test_ksplit_kernel_matches_conv_gemm(built_lib, model_dir):
             ev.debug_set(1, 16)
             want = ev.forward_states(st)
             wbuf = ev.debug_planes(2, n, 128)
-            ev.debug_set(1, 0)
+            ev.debug_set(1, 1 << 20)           # conv_ksplit for the 128 -> 128 layers (the fallback of conv_pair)
+            mid = ev.forward_states(st)
+            assert np.abs(mid - want).max() < 5e-3, float(np.abs(mid - want).max())
+            ev.debug_set(1, 0)                 # default: conv_pair (CTA pairs) + conv_wide
             got = ev.forward_states(st)
             gbuf = ev.debug_planes(2, n, 128)
             assert np.array_equal(got, ev.forward_states(st))
