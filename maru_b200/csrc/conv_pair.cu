@@ -19,17 +19,25 @@
 namespace maru {
 
 constexpr int CP_THREADS = 320;
-constexpr int CP_CIN = 128, CP_N = 128, CP_NH = 64, CP_TAPS = 9;      // NH: B rows (output channels) held per CTA
+constexpr int CP_TAPS = 9;
 constexpr int CP_LEAD = 24, CP_SLAB_ROWS = TILE_M + 2 * CP_LEAD;      // 176
-constexpr int CP_KCH = CP_CIN / 8;
-constexpr int CP_HALF_BYTES = (CP_KCH / 2) * CP_SLAB_ROWS * 16;       // 22 528
-constexpr int CP_W_BYTES = CP_TAPS * CP_CIN * CP_NH * 2;              // 147 456
-constexpr int CP_BIASB_BYTES = 2 * CP_NH * 16;
+constexpr int CP_HALF_PLANES = 8;                                     // a half-item is 64 input channels
+constexpr int CP_HALF_BYTES = CP_HALF_PLANES * CP_SLAB_ROWS * 16;     // 22 528
 constexpr int CP_ONES_BYTES = 2 * TILE_M * 16;
 constexpr int CP_BAR_BYTES = 256;
-constexpr int CP_STAGES = 3;
-constexpr int CP_SMEM = CP_W_BYTES + CP_BIASB_BYTES + CP_ONES_BYTES + CP_BAR_BYTES + CP_STAGES * CP_HALF_BYTES;
-static_assert(CP_SMEM <= 232448, "shared memory budget");
+// <CIN, N>: <128, 128> the inner layers of the C = 256 nets (two half-items per tile, 147 KB of taps per CTA, 3 stages);
+//           <64, 64>   the inner layers of the C = 128 nets (one item per tile, 37 KB of taps per CTA, 4 stages)
+template <int CIN, int N>
+struct PairCfg {
+  static constexpr int NH = N / 2;                                    // B rows (output channels) held per CTA
+  static constexpr int NHALF = CIN / 64;
+  static constexpr int KCH = CIN / 8;
+  static constexpr int W_BYTES = CP_TAPS * CIN * NH * 2;
+  static constexpr int BIASB_BYTES = 2 * NH * 16;
+  static constexpr int STAGES = (CIN == 128) ? 3 : 4;
+  static constexpr int SMEM = W_BYTES + BIASB_BYTES + CP_ONES_BYTES + CP_BAR_BYTES + STAGES * CP_HALF_BYTES;
+  static_assert(SMEM <= 232448, "shared memory budget");
+};
 
 __device__ __forceinline__ uint32_t cp_cluster_rank() {
   uint32_t r;
@@ -94,20 +102,25 @@ __device__ __forceinline__ void cp_commit_both(uint64_t* bar) {
                : "memory");
 }
 
+template <int CIN, int N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_pair_kernel(const ConvParams p) {
+  using Cfg = PairCfg<CIN, N>;
+  constexpr int CP_W_BYTES = Cfg::W_BYTES, CP_BIASB_BYTES = Cfg::BIASB_BYTES, CP_NH = Cfg::NH, CP_N = N, CP_KCH = Cfg::KCH;
+  constexpr int NHALF = Cfg::NHALF;
+  constexpr uint32_t CP_STAGES = Cfg::STAGES;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* s_w = smem;
   uint8_t* s_biasb = s_w + CP_W_BYTES;                    // [W | bias image] is one blob
   uint8_t* s_ones = s_biasb + CP_BIASB_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_ones + CP_ONES_BYTES);
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(bars) + CP_BAR_BYTES;
-  uint64_t* full = bars;            // [3] this CTA's half-slab landed
-  uint64_t* pfull = bars + 3;       // [3] leader only: the peer's half-slab landed (relay arrives)
-  uint64_t* empty = bars + 6;       // [3] half-slab consumed (pair-MMA commit, multicast to both CTAs)
-  uint64_t* tfull = bars + 9;       // [2] accumulator ready (commit, multicast)
-  uint64_t* tempty = bars + 11;     // [2] leader only: accumulator drained by the 16 epilogue warps of the pair
-  uint64_t* wbar = bars + 13;       // this CTA's weights + bias operand landed
-  uint64_t* pwbar = bars + 14;      // leader only: the peer's weights landed
+  uint64_t* full = bars;            // [4] this CTA's half-slab landed
+  uint64_t* pfull = bars + 4;       // [4] leader only: the peer's half-slab landed (relay arrives)
+  uint64_t* empty = bars + 8;       // [4] half-slab consumed (pair-MMA commit, multicast to both CTAs)
+  uint64_t* tfull = bars + 12;      // [2] accumulator ready (commit, multicast)
+  uint64_t* tempty = bars + 14;     // [2] leader only: accumulator drained by the 16 epilogue warps of the pair
+  uint64_t* wbar = bars + 16;       // this CTA's weights + bias operand landed
+  uint64_t* pwbar = bars + 17;      // leader only: the peer's weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 31);
 
   pdl_launch_dependents();
@@ -126,7 +139,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
     mbar_expect_tx(wbar, CP_W_BYTES + CP_BIASB_BYTES);
     // this CTA's half of B: the 64 output channels of group `rank`
     bulk_load_1d(s_w, p.blob + (size_t)rank * (CP_W_BYTES + CP_BIASB_BYTES), CP_W_BYTES + CP_BIASB_BYTES, wbar);
-    for (int i = 0; i < CP_STAGES; i++) {
+    for (int i = 0; i < (int)CP_STAGES; i++) {
       mbar_init(&full[i], 1);
       mbar_init(&pfull[i], 1);
       mbar_init(&empty[i], 1);
@@ -139,7 +152,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
     fence_mbar_init();
   }
   if (warp == 1) {
-    cp_tmem_alloc2(tmem_slot, 256);          // two accumulators of 128 columns (in each CTA of the pair)
+    cp_tmem_alloc2(tmem_slot, 2 * CP_N);     // two accumulators of N columns (in each CTA of the pair)
     cp_tmem_relinquish2();
   }
   if (warp >= 2) {
@@ -165,16 +178,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
       if (tile >= n_tiles) tile = n_tiles - 1;
       const size_t row0 = (size_t)GUARD_ROWS + (size_t)tile * TILE_M;
 #pragma unroll 1
-      for (int half = 0; half < 2; half++, h++) {
+      for (int half = 0; half < NHALF; half++, h++) {
         const uint32_t s = h % CP_STAGES;
         cp_wait_cluster(&empty[s], ((h / CP_STAGES) & 1u) ^ 1u);   // arrived by the leader's multicast commit
         if (elect_one()) {
           mbar_expect_tx(&full[s], CP_HALF_BYTES);
           uint8_t* dst = s_stage + s * CP_HALF_BYTES;
 #pragma unroll 1
-          for (int c = 0; c < CP_KCH / 2; c++) {
+          for (int c = 0; c < CP_HALF_PLANES; c++) {
             const __nv_bfloat16* src =
-                p.in + ((size_t)(p.in_chunk0 + half * (CP_KCH / 2) + c) * p.rows_alloc + row0 - CP_LEAD) * 8;
+                p.in + ((size_t)(p.in_chunk0 + half * CP_HALF_PLANES + c) * p.rows_alloc + row0 - CP_LEAD) * 8;
             bulk_load_1d(dst + c * CP_SLAB_ROWS * 16, src, CP_SLAB_ROWS * 16, &full[s]);
           }
         }
@@ -189,7 +202,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
     uint32_t h = 0;
     for (int q = cluster; q < n_pairs; q += n_clusters) {
 #pragma unroll 1
-      for (int half = 0; half < 2; half++, h++) {
+      for (int half = 0; half < NHALF; half++, h++) {
         const uint32_t s = h % CP_STAGES;
         mbar_wait(&full[s], (h / CP_STAGES) & 1u);
         if (lane == 0) cp_arrive_cluster(cp_mapa(smem_u32(&pfull[s]), 0));
@@ -198,7 +211,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
     }
   } else if (warp == 1) {
     // =========================== MMA issue (leader CTA) ===========================
-    constexpr uint32_t idesc = umma_idesc_bf16(2 * TILE_M, CP_N, 0, 0);
+    constexpr uint32_t idesc = umma_idesc_bf16(2 * TILE_M, N, 0, 0);
     const uint64_t a_d = umma_desc(0, CP_SLAB_ROWS * 16, 128);
     const uint64_t r_d = umma_desc(0, TILE_M * 16, 128);
     const uint64_t b_d = umma_desc(0, CP_NH * 16, 128);            // each CTA holds N/2 = 64 rows of B per K chunk
@@ -215,7 +228,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
       const uint32_t d_tmem = tmem_base + acc * CP_N;
       cp_wait_cluster(&tempty[acc], (uint32_t)((it >> 1) & 1) ^ 1u);
 #pragma unroll 1
-      for (int half = 0; half < 2; half++, h++) {
+      for (int half = 0; half < NHALF; half++, h++) {
         const uint32_t s = h % CP_STAGES;
         mbar_wait(&full[s], (h / CP_STAGES) & 1u);
         cp_wait_cluster(&pfull[s], (h / CP_STAGES) & 1u);
@@ -223,19 +236,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
         if (elect_one()) {
           const uint32_t a_lo = (uint32_t)a_d + (smem_u32(s_stage + s * CP_HALF_BYTES) >> 4);
           if (half == 0) cp_umma2<0>(d_tmem, ones_lo, r_hi, biasb_lo, b_hi, idesc);           // D = bias
-          const uint32_t wh = w_lo + (uint32_t)half * (CP_KCH / 2) * CP_NH;                   // this half's K chunks
+          const uint32_t wh = w_lo + (uint32_t)half * CP_HALF_PLANES * CP_NH;                  // this half's K chunks
 #pragma unroll
           for (int t = 0; t < CP_TAPS; t++) {
             const int off = (t / 3 - 1) * PITCH + (t % 3 - 1);
 #pragma unroll
-            for (int j = 0; j < CP_CIN / 32; j++) {
+            for (int j = 0; j < CP_HALF_PLANES / 2; j++) {
               const uint32_t a16 = (2 * j) * CP_SLAB_ROWS + CP_LEAD + off;                     // in 16-byte units
               const uint32_t b16 = (t * CP_KCH + 2 * j) * CP_NH;
               cp_umma2<1>(d_tmem, a_lo + a16, a_hi, wh + b16, b_hi, idesc);
             }
           }
           cp_commit_both(&empty[s]);
-          if (half == 1) cp_commit_both(&tfull[acc]);
+          if (half == NHALF - 1) cp_commit_both(&tfull[acc]);
         }
         __syncwarp();
       }
@@ -278,7 +291,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
       tc_fence_after();
       uint32_t v[CW];
       tmem_ld32(t_addr, v);
-      tmem_ld32(t_addr + 32, v + 32);
+      if constexpr (CW == 64) tmem_ld32(t_addr + 32, v + 32);
       tmem_ld_wait();
       tc_fence_before();
       __syncwarp();
@@ -314,28 +327,44 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
   cp_cluster_sync();                          // nobody frees TMEM or exits while the peer may still signal / be read
   if (warp == 1) {
     tc_fence_after();
-    cp_tmem_dealloc2(tmem_base, 256);
+    cp_tmem_dealloc2(tmem_base, 2 * CP_N);
   }
 }
 
-cudaError_t configure_conv_pair() {
-  cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CP_SMEM);
+template <int CIN, int N>
+static cudaError_t configure_pair_cfg() {
+  cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<CIN, N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       PairCfg<CIN, N>::SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+  return cudaFuncSetAttribute(conv_pair_kernel<CIN, N>, cudaFuncAttributePreferredSharedMemoryCarveout,
                               cudaSharedmemCarveoutMaxShared);
 }
+cudaError_t configure_conv_pair() {
+  cudaError_t e = configure_pair_cfg<128, 128>();
+  if (e != cudaSuccess) return e;
+  return configure_pair_cfg<64, 64>();
+}
 
-bool conv_pair_supports(int cin, int cout, int taps) { return cin == CP_CIN && cout == CP_N && taps == CP_TAPS; }
+bool conv_pair_supports(int cin, int cout, int taps) {
+  return taps == CP_TAPS && ((cin == 128 && cout == 128) || (cin == 64 && cout == 64));
+}
+int conv_pair_blob_nt(int cout) { return cout / 2; }      // output channels per CTA of the pair = blob group width
 
-// p.blob: [2 groups of 64 output channels][W image | bias operand image] (the conv_ksplit blob)
-cudaError_t launch_conv_pair(ConvParams p, int sm_count, cudaStream_t stream) {
-  if (p.blob == nullptr || p.in_blocked || p.cout_total != CP_N) return cudaErrorInvalidValue;
+// p.blob: [2 groups of cout/2 output channels][W image | bias operand image]
+cudaError_t launch_conv_pair(ConvParams p, int cin, int sm_count, cudaStream_t stream) {
+  if (p.blob == nullptr || p.in_blocked) return cudaErrorInvalidValue;
   const int n_tiles = (p.m_rows + TILE_M - 1) / TILE_M;
   const int n_pairs = (n_tiles + 1) / 2;
   int clusters = sm_count / 2;
   if (clusters > n_pairs) clusters = n_pairs;
   if (clusters < 1) clusters = 1;
-  return launch_kernel(conv_pair_kernel, dim3(2 * clusters), dim3(CP_THREADS), (size_t)CP_SMEM, stream, p.pdl != 0, p);
+  if (cin == 128 && p.cout_total == 128)
+    return launch_kernel(conv_pair_kernel<128, 128>, dim3(2 * clusters), dim3(CP_THREADS), (size_t)PairCfg<128, 128>::SMEM,
+                         stream, p.pdl != 0, p);
+  if (cin == 64 && p.cout_total == 64)
+    return launch_kernel(conv_pair_kernel<64, 64>, dim3(2 * clusters), dim3(CP_THREADS), (size_t)PairCfg<64, 64>::SMEM,
+                         stream, p.pdl != 0, p);
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace maru

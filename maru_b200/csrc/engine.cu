@@ -220,6 +220,10 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
   };
   if (L.nt_blob > 0 && make_blob(L.nt_blob, &L.blob)) return 1;
   if (conv_wide_supports(cin, cout, taps) && make_blob(256, &L.blob_wide)) return 1;
+  if (conv_pair_supports(cin, cout, taps)) {
+    if (L.nt_blob == conv_pair_blob_nt(cout)) L.blob_pair = L.blob;
+    else if (make_blob(conv_pair_blob_nt(cout), &L.blob_pair)) return 1;
+  }
   return 0;
 }
 
@@ -258,6 +262,10 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     return 1;
   }
   gpu_id = gpu;
+  if (const char* pe = getenv("MARU_B200_PAIR64")) {      // "0": never, "N": from batch N up
+    pair64_on = pe[0] != '0' || pe[1] != 0;
+    if (pair64_on) pair64_min_batch = atoi(pe);
+  }
   if (const char* ff = getenv("MARU_B200_FLOW")) {
     // "1": the persistent flow kernels at every batch size, "0": never (default: for 249..354 positions on 148 SMs)
     if (ff[0] == '1') dbg_desc |= 128;
@@ -547,8 +555,10 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   const bool plain = !(dbg_desc & 16) && p.trace == nullptr && p.timeline == nullptr && !use_flags;
   const bool ksplit = plain && conv_ksplit_supports(L.cin, L.nt, L.taps) && p.blob != nullptr && !in.blocked;
   // 128 -> 128 3x3 on CTA pairs (cta_group::2): N = 128 per SM in 64 cycles per K step instead of two N = 64 MMAs of 48
-  const bool pair = ksplit && !(dbg_desc & (1 << 20)) && conv_pair_supports(L.cin, L.cout, L.taps) && L.nt == 64 &&
-                    (res == nullptr || res->blocked == out.blocked);
+  const bool pair = plain && !(dbg_desc & (1 << 20)) && conv_pair_supports(L.cin, L.cout, L.taps) && L.blob_pair != nullptr &&
+                    !in.blocked && (res == nullptr || res->blocked == out.blocked) && pair_pays(L.cin, n);
+  ConvParams pp = p;
+  pp.blob = L.blob_pair;
   // 256 -> k * 256 channels, 1x1 (qkv and the output projection of the C = 256 nets): 256 output channels per CTA, half the
   // redundant input-tile loads of the 128-channel groups
   const bool wide = plain && conv_wide_supports(L.cin, L.cout, L.taps) && L.blob_wide != nullptr && in.blocked &&
@@ -556,7 +566,7 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   ConvParams pw = p;
   pw.blob = L.blob_wide;
   for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) {
-    if (pair) CK(launch_conv_pair(p, sm_count, st));
+    if (pair) CK(launch_conv_pair(pp, L.cin, sm_count, st));
     else if (ksplit) CK(launch_conv_ksplit(p, sm_count, st));
     else if (wide) CK(launch_conv_wide(pw, sm_count, st));
     else CK(launch_conv_gemm(p, L.cin, L.nt, L.taps, sm_count, st));
@@ -701,6 +711,11 @@ void Engine::device_ref(int delta) {
 bool Engine::flow_pays(int n) const {
   const int n_tiles = (total_rows(n) + TILE_M - 1) / TILE_M;
   return 4 * n_tiles >= 21 * sm_count && 2 * n_tiles < 15 * sm_count;     // 5.25 <= tiles per CTA < 7.5: batch 249..354
+}
+// CTA pairs for the 64 -> 64 layers of the C = 128 nets: decided by measurement
+bool Engine::pair_pays(int cin, int n) const {
+  if (cin == 128) return true;
+  return pair64_on && n >= pair64_min_batch;
 }
 bool Engine::flow_enabled() {
   if (dbg_desc & 128) return flow_device_ok();      // debug: force the flow kernels at any batch size

@@ -27,6 +27,7 @@ struct ConvLayer {
   // channels-per-tile it was packed for (0: this layer cannot run inside a chain)
   uint8_t* blob = nullptr;
   int nt_flow = 0;
+  uint8_t* blob_pair = nullptr;   // per group of cout/2 output channels (conv_pair.cu: one group per CTA of a pair)
   uint8_t* blob_wide = nullptr;   // the same per group of 256 output channels (conv_wide.cu), when the shape allows
   int nt_blob = 0;     // channels per group the blob was packed for (nt_flow, or nt for the K-split kernel)
 };
@@ -150,6 +151,9 @@ struct Engine {
   double pending_flops = 0, pending_bytes = 0;
   bool flow_enabled();
   bool flow_device_ok();
+  bool pair_pays(int cin, int n) const;
+  bool pair64_on = false;           // measured slower than conv_gemm<64,64,9> at every batch size
+  int pair64_min_batch = 1;
   bool flow_pays(int n) const;      // enough tiles per CTA for the persistent kernels to win
   bool flow_live = true;            // flow_pays(live batch size) of the forward being enqueued
   void device_ref(int delta);

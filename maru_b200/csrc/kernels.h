@@ -114,7 +114,8 @@ cudaError_t launch_conv_wide(ConvParams p, int sm_count, cudaStream_t stream);
 // ---- 3x3 128 -> 128 on CTA pairs, cta_group::2 (conv_pair.cu) ------------------------------------------
 cudaError_t configure_conv_pair();
 bool conv_pair_supports(int cin, int cout, int taps);
-cudaError_t launch_conv_pair(ConvParams p, int sm_count, cudaStream_t stream);
+int conv_pair_blob_nt(int cout);
+cudaError_t launch_conv_pair(ConvParams p, int cin, int sm_count, cudaStream_t stream);
 
 cudaError_t configure_conv_gemm();
 cudaError_t launch_conv_gemm(const ConvParams& p, int cin, int nt, int taps, int sm_count,
