@@ -138,10 +138,17 @@ __device__ __forceinline__ void flow_wait_flag(const unsigned* flag, unsigned ne
     if (++spins > MARU_SPIN_LIMIT) flow_timeout(2, l, i, ld_acquire_gpu(flag), need);
   }
 }
+// The blob of a 3x3 layer is 74 KB: as ONE bulk copy it occupies the SM's copy engine for ~0.9 us and the slab requests
+// of the tiles being computed queue behind it; in 4 KB pieces the slab requests issued meanwhile slip in between.
 __device__ __forceinline__ void flow_request_blob(const FlowLayer& N, uint32_t dst, uint32_t bar) {
   const uint32_t blob = (uint32_t)(N.taps * N.cin * N.nt * 2 + 2 * N.nt * 16);
+  const uint8_t* src = N.blob;
   mbar_expect_tx_a(bar, blob);
-  bulk_load_a(dst, N.blob, blob, bar);
+#pragma unroll 1
+  for (uint32_t off = 0; off < blob; off += 4096u) {
+    const uint32_t n = (blob - off < 4096u) ? blob - off : 4096u;
+    bulk_load_a(dst + off, src + off, n, bar);
+  }
 }
 
 // what every role needs to know about the CTA
