@@ -710,7 +710,8 @@ void Engine::device_ref(int delta) {
 // 224: 444 / 433, 256: 448-458 / 466, 320: 544 / 562, 384: 666 / 659, 512: 838 / 824, 1024: 1710 / 1617.
 bool Engine::flow_pays(int n) const {
   const int n_tiles = (total_rows(n) + TILE_M - 1) / TILE_M;
-  return 4 * n_tiles >= 21 * sm_count && 2 * n_tiles < 15 * sm_count;     // 5.25 <= tiles per CTA < 7.5: batch 249..354
+  // C = 256 nets: only the 128 -> 256 expansions fit a chain (two-layer launches, measured 0.7 % slower at batch 256)
+  return C <= 128 && 4 * n_tiles >= 21 * sm_count && 2 * n_tiles < 15 * sm_count;     // 5.25 <= tiles per CTA < 7.5: batch 249..354
 }
 // CTA pairs for the 64 -> 64 layers of the C = 128 nets: decided by measurement
 bool Engine::pair_pays(int cin, int n) const {
