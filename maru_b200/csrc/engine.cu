@@ -119,7 +119,7 @@ static int choose_nt(int cin, int cout, int taps) {
                        (cin == 64 && (nt == 128 || nt == 64 || nt == 32)) ||
                        (cin == 32 && (nt == 64 || nt == 32))));
     if (!ok) continue;
-    if (taps == 9 && cin == 64 && nt == 128 && cout != 128) continue;
+    if (taps == 9 && cin == 64 && nt == 128 && cout % 128 != 0) continue;
     return nt;
   }
   return 0;
