@@ -233,7 +233,6 @@ constexpr int A2_PN = 80;                   // keys per step
 constexpr int A2_NP = POS_ROWS / A2_PN;     // 5 parts
 constexpr int A2_NT = 3;                    // query tiles
 constexpr int A2_Q0 = PITCH;                // first query row: skip the top halo row of the position
-constexpr int A2_STEPS = A2_NT * A2_NP;
 constexpr int A2_P_BYTES = (A2_PN / 8) * TILE_M * 16; // 20 480 per buffer
 constexpr int A2_Q_BYTES = A2_DCH * TILE_M * 16;
 constexpr int A2_SMEM = A2_K_BYTES + A2_V_BYTES + 2 * A2_P_BYTES + 2 * A2_Q_BYTES + 416 + 32 + 112;
@@ -276,6 +275,28 @@ __device__ __forceinline__ void exp_store16(const uint32_t* v, float c, uint8_t*
       o[e] = (POLY && h == 1) ? pack_bf16x2(exp2_fma(x0), exp2_fma(x1)) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
     }
     *reinterpret_cast<uint4*>(s_p + ((chunk + h) * TILE_M + trow) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// Key parts (80 padded rows each) that hold at least one on-board cell: a 9x9 board centred in the 19x19 frame lives in
+// parts 1-3, a 13x13 board in parts 1-4. A part without on-board keys contributes exactly nothing (its V rows and its
+// ones column are zero), so skipping it leaves the result bit-identical and saves its QK, its 128 x 80 exponentials and
+// its PV. `m16` is this lane's 16 mask bytes (lanes 0..24 cover the 400 rows), the result is the same in every lane.
+__device__ __forceinline__ void a2_active_parts(const uint4 m16, const int lane, int& np, uint32_t& plist) {
+  const bool any = lane < POS_ROWS / 16 && (m16.x | m16.y | m16.z | m16.w) != 0u;
+  const uint32_t b = __ballot_sync(0xffffffffu, any);           // bit i: rows 16i .. 16i+15
+  np = 0;
+  plist = 0u;
+#pragma unroll
+  for (int part = 0; part < A2_NP; part++) {
+    if ((b >> (5 * part)) & 31u) {                               // 80 rows = 5 groups of 16
+      plist |= (uint32_t)part << (3 * np);
+      np++;
+    }
+  }
+  if (np == 0) {                                                 // no on-board cell at all: keep the full sequence
+    np = A2_NP;
+    plist = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
   }
 }
 
@@ -359,12 +380,28 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     const uint32_t v_lo = (uint32_t)v_d + (smem_u32(s_v) >> 4);
     const uint32_t p_lo = (uint32_t)q_d + (smem_u32(s_p) >> 4);
     const uint32_t q_lo = (uint32_t)q_d + (smem_u32(s_q) >> 4);
+    int np;
+    uint32_t plist;
+    {
+      uint4 m16 = make_uint4(0u, 0u, 0u, 0u);
+      if (lane < POS_ROWS / 16) m16 = reinterpret_cast<const uint4*>(p.mask + (size_t)pos * POS_ROWS)[lane];
+      a2_active_parts(m16, lane, np, plist);
+    }
+    const int n_steps = A2_NT * np;
     mbar_wait(kv_full, 0);
 
     // S[step & 1] = Q(tile) K(part)^T ; the first QK of a tile waits for its Q buffer
+    // (tile, part index) are advanced incrementally: np is a per-CTA runtime value and a division by it in these loops
+    // cost 10 % of the kernel
+    int q_tile = 0, q_pi = 0;
     auto issue_qk = [&](int step) {
-      const int tile = step / A2_NP, part = step - tile * A2_NP;
-      if (part == 0) mbar_wait(&q_full[tile & 1], (tile >> 1) & 1);
+      const int tile = q_tile, pi = q_pi;
+      if (++q_pi == np) {
+        q_pi = 0;
+        q_tile++;
+      }
+      const int part = (int)((plist >> (3 * pi)) & 7u);
+      if (pi == 0) mbar_wait(&q_full[tile & 1], (tile >> 1) & 1);
       tc_fence_after();
       if (elect_one()) {
         const uint32_t t_s = tmem_base + (step & 1) * A2_PN;
@@ -378,32 +415,38 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     };
     issue_qk(0);
     issue_qk(1);
+    int m_tile = 0, m_pi = 0;
 #pragma unroll 1
-    for (int step = 0; step < A2_STEPS; step++) {
-      const int tile = step / A2_NP, part = step - tile * A2_NP;
+    for (int step = 0; step < n_steps; step++) {
+      const int tile = m_tile, pi = m_pi;
+      if (++m_pi == np) {
+        m_pi = 0;
+        m_tile++;
+      }
+      const int part = (int)((plist >> (3 * pi)) & 7u);
       const int sb = step & 1, ob = tile & 1;
       mbar_wait(&p_full[sb], (step >> 1) & 1);     // P[sb] written (and fenced), S[sb] consumed
-      if (part == 0 && tile >= 2) mbar_wait(&o_empty[ob], 0);   // epilogue of tile-2 has read O[ob]
+      if (pi == 0 && tile >= 2) mbar_wait(&o_empty[ob], 0);     // epilogue of tile-2 has read O[ob]
       tc_fence_after();
       if (elect_one()) {
         const uint32_t t_o = tmem_base + A2_O_COL + ob * A2_NV;
         const uint32_t pa = p_lo + sb * (A2_P_BYTES >> 4);
         const uint32_t vb = v_lo + part * A2_PN;
-        if (part == 0) umma_bf16_lohi<0>(t_o, pa, q_hi, vb, v_hi, idesc_pv);
+        if (pi == 0) umma_bf16_lohi<0>(t_o, pa, q_hi, vb, v_hi, idesc_pv);
         else umma_bf16_lohi<1>(t_o, pa, q_hi, vb, v_hi, idesc_pv);
 #pragma unroll
         for (int j = 1; j < A2_PN / 16; j++)
           umma_bf16_lohi<1>(t_o, pa + 2 * j * TILE_M, q_hi, vb + 16 * j, v_hi, idesc_pv);
-        if (part == A2_NP - 1) umma_commit(&o_full[ob]);
+        if (pi == np - 1) umma_commit(&o_full[ob]);
       }
       __syncwarp();
       // the last QK of this tile completed before p_full(step): its Q buffer can take tile+2
-      if (part == A2_NP - 1 && tile + 2 < A2_NT && elect_one()) load_q(tile + 2);
+      if (pi == np - 1 && tile + 2 < A2_NT && elect_one()) load_q(tile + 2);
       __syncwarp();
       // QK(step+2) is issued AFTER PV(step): its commit (s_full) then also covers PV(step), which is
       // what allows the softmax group to overwrite P[sb] at step+2. (Issuing it earlier, as soon as S[sb]
       // had been read out, was tried: no gain, and it needs an extra P-free barrier.)
-      if (step + 2 < A2_STEPS) issue_qk(step + 2);
+      if (step + 2 < n_steps) issue_qk(step + 2);
     }
   } else {
     // =========================== softmax + epilogue warps ===========================
@@ -413,6 +456,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     if (st < POS_ROWS / 16)                                 // 400 mask bytes = 25 16-byte vectors
       reinterpret_cast<uint4*>(s_mask)[st] = reinterpret_cast<const uint4*>(p.mask + (size_t)pos * POS_ROWS)[st];
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
+    int np;
+    uint32_t plist;
+    {
+      uint4 m16 = make_uint4(0u, 0u, 0u, 0u);
+      if (lane < POS_ROWS / 16) m16 = reinterpret_cast<const uint4*>(s_mask)[lane];
+      a2_active_parts(m16, lane, np, plist);       // the same list the control warp derives from global memory
+    }
+    const int n_steps = A2_NT * np;
     // ones plane of V: 1.0 for on-board keys, 0 otherwise (row sums + key mask in one column)
     for (int r = st; r < POS_ROWS; r += 256)
       *reinterpret_cast<uint4*>(s_v + A2_DCH * A2_PLANE + r * 16) =
@@ -475,9 +526,20 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
 
     float c = 0.0f;
     int c_tile = -1, epi_done = 0;
+    int s_tile = 0, s_pi = grp;                             // (tile, part index) of `step`, advanced by two per iteration
+    while (s_pi >= np) {
+      s_pi -= np;
+      s_tile++;
+    }
 #pragma unroll 1
-    for (int step = grp; step < A2_STEPS; step += 2) {
-      const int tile = step / A2_NP;
+    for (int step = grp; step < n_steps; step += 2) {
+      const int tile = s_tile;
+      const int tile_first_step = step - s_pi;              // == tile * np
+      s_pi += 2;
+      while (s_pi >= np) {
+        s_pi -= np;
+        s_tile++;
+      }
       const int buf = tile & 1;
       if (tile != c_tile) {                                 // new tile: shift c_i of this row
         c_tile = tile;
@@ -521,7 +583,8 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
-      if (epi_done < tile && step >= tile * A2_NP + 1) {
+      // (with fewer than three parts per tile a group may not see a later step of the tile: it takes the epilogue at once)
+      if (epi_done < tile && (step >= tile_first_step + 1 || np < 3)) {
         epilogue(epi_done);
         epi_done++;
       }
