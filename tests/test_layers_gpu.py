@@ -138,3 +138,30 @@ def test_ksplit_kernel_matches_conv_gemm(built_lib, model_dir):
             assert np.abs(got - want).max() < 5e-3, float(np.abs(got - want).max())
     finally:
         ev.close()
+
+
+@pytest.mark.parametrize('size', [3, 5, 7])
+def test_small_boards_skip_key_parts(built_lib, model_dir, size):
+    """Attention skips key parts (80 padded rows) without an on-board cell: a 3x3 board lives in ONE of the five parts,
+    5x5 in two, 7x7 in three — the short step sequences (and their epilogue placement) against the torch port."""
+    import maru_b200
+    from maru_b200 import synth
+    from oracle import net_port
+    path = model_dir('b4c128')
+    arch, T = net_port.read_pack(str(path) + '.b200')
+    ev = maru_b200.Evaluator(path, gpu=0, max_batch=16)
+    try:
+        st = synth.random_states(9, size, seed=70 + size)
+        rows = ev.encode_planes(st)
+        _, want, logits = net_port.staged_forward(arch, T, rows, emulate_bf16=True)
+        got = ev.forward_states(st)
+        assert np.array_equal(got, ev.forward_states(st))
+        mask = rows[:, 32 * 361:33 * 361] > 0
+        assert mask.sum(1).max() == size * size
+        glog = ev.debug_policy_logits(len(rows))
+        logits = np.asarray(logits)
+        want = np.asarray(want)
+        assert np.abs(glog - logits)[np.repeat(mask[:, None], 2, 1)].max() < 2e-2
+        assert np.abs(got - want).max() < 1e-2
+    finally:
+        ev.close()
