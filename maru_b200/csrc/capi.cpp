@@ -1,6 +1,7 @@
 // capi.cpp — extern "C" surface of libmaru_b200.so (declared in include/maru_b200.h).
 #include "../dropin/lean_game.h"
 #include <cstring>
+#include <exception>
 #include <new>
 
 #include "engine.h"
@@ -36,7 +37,15 @@ int maru_eval_create(const char* weights_path, int gpu_id, int max_batch, unsign
     maru::set_error("out of memory");
     return 1;
   }
-  if (e->init(weights_path, gpu_id, max_batch, flags)) {
+  int rc = 1;
+  try {                                      // no C++ exception may cross the C ABI
+    rc = e->init(weights_path, gpu_id, max_batch, flags);
+  } catch (const std::exception& ex) {
+    maru::set_error(std::string("maru_eval_create: ") + ex.what());
+  } catch (...) {
+    maru::set_error("maru_eval_create: unknown exception");
+  }
+  if (rc) {
     const std::string keep = maru::g_last_error;
     delete e;
     maru::set_error(keep);
@@ -96,6 +105,10 @@ int maru_eval_forward_leaves(maru_eval* e, const maru_state* s, maru_leaf* out, 
 }
 
 int maru_eval_forward_leaves_device(maru_eval* ev, const maru_state* d_states, maru_leaf* d_out, int n) {
+  if (ev == nullptr || d_states == nullptr || d_out == nullptr || n < 0) {
+    maru::set_error("maru_eval_forward_leaves_device: bad argument");
+    return 1;
+  }
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
   CKC(cudaSetDevice(e->gpu_id));
@@ -107,6 +120,10 @@ int maru_eval_forward_leaves_device(maru_eval* ev, const maru_state* d_states, m
 }
 
 int maru_eval_forward_states_device(maru_eval* ev, const maru_state* d_states, float* d_out, int n) {
+  if (ev == nullptr || d_states == nullptr || d_out == nullptr || n < 0) {
+    maru::set_error("maru_eval_forward_states_device: bad argument");
+    return 1;
+  }
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
   CKC(cudaSetDevice(e->gpu_id));
@@ -119,6 +136,10 @@ int maru_eval_forward_states_device(maru_eval* ev, const maru_state* d_states, f
 }
 
 int maru_eval_forward_planes_device(maru_eval* ev, const float* d_in, float* d_out, int n) {
+  if (ev == nullptr || d_in == nullptr || d_out == nullptr || n < 0) {
+    maru::set_error("maru_eval_forward_planes_device: bad argument");
+    return 1;
+  }
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
   CKC(cudaSetDevice(e->gpu_id));
@@ -149,6 +170,10 @@ int maru_encode_planes(maru_eval* e, const maru_state* s, float* out_rows, int n
 }
 
 int maru_encode_planes_device(maru_eval* ev, const maru_state* d_s, float* d_rows, int n) {
+  if (ev == nullptr || d_s == nullptr || d_rows == nullptr || n < 0) {
+    maru::set_error("maru_encode_planes_device: bad argument");
+    return 1;
+  }
   Engine* e = E(ev);
   std::lock_guard<std::mutex> lock(e->mu);
   CKC(cudaSetDevice(e->gpu_id));

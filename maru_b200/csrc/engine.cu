@@ -75,6 +75,11 @@ static int load_pack(const std::string& path_in, Pack& pk) {
   fseek(f, 0, SEEK_END);
   const long sz = ftell(f);
   fseek(f, 0, SEEK_SET);
+  if (sz < (long)sizeof(PackHeader)) {
+    fclose(f);
+    set_error("short read on weight pack '" + path + "'");
+    return 1;
+  }
   pk.data.resize(sz);
   const size_t rd = fread(pk.data.data(), 1, sz, f);
   fclose(f);
@@ -96,7 +101,17 @@ static int load_pack(const std::string& path_in, Pack& pk) {
     PackEntry e;
     memcpy(&e, pk.data.data() + sizeof(PackHeader) + (size_t)i * sizeof(PackEntry), sizeof(PackEntry));
     e.name[47] = 0;
-    if (e.offset + e.nbytes > (uint64_t)sz) {
+    uint64_t count = 1;
+    bool dims_ok = e.ndim >= 1 && e.ndim <= 4 && e.dtype <= 1;
+    for (uint32_t d = 0; dims_ok && d < e.ndim; d++) {
+      if (e.dims[d] == 0 || e.dims[d] > (1u << 24)) dims_ok = false;
+      else count *= e.dims[d];
+      if (count > (1ull << 32)) dims_ok = false;
+    }
+    // overflow-safe bounds, and the byte count must be what the dims say (a truncated or crafted pack must not
+    // make upload_* read past the file image)
+    if (!dims_ok || e.offset > (uint64_t)sz || e.nbytes > (uint64_t)sz - e.offset ||
+        e.nbytes != count * (e.dtype == 1 ? 2u : 4u)) {
       set_error(std::string("corrupt weight pack entry ") + e.name);
       return 1;
     }
@@ -134,7 +149,7 @@ int Engine::upload_conv(const Pack& pk, const std::string& name, int cin, int co
     return 1;
   }
   if (w->dtype != 1 || w->ndim != 3 || (int)w->dims[0] != taps || (int)w->dims[1] != cout ||
-      (int)w->dims[2] != cin || b->dtype != 0 || (int)b->dims[0] != cout) {
+      (int)w->dims[2] != cin || b->dtype != 0 || b->ndim != 1 || (int)b->dims[0] != cout) {
     set_error("weight pack tensor " + name + " has unexpected shape");
     return 1;
   }
@@ -302,7 +317,8 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   head_dim = pk.hdr.arch[3];
   Ch = pk.hdr.arch[4];
   Cv = pk.hdr.arch[5];
-  if (C % 64 != 0 || C > 256 || (head_dim != 32 && head_dim != 64) || Ch != 32 || Cv > 128) {
+  if (blocks < 1 || blocks > 64 || C < 64 || C % 64 != 0 || C > 256 || (head_dim != 32 && head_dim != 64) || Ch != 32 ||
+      Cv < 1 || Cv > 128 || attn_every < 0 || attn_every > blocks) {
     set_error("unsupported architecture in weight pack");
     return 1;
   }
@@ -426,6 +442,7 @@ Engine::~Engine() {
     if (sl.t1) cudaEventDestroy(sl.t1);
   }
   if (h_n) cudaFreeHost(h_n);
+  for (cudaEvent_t e : prof_ev) cudaEventDestroy(e);
   if (ev0) cudaEventDestroy(ev0);
   if (ev1) cudaEventDestroy(ev1);
   if (stream) cudaStreamDestroy(stream);
@@ -605,6 +622,8 @@ void Engine::prof_end(cudaStream_t st) {
   if (prof == nullptr) return;
   cudaEventRecord(prof_ev[2 * (prof->size() - 1) + 1], st);
 }
+
+__global__ void set_live_n_kernel(int* d_n, int n) { *d_n = n; }
 
 // Holds the stream busy so that the CPU can enqueue every launch + event of the profiled forward
 // ahead of the GPU: the event deltas then measure GPU time, not API submission time.
@@ -863,21 +882,34 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
     GraphKey key{kind, bucket, d_in, d_out, flow_enabled()};
     auto it = graphs.find(key);
     if (it == graphs.end()) {
+      // The cache is keyed by the caller's buffers: a device-API caller that rotates buffers must not grow it
+      // without bound. Graphs still in flight keep running (a cudaGraphExec_t may be destroyed once launched work
+      // has been submitted only after it completes, hence the sync).
+      if (graphs.size() >= 64) {
+        CK(cudaStreamSynchronize(stream));
+        clear_graphs();
+      }
       cudaGraph_t gr = nullptr;
       cudaGraphExec_t ex = nullptr;
       CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
       const int rc = launch_all(kind, d_in, d_out, bucket, d_n, stream);
       cudaError_t ce = cudaStreamEndCapture(stream, &gr);
-      if (rc) return 1;
+      if (rc || ce != cudaSuccess) {
+        if (gr != nullptr) cudaGraphDestroy(gr);
+        if (rc) return 1;
+      }
       CK(ce);
-      CK(cudaGraphInstantiate(&ex, gr, 0));
+      const cudaError_t ie = cudaGraphInstantiate(&ex, gr, 0);
+      if (ie != cudaSuccess) cudaGraphDestroy(gr);
+      CK(ie);
       cudaGraphDestroy(gr);
       it = graphs.emplace(key, ex).first;
     }
-    // h_n is a ring of 16 pinned ints so that back-to-back async forwards do not race on it
-    int* hn = h_n + (n_seq++ & 15);
-    *hn = n;
-    CK(cudaMemcpyAsync(d_n, hn, sizeof(int), cudaMemcpyHostToDevice, stream));
+    // The live batch size travels BY VALUE as a kernel parameter (fixed at enqueue time): any number of forwards
+    // with different n may be in flight on the stream. (A pinned staging int read by an async copy at execution
+    // time was overwritten by later calls once more than a handful of forwards were outstanding.)
+    set_live_n_kernel<<<1, 1, 0, stream>>>(d_n, n);
+    CK(cudaGetLastError());
     CK(cudaGraphLaunch(it->second, stream));
   }
   n_forward++;

@@ -227,6 +227,7 @@ static int queue_execute(maru_queue* q, int kind, const void* in, void* out, int
   {
     std::lock_guard<std::mutex> l(w->mu);
     if (w->stop) {
+      w->reserved = w->reserved - n > 0 ? w->reserved - n : 0;   // undo the reservation of this job
       set_error("maru_queue is shutting down");
       return 1;
     }

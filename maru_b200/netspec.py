@@ -190,11 +190,41 @@ def randomize_(net: nn.Module, seed: int = 0) -> nn.Module:
     return net
 
 
+# input planes that carry a "recent move" (Appendix A of SURVEY.md: 24-26 opponent's newest three moves,
+# 11-13 the mover's) and the prior (in logit units) a peaked test policy gives their cells
+PEAKED_PRIOR = ((24, 1.0), (11, 0.72), (25, 0.52), (12, 0.37), (26, 0.25), (13, 0.15))
+
+
+def sharpen_policy_(net: MaruNet, scale: float = 0.5) -> MaruNet:
+    """Turn the near-uniform policy of a random-init net (logit sigma ~0.02-0.1: argmax decided by bf16
+    round-off) into a PEAKED one, the way a trained net's policy is, without training: one trunk channel
+    is wired to carry `sum_p A_p * plane_p` from the stem's centre tap through the residual stream, one
+    head feature reads it, and policy planes 0/1 read that feature. Every other weight stays random, so the
+    signal travels through (and is perturbed by) every layer of the trunk, attention included.
+    Used by the parity tests that gate top-1 agreement on ALL positions (north_star: >= 99 %)."""
+    with torch.no_grad():
+        k = net.stem_conv.out_channels - 1                 # trunk channel that carries the prior
+        j = net.heads.g.conv.out_channels - 1              # head feature that reads it
+        bn = net.stem_bn
+        s_k = float(bn.weight[k] / torch.sqrt(bn.running_var[k] + BN_EPS))
+        for plane, amp in PEAKED_PRIOR:
+            net.stem_conv.weight[k, plane, 1, 1] += 4.0 * amp / s_k      # +4*amp on h[k] at that cell
+        gb = net.heads.g.bn
+        s_j = float(gb.weight[j] / torch.sqrt(gb.running_var[j] + BN_EPS))
+        net.heads.g.conv.weight[j].zero_()
+        net.heads.g.conv.weight[j, k, 0, 0] = 1.0 / s_j                   # g[j] = relu(h[k]) once BN is folded
+        gb.bias[j] = gb.running_mean[j] * s_j
+        net.heads.planes.weight[0:2, j, 0, 0] += 0.25 * scale             # logit ~ amp * scale
+    return net
+
+
 def build(blocks: int = 4, channels: int = 128, attn_every: int = 2, head_dim: int = 32,
-          head_channels: int = 32, value_channels: int = 64, seed: int = 0) -> MaruNet:
+          head_channels: int = 32, value_channels: int = 64, seed: int = 0, peaked: bool = False) -> MaruNet:
     torch.manual_seed(seed)
     net = MaruNet(blocks, channels, attn_every, head_dim, head_channels, value_channels)
     randomize_(net, seed)
+    if peaked:
+        sharpen_policy_(net)
     return net.eval()
 
 

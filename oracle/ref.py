@@ -282,7 +282,7 @@ def random_playout(width: int, height: int, n_moves: int, rng: np.random.Generat
 
 
 def make_positions(n: int, size: int | Tuple[int, int] = 19, seed: int = 0, komi: float = 7.5,
-                   with_mask: bool = False, max_fill: float = 0.6):
+                   with_mask: bool = False, max_fill: float = 0.6, min_moves: int = 0):
     """n seeded positions -> (rows [n,11920] fp32 from Board::getInputs, states [n,448] uint8,
     meta list). Move counts ~U[0, max_fill*w*h]; komi/rule/superko varied deterministically."""
     w, h = (size, size) if isinstance(size, int) else size
@@ -291,8 +291,8 @@ def make_positions(n: int, size: int | Tuple[int, int] = 19, seed: int = 0, komi
     states = np.zeros((n, STATE_SIZE), np.uint8)
     meta = []
     for i in range(n):
-        moves = int(rng.integers(0, int(max_fill * w * h) + 1))
-        b, color = random_playout(w, h, moves, rng)
+        moves = int(rng.integers(min_moves, int(max_fill * w * h) + 1))
+        b, color = random_playout(w, h, moves, rng, pass_prob=0.03 if min_moves == 0 else 0.0)
         rule = RULE_JP if (i % 5 == 4) else (RULE_COM if i % 7 == 6 else RULE_CH)
         superko = (i % 3 == 2)
         k = komi if i % 4 else float(rng.choice([0.5, 5.5, 6.5, 7.5, -7.5, 0.0]))

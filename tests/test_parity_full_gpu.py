@@ -1,0 +1,88 @@
+"""GPU: the BENCHMARKED paths against the reference runtime at BASELINE.json's batch sizes.
+
+  * b4c128 @ batch 256 on 19x19 — the persistent multi-layer conv kernels (conv_flow.cu) are live:
+    the test asserts the 7-launch forward bench.py times — and full batches of 13x13 and 9x9;
+  * b10c256 @ batch 512 on 19x19 (conv_pair / conv_wide / conv_ksplit), 13x13 and 9x9 at 256.
+
+Oracle = deepgo::Processor::execute -> Executor -> Model::forward on libtorch CPU fp32
+(reference src/deepgo/native/cpp/Processor.cpp:36-60, Model.cpp:88-100; oracle/_ref, built from the
+reference's own sources) on the SAME legal positions (random playouts on the reference Board) and the
+same TorchScript file.  All three north_star gates, on EVERY position:
+  policy logits max-abs <= 2e-2 (centred log-probabilities over the on-board cells), value <= 1e-2,
+  top move agreement >= 99 %.
+The model is random-init with a PEAKED policy (netspec.sharpen_policy_: recent-move planes wired
+through the whole trunk to the policy planes) — a plain random-init net has logit sigma ~0.02, its
+argmax is decided by round-off in ANY reduced-precision path, which is why the
+random-init tests in test_parity_gpu.py can only gate top-1 on clear-gap positions.
+"""
+import numpy as np
+import pytest
+
+from test_convert import centered_log_policy
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 2e-2
+VALUE_TOL = 1e-2
+TOP1_MIN = 0.99
+
+
+@pytest.fixture(scope='module')
+def peaked_models(tmp_path_factory):
+    from maru_b200 import convert, netspec
+    d = tmp_path_factory.mktemp('peaked')
+    made = {}
+
+    def get(name):
+        if name not in made:
+            p = d / f'{name}-peaked.model'
+            netspec.export(netspec.build(**netspec.CONFIGS[name], seed=0, peaked=True), str(p))
+            convert.convert(str(p))
+            made[name] = p
+        return made[name]
+    return get
+
+
+def gates(out, want, rows, what):
+    mask = rows[:, 32 * 361:33 * 361] > 0
+    assert np.all(out[:, :361][~mask] == 0)
+    dl = np.abs(centered_log_policy(out, rows) - centered_log_policy(want, rows)).max()
+    dv = np.abs(out[:, 2166] - want[:, 2166]).max()
+    dplanes = np.abs(out[:, 361:2166] - want[:, 361:2166]).max()
+    agree = out[:, :361].argmax(1) == want[:, :361].argmax(1)
+    lp = np.where(mask, np.log(np.maximum(want[:, :361], 1e-30)), -1e9)
+    srt = np.sort(lp, axis=1)
+    print(f'{what}: n={len(rows)} logit maxabs={dl:.3g} value maxabs={dv:.3g} planes maxabs={dplanes:.3g} '
+          f'top1={agree.mean():.4f} (ALL positions; reference top-2 gap 1%/50% quantile '
+          f'{np.quantile(srt[:, -1] - srt[:, -2], 0.01):.3g}/{np.median(srt[:, -1] - srt[:, -2]):.3g})')
+    assert dl <= LOGIT_TOL, what
+    assert dv <= VALUE_TOL, what
+    assert dplanes <= VALUE_TOL, what
+    assert agree.mean() >= TOP1_MIN, what
+
+
+@pytest.mark.parametrize('name,cases', [
+    ('b4c128', ((19, 256, 7), (13, 256, None), (9, 256, None))),
+    ('b10c256', ((19, 512, None), (13, 256, None), (9, 256, None))),
+])
+def test_benchmarked_path_vs_reference_runtime(built_lib, peaked_models, name, cases):
+    import maru_b200
+    from oracle import ref
+    if not ref.available('nn'):
+        pytest.skip('oracle/_ref nn not present')
+    path = peaked_models(name)
+    proc = ref.RefProcessor(str(path), gpus=[-1], batch_size=512, deterministic=True)
+    ev = maru_b200.Evaluator(path, gpu=0, max_batch=max(c[1] for c in cases))
+    try:
+        for size, n, launches in cases:
+            rows, states, _ = ref.make_positions(n, size, seed=900 + size, min_moves=4)
+            got = ev.forward_states(states)                   # ONE forward of the full batch
+            if launches is not None:                          # the path bench.py's `value` times
+                assert ev.info().launches_per_forward == launches
+            want = proc.execute(rows)
+            gates(got, want, rows, f'{name}/{size}x{size}/batch {n}')
+            # the reference's own contract (fp32 planes in) runs the same kernels after ingest
+            assert np.array_equal(ev.forward(rows[:64]), ev.forward_states(states[:64]))
+    finally:
+        ev.close()
+        proc.close()

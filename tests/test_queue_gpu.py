@@ -79,3 +79,37 @@ def test_queue_on_the_flow_kernels(built_lib, model_dir):
         assert proc.queue.stats().batches >= 3
     finally:
         proc.close()
+
+
+def test_many_outstanding_device_forwards_with_varying_n(built_lib, model_dir):
+    """More than 16 forwards of DIFFERENT live batch sizes enqueued on the stream without a sync: the live n of a
+    graph replay travels by value (a ring of 16 pinned ints once let a later call overwrite an earlier one's n,
+    which silently left rows uncomputed)."""
+    import torch
+    import maru_b200
+    path = model_dir('b2c64')
+    rows, states = load_positions('19')
+    states = np.concatenate([states] * 4)[:8 * 22 + 3]          # 23 chunks of max_batch 8, the last one of 3
+    ev = maru_b200.Evaluator(path, gpu=0, max_batch=8)
+    try:
+        want = ev.forward_states(states)                        # blocking, chunk by chunk
+        d_states = torch.from_numpy(states).cuda()
+        d_out = torch.zeros((len(states), maru_b200.OUTPUT_SIZE), dtype=torch.float32, device='cuda')
+        torch.cuda.synchronize()
+        # ragged sizes back to back, all asynchronous: 5, 8, 1, 7, ... (each call is its own graph replay)
+        off = 0
+        sizes = []
+        while off < len(states):
+            m = min([5, 8, 1, 7, 3, 8, 2][len(sizes) % 7], len(states) - off)
+            ev.forward_states_device(d_states[off:].data_ptr(), d_out[off:].data_ptr(), m)
+            sizes.append(m)
+            off += m
+        assert len(sizes) > 16
+        ev.sync()
+        assert np.array_equal(d_out.cpu().numpy(), want)
+        d_out.zero_()
+        ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), len(states))   # one call, 23 chunks inside
+        ev.sync()
+        assert np.array_equal(d_out.cpu().numpy(), want)
+    finally:
+        ev.close()
