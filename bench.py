@@ -17,6 +17,13 @@ independent: weak scaling, no data-path collective; NCCL only reduces the timing
   roofline     : dominant kernel (3x3 implicit-GEMM conv) algorithmic FLOPs / CUDA-event duration,
                  against the measured bf16 peak of MEASURED_PEAKS.json
   cpu_baseline : the reference runtime (deepgo::Processor on libtorch CPU) on a bounded sample
+  sustained    : the same device-resident forward back to back for >= 2 s, with its own clock record
+  gpu_reference: (N = 1) the UNMODIFIED reference runtime on libtorch CUDA on the same B200, fp32 / fp16
+  selfplay     : the second half of the BASELINE metric, run by EVERY rank: self-play visits/s of the
+                 native search + game scheduler (maru_selfplay_*: many games per host thread, leaves
+                 submitted asynchronously in batches to this rank's leaf queue), games sharded by rank,
+                 visits summed over ranks / slowest rank's time.  Reference arm: G reference Players
+                 (deepgo::Player, unmodified) on the libtorch CPU Processor, same schedule.
 """
 from __future__ import annotations
 
@@ -48,15 +55,47 @@ def parse():
     ap.add_argument('--batch', type=int, default=256)
     ap.add_argument('--board', type=int, default=19)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-selfplay', action='store_true')
+    ap.add_argument('--no-gpu-reference', action='store_true')
+    ap.add_argument('--sustained-s', type=float, default=2.0)
+    ap.add_argument('--sp-board', type=int, default=19)
+    ap.add_argument('--sp-visits', type=int, default=50, help='descents per move (reference default --visits 50)')
+    ap.add_argument('--sp-moves', type=int, default=4, help='timed moves per game (after 1 untimed move)')
+    ap.add_argument('--sp-games-per-thread', type=int, default=64)
+    ap.add_argument('--sp-opening', type=int, default=-1, help='random opening moves (-1: board*board/6)')
+    ap.add_argument('--sp-root', default='pucb', choices=['pucb', 'gumbel'])
+    ap.add_argument('--sp-threads', type=int, default=0, help='search threads per rank (0: this rank\'s cores - 1)')
     return ap.parse_args()
 
 
 def base_config(args, world: int) -> dict:
-    """Workload description shared verbatim by both arms."""
+    """Workload description shared verbatim by both arms (identical keys and values)."""
+    if (args.model, args.board, args.batch) == ('b4c128', 19, 256):
+        which = ' (BASELINE.json configs[1])'
+    elif args.model == 'b10c256' and args.board == 19 and args.batch in (512, 1024, 2048):
+        which = ' (BASELINE.json configs[2])'
+    else:
+        which = ' (not a BASELINE.json config: builder-chosen variant)'
     return dict(workload=f'{args.model} random-init (seed 0), {args.board}x{args.board} leaf evaluation, '
-                         f'batch {args.batch} per GPU (BASELINE.json configs[1])',
+                         f'batch {args.batch} per GPU{which}',
                 model=args.model, board=args.board, batch_per_gpu=args.batch,
                 parallelism=f'replica x{world}')
+
+
+def selfplay_config(args) -> dict:
+    opening = args.sp_opening if args.sp_opening >= 0 else args.sp_board * args.sp_board // 6
+    return dict(board=args.sp_board, visits_per_move=args.sp_visits, timed_moves_per_game=args.sp_moves,
+                warmup_moves_per_game=1, opening_moves=opening, root=args.sp_root, model=args.model,
+                workload=f'{args.sp_board}x{args.sp_board} self-play, {args.sp_root} root, {args.sp_visits} descents per '
+                         f'move on top of the inherited subtree, games sharded by rank (BASELINE.json configs[{3 if args.sp_root == "gumbel" else 4}])')
+
+
+def rank_cpus(local: int) -> list:
+    """This rank's share of the host cores: the process's affinity mask split evenly over the local ranks."""
+    cpus = sorted(os.sched_getaffinity(0))
+    nlocal = int(os.environ.get('LOCAL_WORLD_SIZE', os.environ.get('WORLD_SIZE', '1')))
+    per = max(1, len(cpus) // max(1, nlocal))
+    return cpus[(local % max(1, nlocal)) * per:(local % max(1, nlocal)) * per + per] or cpus
 
 
 def model_files(name: str):
@@ -157,25 +196,91 @@ class ClockSampler:
                     reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_reference_evals_per_sec(model_path: Path, rows: np.ndarray, budget_s: float = 20.0):
+def time_reference_cpu(model_path: Path, rows: np.ndarray, steps: int, warmup: int, budget_s: float):
     """The reference's own path on the host cores: deepgo::Processor::execute -> Executor ->
-    Model::forward (libtorch CPU fp32), built unmodified into oracle/_ref."""
+    Model::forward (libtorch CPU fp32), built unmodified into oracle/_ref.  ONE procedure for the
+    reference arm and for the b200 arm's cpu_baseline leg: a step is `sample` positions of the batch, sized
+    from a 16-row probe so that warmup + steps fit the budget; `warmup` untimed steps, then `steps` timed."""
     import torch
     from oracle import ref
     torch.set_num_threads(os.cpu_count() or 1)
     proc = ref.RefProcessor(str(model_path), gpus=[-1], batch_size=len(rows))
-    n = min(len(rows), 32)
+    proc.execute(rows[:16])                                    # first call: allocator / oneDNN primitive cache
     t0 = time.perf_counter()
-    proc.execute(rows[:n])                                     # warm-up + cost estimate
-    per_row = (time.perf_counter() - t0) / n
-    n = int(max(16, min(len(rows), budget_s / 2 / max(per_row, 1e-6))))
-    reps = 2
+    proc.execute(rows[:16])
+    per_row = (time.perf_counter() - t0) / 16
+    sample = int(max(8, min(len(rows), budget_s / (steps + warmup) / max(per_row, 1e-6))))
+    for _ in range(warmup):
+        proc.execute(rows[:sample])
     t0 = time.perf_counter()
-    for _ in range(reps):
-        proc.execute(rows[:n])
+    for _ in range(steps):
+        proc.execute(rows[:sample])
     dt = time.perf_counter() - t0
     proc.close()
-    return n * reps / dt, n, reps, torch.get_num_threads()
+    return sample * steps / dt, sample, dt, torch.get_num_threads()
+
+
+def reference_selfplay(args, model_path: Path, budget_s: float = 40.0):
+    """Self-play visits/s of the UNMODIFIED reference: G deepgo::Player objects (Player.cpp, Node.cpp; each
+    with its own search thread pool) over ONE deepgo::Processor on libtorch CPU, driven by the same schedule
+    as the native scheduler (maru_b200.selfplay.SelfPlayScheduler).  Bounded sample: few games, 1 + 1 moves."""
+    import torch
+    from maru_b200 import selfplay
+    from oracle import ref
+    cfg = selfplay_config(args)
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
+    games, threads = 8, 2
+    proc = ref.RefProcessor(str(model_path), gpus=[-1], batch_size=games * threads)
+    made = []
+
+    class Opened:
+        def __init__(self, g):
+            self.p = ref.RefPlayer(proc, threads, args.sp_board, args.sp_board)
+            self.g, self.ready = g, False
+
+        def initialize(self):
+            if self.ready:
+                return
+            self.ready = True
+            self.p.initialize()
+            rng = np.random.default_rng(1000 + self.g)
+            b = ref.RefBoard(args.sp_board, args.sp_board)
+            color = ref.BLACK
+            for _ in range(cfg['opening_moves']):
+                en = np.flatnonzero(b.get_enableds(color, True))
+                if len(en) == 0:
+                    break
+                i = int(rng.choice(en))
+                b.play(i % args.sp_board, i // args.sp_board, color)
+                self.p.play(i % args.sp_board, i // args.sp_board)
+                color = -color
+
+        def evaluate(self, **kw):
+            return self.p.evaluate(**kw)
+
+        def play(self, x, y):
+            return self.p.play(x, y)
+
+    def make(g):
+        made.append(Opened(g))
+        return made[-1]
+    # probe the cost of one move with 2 games, then size the sample
+    moves = 2
+    sched = selfplay.SelfPlayScheduler(make, games, args.sp_visits, max_moves=moves, root=args.sp_root, width=16,
+                                       noise=1.0 if args.sp_root == 'gumbel' else 0.0, criterion='lcb')
+    for pl in sched.players:
+        pl.initialize()
+    t0 = time.perf_counter()
+    st = sched.run()
+    dt = time.perf_counter() - t0
+    for pl in made:
+        pl.p.close()
+    proc.close()
+    return dict(value=st.visits / dt, unit='visits/s', visits=st.visits, wall_s=dt, games=games,
+                threads_per_game=threads, moves_per_game=moves, cores=os.cpu_count(),
+                torch_threads=torch.get_num_threads(),
+                impl='deepgo::Player x %d over deepgo::Processor on libtorch CPU fp32 (oracle/_ref, unmodified)' % games,
+                config=cfg)
 
 
 def rows_from_states(states: np.ndarray) -> np.ndarray:
@@ -199,31 +304,114 @@ def run_reference(args):
     model_path, _ = model_files(args.model)
     states = synth.random_states(args.batch, args.board, seed=1234)
     rows = rows_from_states(states)
-    import torch
-    from oracle import ref
-    torch.set_num_threads(os.cpu_count() or 1)
-    proc = ref.RefProcessor(str(model_path), gpus=[-1], batch_size=args.batch)
-    t0 = time.perf_counter()
-    proc.execute(rows[:16])
-    per_row = (time.perf_counter() - t0) / 16
-    total = args.steps + args.warmup
-    sample = int(max(8, min(args.batch, 150.0 / total / max(per_row, 1e-6))))
-    for _ in range(args.warmup):
-        proc.execute(rows[:sample])
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        proc.execute(rows[:sample])
-    dt = time.perf_counter() - t0
-    value = sample * args.steps / dt
+    value, sample, dt, cores = time_reference_cpu(model_path, rows, args.steps, args.warmup, budget_s=150.0)
+    sp = None
+    if not args.no_selfplay:
+        try:
+            sp = reference_selfplay(args, model_path)
+        except Exception as exc:
+            sp = dict(value=None, unit='visits/s', error=str(exc))
     line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                 warmup=args.warmup, ms_per_step=dt / args.steps * 1e3, higher_is_better=True,
                 scaling='weak', vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
                 config=base_config(args, args.gpus),
-                cpu_baseline=dict(value=value, unit=UNIT, cores=torch.get_num_threads(), kind='reference',
+                cpu_baseline=dict(value=value, unit=UNIT, cores=cores, kind='reference',
                                   sample=f'{sample} of the {args.batch} positions per step through '
                                          'deepgo::Processor::execute (libtorch CPU fp32, oracle/_ref)'),
-                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+                e2e=dict(value=value, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
+                note='one host\'s CPU cores: this arm does not grow with --gpus (rank 0 alone runs it)',
+                selfplay=sp)
     print(json.dumps(line), flush=True)
+
+
+def gpu_reference_leg(model_path: Path, rows: np.ndarray, ours: np.ndarray, B: int, reps: int = 20) -> dict:
+    """Same-box GPU bar (SURVEY 8d): deepgo::Processor -> Executor -> Model::forward on libtorch CUDA
+    (oracle/_ref, unmodified), fp32 and fp16, on the reference's own contract (fp32 rows on the host)."""
+    from oracle import ref
+    out = {}
+    mask = rows[:, 32 * 361:33 * 361] > 0
+
+    def cl(o):
+        lp = np.where(mask, np.log(np.maximum(o[:, :361], 1e-30)), 0.0)
+        return np.where(mask, lp - (lp.sum(1) / mask.sum(1))[:, None], 0.0)
+    for fp16 in (False, True):
+        proc = ref.RefProcessor(str(model_path), gpus=[0], batch_size=B, fp16=fp16, deterministic=False)
+        for _ in range(5):                         # cudnn.benchmark tunes on the first calls of a batch size
+            got = proc.execute(rows)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            got = proc.execute(rows)
+        dt = (time.perf_counter() - t0) / reps
+        proc.close()
+        out['fp16' if fp16 else 'fp32'] = dict(
+            value=B / dt, unit=UNIT, ms_per_step=dt * 1e3,
+            logit_maxabs_vs_b200=float(np.abs(cl(got) - cl(ours)).max()),
+            value_maxabs_vs_b200=float(np.abs(got[:, 2166] - ours[:, 2166]).max()))
+    out['api'] = ('deepgo::Processor::execute on libtorch CUDA (oracle/_ref), host fp32 rows in / out: compare with '
+                  'e2e.planes (the same contract through maru_eval_forward_planes)')
+    return out
+
+
+def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist, dev) -> dict:
+    """Self-play visits/s of the native scheduler on this rank's GPU; whole job = sum of visits over ranks /
+    slowest rank's wall time (barrier + synchronize on both sides)."""
+    import torch
+    import maru_b200
+    from maru_b200 import selfplay
+    cfg = selfplay_config(args)
+    cpus = rank_cpus(local)
+    threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus) - 1)
+    games = threads * args.sp_games_per_thread
+    ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=1024)
+    q = maru_b200.LeafQueue([ev], batch_size=1024)
+    sp = selfplay.NativeSelfPlay(q, games=games, size=args.sp_board, visits=args.sp_visits, threads=threads,
+                                 max_moves=10 ** 6, root=args.sp_root, width=16,
+                                 noise=1.0 if args.sp_root == 'gumbel' else 0.0, criterion='lcb',
+                                 opening_moves=cfg['opening_moves'], restart=True, seed=1000 + rank,
+                                 cpus=cpus[:threads])
+
+    def sync_all():
+        torch.cuda.synchronize(dev)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+    sp.run(1)                                                     # untimed: first move of every game
+    s0, q0 = sp.stats(), q.stats()
+    v0, e0, h0, st0, sub0 = s0.visits, s0.evals, s0.host_s, s0.stall_s, s0.submits
+    b0, p0, d0 = q0.batches, q0.positions, q0.device_ms_total
+    sync_all()
+    with ClockSampler(local) as clocks:
+        t0 = time.perf_counter()
+        sp.run(args.sp_moves)
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        sync_all()
+    s1, q1 = sp.stats(), q.stats()
+    mine = dict(visits=s1.visits - v0, evals=s1.evals - e0, wall_s=dt, host_s=s1.host_s - h0,
+                stall_s=s1.stall_s - st0, submits=s1.submits - sub0, batches=q1.batches - b0,
+                positions=q1.positions - p0, device_ms=q1.device_ms_total - d0, max_batch=q1.max_batch_seen)
+    sp.close()
+    q.close()
+    ev.close()
+    sums = torch.tensor([mine['visits'], mine['evals'], mine['batches'], mine['positions'], mine['host_s'],
+                         mine['stall_s'], mine['device_ms']], dtype=torch.float64, device=dev)
+    mx = torch.tensor([dt, float(mine['max_batch'])], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    visits, evals, batches, positions, host_s, stall_s, device_ms = [float(x) for x in sums.tolist()]
+    wall = float(mx[0].item())
+    gpu_busy = device_ms / 1e3 / (wall * world)
+    host_busy = host_s / (wall * world * threads)
+    return dict(metric='selfplay_visits_per_sec', value=visits / wall, unit='visits/s', n_gpus=world,
+                evals_per_sec=evals / wall, visits=int(visits), wall_s=wall, games_per_gpu=games,
+                search_threads_per_gpu=threads, host_cores_per_gpu=len(cpus),
+                mean_batch=positions / max(batches, 1.0), max_batch=int(mx[1].item()),
+                host_us_per_visit=host_s / max(visits, 1.0) * 1e6,
+                gpu_busy_frac=gpu_busy, host_busy_frac=host_busy, stall_frac=stall_s / (wall * world * threads),
+                limiter='host cores (search threads busy, GPU mostly idle)' if gpu_busy < 0.6 else 'GPU',
+                clocks=clocks.summary(), config=cfg,
+                impl='maru_selfplay_* (native search, one descent in flight per game, asynchronous leaf batches)')
 
 
 def run_b200(args):
@@ -290,6 +478,26 @@ def run_b200(args):
     dev_ms = float(sum(step_ms))
     clock = clocks.summary()
 
+    # ---------------- sustained: the same forward back to back for >= 2 s (no L2 flush: one forward streams
+    # ~160 MB of activations through the 126 MB L2 anyway), its own clock record ---------------------
+    sustained = None
+    if args.sustained_s > 0:
+        n_sus = max(args.steps, int(args.sustained_s * 1e3 / max(dev_ms / args.steps, 1e-3)) + 1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        with ClockSampler(local) as clocks_sus:
+            with torch.cuda.stream(stream):
+                e0.record(stream)
+            for _ in range(n_sus):
+                ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), B)
+            with torch.cuda.stream(stream):
+                e1.record(stream)
+            sync_all()
+        sus_ms = e0.elapsed_time(e1)
+        sustained = dict(forwards=n_sus, seconds=sus_ms / 1e3, ms_per_step=sus_ms / n_sus,
+                         value_per_gpu=B * n_sus / (sus_ms / 1e3), clocks=clocks_sus.summary(),
+                         l2='not flushed (back-to-back forwards)')
+
     # ---------------- e2e: blocking C-ABI call on host buffers -----------------------------------
     lib = ev.lib
     for _ in range(3):
@@ -351,6 +559,22 @@ def run_b200(args):
         if acc['launches']:
             per_layer = acc
 
+    ours_rows = h_out.numpy().copy()            # outputs of the plane contract (last e2e leg), for gpu_reference
+    ev.close()                                  # the legs below create their own evaluators (one engine per device)
+
+    # ---------------- gpu_reference: the unmodified reference on libtorch CUDA, same box (N = 1) -------
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_reference:
+        try:
+            gpu_ref = gpu_reference_leg(model_path, h_rows.numpy(), ours_rows, B)
+        except Exception as exc:
+            gpu_ref = dict(error=str(exc))
+
+    # ---------------- selfplay: every rank plays its shard of the games ---------------------------------
+    sp_block = None
+    if not args.no_selfplay:
+        sp_block = selfplay_leg(args, model_path, rank, local, world, dist, dev)
+
     # ---------------- reduce over ranks ----------------------------------------------------------
     from maru_b200 import shard
     agg = shard.reduce_stats(shard.RankStats(positions=B * args.steps, batches=args.steps,
@@ -385,7 +609,9 @@ def run_b200(args):
         traffic = None
         try:  # dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed ncu capture
             if dom_key[0] == 5:
-                cap = json.loads((ROOT / 'profiles' / 'r1_conv_flow_ncu_full.json').read_text())
+                capf = next(f for f in ('r2_conv_flow_ncu_full.json', 'r1_conv_flow_ncu_full.json')
+                            if (ROOT / 'profiles' / f).exists())
+                cap = json.loads((ROOT / 'profiles' / capf).read_text())
                 traffic = cap['_traffic_bytes_per_launch'][dom['name'].split('[')[0]]
             else:
                 cap = json.loads((ROOT / 'profiles' / 'r1_conv3x3_ncu_full.json').read_text())
@@ -404,15 +630,18 @@ def run_b200(args):
                             frac=per_layer['flops'] / (per_layer['ms'] / 1e3) / 1e12 / peaks['bf16_burst'],
                             us_per_launch=per_layer['ms'] / per_layer['launches'] * 1e3,
                             note='same 3x3 C/2->C/2 layer timed alone on the one-launch-per-layer path (debug bit 5)')),
-                        whole_net_tflops=value * info.flops_per_eval / 1e12,
-                        whole_net_frac_of_sustained=value * info.flops_per_eval / 1e12 / peaks['bf16_sustained'])
+                        traffic_source='profiles/ ncu --set full capture of this kernel (dram__bytes_read.sum + '
+                                       'dram__bytes_write.sum per launch); not re-measured in this run',
+                        whole_net_tflops_per_gpu=value / world * info.flops_per_eval / 1e12,
+                        whole_net_frac_of_burst_per_gpu=value / world * info.flops_per_eval / 1e12 / peaks['bf16_burst'],
+                        whole_net_frac_of_sustained_per_gpu=value / world * info.flops_per_eval / 1e12 / peaks['bf16_sustained'])
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             try:
                 rows = h_rows.numpy()
-                v, n, reps, cores = cpu_reference_evals_per_sec(model_path, rows)
+                v, n, dt_cpu, cores = time_reference_cpu(model_path, rows, steps=3, warmup=1, budget_s=20.0)
                 cpu = dict(value=v, unit=UNIT, cores=cores, kind='reference',
-                           sample=f'{reps} x {n} of the step\'s {B} positions through '
+                           sample=f'3 timed steps (1 warm-up) of {n} of the step\'s {B} positions through '
                                   'deepgo::Processor::execute (libtorch CPU fp32, oracle/_ref)')
             except Exception as exc:  # the oracle always exists; report instead of hiding
                 cpu = dict(value=None, unit=UNIT, cores=os.cpu_count(), kind='reference',
@@ -421,9 +650,9 @@ def run_b200(args):
             metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
             ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling='weak', vs_baseline=None,
             dtype='bf16', data='synthetic', impl='b200',
-            config=dict(base_config(args, world), l2='flushed between steps (256 MiB write)',
-                        launches_per_step=info.launches_per_forward, flops_per_eval=info.flops_per_eval,
-                        flops_per_eval_executed=info.flops_per_eval_executed),
+            config=base_config(args, world),
+            details=dict(l2='flushed between steps (256 MiB write)', launches_per_step=info.launches_per_forward,
+                         flops_per_eval=info.flops_per_eval, flops_per_eval_executed=info.flops_per_eval_executed),
             e2e=dict(value=total / e2e_leaf_s, unit=UNIT, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
                      d2h_bytes_per_step=B * maru_b200.LEAF_SIZE * 4,
                      api='maru_eval_forward_leaves (blocking, pinned host buffers): compact records in, '
@@ -436,9 +665,9 @@ def run_b200(args):
                                  api='maru_eval_forward_planes (reference Model::forward contract)')),
             gpu_launches=info.launches_per_forward * args.steps,
             clocks=clock, roofline=roofline, cpu_baseline=cpu, kernels=table,
-            wall_ms_per_step=t_wall / args.steps * 1e3)
+            wall_ms_per_step=t_wall / args.steps * 1e3, sustained=sustained,
+            gpu_reference=gpu_ref, selfplay=sp_block)
         print(json.dumps(line), flush=True)
-    ev.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -219,6 +219,24 @@ typedef struct maru_queue_stats {
 } maru_queue_stats;
 int  maru_queue_get_stats(maru_queue* q, maru_queue_stats* st);
 
+/* Asynchronous variant (SURVEY 8b "async variant submit/poll for the new leaf queue"): the reference
+ * parks every search thread on a per-job mutex + condition variable inside Processor::execute
+ * (ExecutorJob.cpp:8-36); here a caller hands over a whole batch of leaves, keeps working, and
+ * collects the result later.  `s` and `out` must stay valid until the ticket is retired.
+ * submit: routed and batched exactly like maru_queue_execute_leaves (least-loaded evaluator, jobs never
+ * split).  poll: *done = 1 once the results are in `out` (non-blocking; the ticket stays valid).
+ * wait: blocks until done, returns the job's rc and RETIRES the ticket (every ticket must be waited on
+ * exactly once). */
+typedef struct maru_ticket maru_ticket;
+int  maru_queue_submit_leaves(maru_queue* q, const maru_state* s, maru_leaf* out, int n, maru_ticket** t);
+int  maru_queue_poll(maru_queue* q, maru_ticket* t, int* done);
+int  maru_queue_wait(maru_queue* q, maru_ticket* t);
+/* Batch forming when the evaluator is idle: the reference (and the default here) launches whatever is
+ * queued the moment one job arrives (Executor.cpp:108-124).  With min_rows > 0 an idle worker waits up
+ * to max_wait_us for at least min_rows queued rows first, so many small submitters still form batches
+ * the tensor-core kernels are efficient at.  min_rows = 0 restores the default. */
+int  maru_queue_set_coalesce(maru_queue* q, int min_rows, int max_wait_us);
+
 /* ---- host-side helper: exact ladder flags without the reference's Board copies ------------------ */
 /* colors: [height*width] raster, 0 empty / +1 black / -1 white. (ko_x, ko_y, ko_color): the point the
  * side ko_color may not retake (Board::_koIndex/_koColor, Board.cpp:140-205), or ko_x < 0 for none.
@@ -245,6 +263,74 @@ void maru_game_destroy(maru_game* g);
 int  maru_game_play(maru_game* g, int x, int y, int color);      /* captured stones, 0 = pass, -1 = illegal */
 int  maru_game_state(const maru_game* g, int color, float komi, int rule, int superko, int with_move_mask,
                      maru_state* out);
+
+/* ---- native search + self-play game scheduler (rows a10 / f1) -------------------------------- */
+/* Many concurrent games per host thread over the flat board: the reference's tree policy
+ * (Node::evaluate, Node.cpp:71-225; Player::_evaluate / play / getCandidates, Player.cpp:93-115,
+ * 229-261, 319-368) as a resumable state machine per game (maru_b200/csrc/search.h) — one descent in
+ * flight per game (the reference's threads = 1), leaves of all games of a worker submitted as ONE
+ * asynchronous batch (maru_queue_submit_leaves), two batches per worker in flight so host work and GPU
+ * overlap.  Move decision = the reference's Python driver (player.py:295-366: search, candidates,
+ * LCB / visits criterion, pass when nothing is legal), optionally with a Gumbel sequential-halving
+ * root over the reference's equally / width / noise hooks (Node.cpp:99-140, 191-210).
+ * `visits` is the number of descents made for every move ON TOP of the subtree the new root
+ * inherited (target = inherited root visits + visits; Player.cpp:189, 214-219). */
+#define MARU_ROOT_PUCB 0                /* the reference's default search (run.py / gtp.py genmove)   */
+#define MARU_ROOT_GUMBEL 1              /* sequential halving: widths m, m/2, .., 1; budget split evenly */
+#define MARU_CRITERION_LCB 0            /* player.py:92-93, 349-352: win-chance lower confidence bound */
+#define MARU_CRITERION_VISITS 1
+typedef struct maru_selfplay_config {
+  int32_t width, height;                /* board size, 1..19                                          */
+  float   komi;
+  int32_t rule, superko;                /* MARU_RULE_*; superko only travels in the record            */
+  int32_t games;                        /* concurrent games of THIS scheduler (one GPU's shard)       */
+  int32_t threads;                      /* host worker threads; each owns games/threads games         */
+  int32_t visits;                       /* descents per move                                          */
+  int32_t max_moves;                    /* a game stops after this many moves (or two passes)         */
+  int32_t root;                         /* MARU_ROOT_*                                                */
+  int32_t root_width;                   /* Gumbel: candidates of the first phase                      */
+  float   noise;                        /* Gumbel(0, noise) on the root log-priors (Node.cpp:105-118) */
+  float   temperature;                  /* root temperature (Node.cpp:100-114)                        */
+  int32_t criterion;                    /* MARU_CRITERION_*                                           */
+  int32_t eval_leaf_only;               /* Player::_evalLeafOnly                                      */
+  int32_t opening_moves;                /* seeded random legal moves played before the first search   */
+  int32_t restart;                      /* 1: a finished game starts over (steady load for benchmarks) */
+  uint64_t seed;
+  int32_t cpu_first, cpu_count;         /* cpu_count > 0: pin worker i to core cpu_first + i % cpu_count */
+  int32_t lanes;                        /* batches in flight per worker (0 -> 2)                      */
+  int32_t record;                       /* 1: keep every move's candidate list (maru_selfplay_get_candidates) */
+} maru_selfplay_config;
+typedef struct maru_selfplay_stats {
+  uint64_t visits;                      /* root descents (Player.cpp:300)                              */
+  uint64_t evals;                       /* leaves evaluated by the network                             */
+  uint64_t moves, games_finished;
+  uint64_t submits;                     /* asynchronous batches handed to the queue                    */
+  uint64_t max_submit;                  /* largest of them                                             */
+  double   run_s;                       /* wall time inside maru_selfplay_run                          */
+  double   host_s;                      /* summed over workers: tree + record building                 */
+  double   stall_s;                     /* summed over workers: blocked on a ticket                    */
+} maru_selfplay_stats;
+typedef struct maru_candidate {         /* deepgo::Candidate (player.py:65-93)                         */
+  int32_t x, y, color, visits, playouts;
+  float   prior, value;
+} maru_candidate;
+typedef struct maru_selfplay maru_selfplay;
+/* Any evaluator of leaves: [n] records in, [n] results out, rc 0.  The product binding is the leaf-batch
+ * queue (maru_selfplay_create); a caller-supplied function lets the SAME search run over another
+ * evaluator (tests drive it and the reference Player with one synthetic evaluator on the CPU). */
+typedef int (*maru_leaf_fn)(const maru_state* s, maru_leaf* out, int n, void* user);
+int  maru_selfplay_create(maru_queue* q, const maru_selfplay_config* cfg, maru_selfplay** out);
+int  maru_selfplay_create_fn(maru_leaf_fn fn, void* user, const maru_selfplay_config* cfg, maru_selfplay** out);
+void maru_selfplay_destroy(maru_selfplay* sp);
+/* Force a move in one game (Player::play): openings, replays.  Not while maru_selfplay_run is active. */
+int  maru_selfplay_play(maru_selfplay* sp, int game, int x, int y);
+/* Every unfinished game plays `moves` more moves (search + play); blocks until all are done. */
+int  maru_selfplay_run(maru_selfplay* sp, int moves);
+int  maru_selfplay_get_stats(maru_selfplay* sp, maru_selfplay_stats* st);
+/* Moves of a game so far as (x, y) int16 pairs ((-1, -1) = pass); returns the count, writes <= cap. */
+int  maru_selfplay_get_moves(maru_selfplay* sp, int game, int16_t* xy, int cap);
+/* Candidate list the move `move` of `game` was chosen from (cfg.record = 1); returns the count. */
+int  maru_selfplay_get_candidates(maru_selfplay* sp, int game, int move, maru_candidate* out, int cap);
 
 /* ---- errors ---------------------------------------------------------------------------------- */
 const char* maru_last_error(void);      /* thread-local text of the last failing call              */

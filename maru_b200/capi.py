@@ -46,6 +46,30 @@ class QueueStats(C.Structure):
                 ('device_ms_total', C.c_double)]
 
 
+class SelfPlayConfig(C.Structure):
+    """maru_selfplay_config (include/maru_b200.h)."""
+    _fields_ = [('width', C.c_int32), ('height', C.c_int32), ('komi', C.c_float), ('rule', C.c_int32),
+                ('superko', C.c_int32), ('games', C.c_int32), ('threads', C.c_int32), ('visits', C.c_int32),
+                ('max_moves', C.c_int32), ('root', C.c_int32), ('root_width', C.c_int32), ('noise', C.c_float),
+                ('temperature', C.c_float), ('criterion', C.c_int32), ('eval_leaf_only', C.c_int32),
+                ('opening_moves', C.c_int32), ('restart', C.c_int32), ('seed', C.c_uint64),
+                ('cpu_first', C.c_int32), ('cpu_count', C.c_int32), ('lanes', C.c_int32), ('record', C.c_int32)]
+
+
+class SelfPlayStats(C.Structure):
+    _fields_ = [('visits', C.c_uint64), ('evals', C.c_uint64), ('moves', C.c_uint64),
+                ('games_finished', C.c_uint64), ('submits', C.c_uint64), ('max_submit', C.c_uint64),
+                ('run_s', C.c_double), ('host_s', C.c_double), ('stall_s', C.c_double)]
+
+
+class CandidateRec(C.Structure):
+    _fields_ = [('x', C.c_int32), ('y', C.c_int32), ('color', C.c_int32), ('visits', C.c_int32),
+                ('playouts', C.c_int32), ('prior', C.c_float), ('value', C.c_float)]
+
+
+LEAF_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p)   # maru_leaf_fn
+
+
 # every symbol include/maru_b200.h declares (tests check that the library exports all of them)
 ABI_SYMBOLS = [
     'maru_eval_create', 'maru_eval_destroy', 'maru_eval_get_info', 'maru_eval_forward_planes',
@@ -57,6 +81,9 @@ ABI_SYMBOLS = [
     'maru_queue_create', 'maru_queue_destroy', 'maru_queue_execute', 'maru_queue_execute_states',
     'maru_queue_get_stats', 'maru_ladder_flags', 'maru_rules_eval', 'maru_game_create', 'maru_game_clone',
     'maru_game_destroy', 'maru_game_play', 'maru_game_state', 'maru_last_error', 'maru_abi_version',
+    'maru_queue_submit_leaves', 'maru_queue_poll', 'maru_queue_wait', 'maru_queue_set_coalesce',
+    'maru_selfplay_create', 'maru_selfplay_create_fn', 'maru_selfplay_destroy', 'maru_selfplay_play',
+    'maru_selfplay_run', 'maru_selfplay_get_stats', 'maru_selfplay_get_moves', 'maru_selfplay_get_candidates',
 ]
 
 
@@ -119,6 +146,19 @@ def load_library():
     lib.maru_game_destroy.restype = None
     lib.maru_game_play.argtypes = [vp, ci, ci, ci]
     lib.maru_game_state.argtypes = [vp, ci, C.c_float, ci, ci, ci, vp]
+    lib.maru_queue_submit_leaves.argtypes = [vp, vp, vp, ci, C.POINTER(vp)]
+    lib.maru_queue_poll.argtypes = [vp, vp, C.POINTER(ci)]
+    lib.maru_queue_wait.argtypes = [vp, vp]
+    lib.maru_queue_set_coalesce.argtypes = [vp, ci, ci]
+    lib.maru_selfplay_create.argtypes = [vp, C.POINTER(SelfPlayConfig), C.POINTER(vp)]
+    lib.maru_selfplay_create_fn.argtypes = [vp, vp, C.POINTER(SelfPlayConfig), C.POINTER(vp)]
+    lib.maru_selfplay_destroy.argtypes = [vp]
+    lib.maru_selfplay_destroy.restype = None
+    lib.maru_selfplay_play.argtypes = [vp, ci, ci, ci]
+    lib.maru_selfplay_run.argtypes = [vp, ci]
+    lib.maru_selfplay_get_stats.argtypes = [vp, C.POINTER(SelfPlayStats)]
+    lib.maru_selfplay_get_moves.argtypes = [vp, ci, vp, ci]
+    lib.maru_selfplay_get_candidates.argtypes = [vp, ci, ci, C.POINTER(CandidateRec), ci]
     lib.maru_last_error.restype = C.c_char_p
     lib.maru_abi_version.restype = ci
     _lib = lib
@@ -391,6 +431,29 @@ class LeafQueue:
         st = QueueStats()
         self.lib.maru_queue_get_stats(self.handle, C.byref(st))
         return st
+
+    # asynchronous variant: submit a batch of leaves, keep working, collect later
+    def submit_leaves(self, states: np.ndarray):
+        """-> ticket (opaque); the result array is returned by wait(ticket)."""
+        s = _rows(states, STATE_SIZE, np.uint8)
+        out = np.zeros((s.shape[0], LEAF_SIZE), np.float32)
+        t = C.c_void_p()
+        _check(self.lib, self.lib.maru_queue_submit_leaves(self.handle, s.ctypes.data, out.ctypes.data,
+                                                           s.shape[0], C.byref(t)), 'maru_queue_submit_leaves')
+        return (t, s, out)                       # the buffers must outlive the ticket
+
+    def poll(self, ticket) -> bool:
+        done = C.c_int(0)
+        _check(self.lib, self.lib.maru_queue_poll(self.handle, ticket[0], C.byref(done)), 'maru_queue_poll')
+        return bool(done.value)
+
+    def wait(self, ticket) -> np.ndarray:
+        _check(self.lib, self.lib.maru_queue_wait(self.handle, ticket[0]), 'maru_queue_wait')
+        return ticket[2]
+
+    def set_coalesce(self, min_rows: int, max_wait_us: int) -> None:
+        _check(self.lib, self.lib.maru_queue_set_coalesce(self.handle, min_rows, max_wait_us),
+               'maru_queue_set_coalesce')
 
 
 class Processor:

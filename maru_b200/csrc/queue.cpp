@@ -20,6 +20,7 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -57,6 +58,8 @@ struct maru_queue {
   std::vector<std::unique_ptr<maru::Worker>> workers;
   std::mutex mu;  // dispatcher (Processor::_mutex)
   int batch_size = 0;
+  std::atomic<int> coalesce_rows{0};     // idle worker: wait for this many queued rows ...
+  std::atomic<int> coalesce_us{0};       // ... but not longer than this (maru_queue_set_coalesce)
   std::mutex stat_mu;
   maru_queue_stats stats{};
 };
@@ -123,6 +126,12 @@ static void worker_main(maru_queue* q, Worker* w) {
       std::unique_lock<std::mutex> l(w->mu);
       if (inflight.slot < 0) {
         w->cv.wait(l, [w] { return !w->q.empty() || w->stop; });
+        const int want = q->coalesce_rows.load(std::memory_order_relaxed);
+        if (want > 0 && !w->stop && w->waiting < (want < cap ? want : cap)) {
+          const int lim = want < cap ? want : cap;
+          w->cv.wait_for(l, std::chrono::microseconds(q->coalesce_us.load(std::memory_order_relaxed)),
+                         [w, lim] { return w->waiting >= lim || w->stop; });
+        }
       }
       if (w->stop && w->q.empty()) {
         l.unlock();
@@ -194,15 +203,11 @@ static void worker_main(maru_queue* q, Worker* w) {
   }
 }
 
-static int queue_execute(maru_queue* q, int kind, const void* in, void* out, int n) {
-  if (q == nullptr || in == nullptr || out == nullptr || n < 0) {
-    set_error("maru_queue_execute: bad argument");
-    return 1;
-  }
-  if (n == 0) return 0;
+// Processor.cpp:42-55: least waiting + reserved rows, then reserve; Executor.cpp:52-67: enqueue + notify
+static int enqueue_job(maru_queue* q, Job* job) {
+  const int n = job->n;
   Worker* w = nullptr;
   {
-    // Processor.cpp:42-55: least waiting + reserved rows, then reserve
     std::lock_guard<std::mutex> l(q->mu);
     int best = -1, best_cnt = 0;
     for (size_t i = 0; i < q->workers.size(); i++) {
@@ -218,12 +223,7 @@ static int queue_execute(maru_queue* q, int kind, const void* in, void* out, int
     std::lock_guard<std::mutex> lw(w->mu);
     w->reserved += n;
   }
-  Job job;
-  job.kind = kind;
-  job.in = in;
-  job.out = out;
-  job.n = n;
-  job.t_enq = std::chrono::steady_clock::now();
+  job->t_enq = std::chrono::steady_clock::now();
   {
     std::lock_guard<std::mutex> l(w->mu);
     if (w->stop) {
@@ -231,11 +231,26 @@ static int queue_execute(maru_queue* q, int kind, const void* in, void* out, int
       set_error("maru_queue is shutting down");
       return 1;
     }
-    w->q.push_back(&job);
+    w->q.push_back(job);
     w->waiting += n;
     w->reserved = w->reserved - n > 0 ? w->reserved - n : 0;  // Executor.cpp:60
   }
-  w->cv.notify_one();
+  w->cv.notify_all();
+  return 0;
+}
+
+static int queue_execute(maru_queue* q, int kind, const void* in, void* out, int n) {
+  if (q == nullptr || in == nullptr || out == nullptr || n < 0) {
+    set_error("maru_queue_execute: bad argument");
+    return 1;
+  }
+  if (n == 0) return 0;
+  Job job;
+  job.kind = kind;
+  job.in = in;
+  job.out = out;
+  job.n = n;
+  if (enqueue_job(q, &job)) return 1;
   {
     std::unique_lock<std::mutex> l(job.mu);
     job.cv.wait(l, [&job] { return job.done; });
@@ -289,6 +304,67 @@ int maru_queue_execute_states(maru_queue* q, const maru_state* s, float* out, in
 
 int maru_queue_execute_leaves(maru_queue* q, const maru_state* s, maru_leaf* out, int n) {
   return maru::queue_execute(q, maru::KIND_LEAVES, s, out, n);
+}
+
+// ---- asynchronous submit / poll / wait: a ticket is a heap Job ---------------------------------
+int maru_queue_submit_leaves(maru_queue* q, const maru_state* s, maru_leaf* out, int n, maru_ticket** t) {
+  if (q == nullptr || s == nullptr || out == nullptr || t == nullptr || n <= 0) {
+    maru::set_error("maru_queue_submit_leaves: bad argument");
+    return 1;
+  }
+  *t = nullptr;
+  auto* job = new (std::nothrow) maru::Job();
+  if (job == nullptr) {
+    maru::set_error("out of memory");
+    return 1;
+  }
+  job->kind = maru::KIND_LEAVES;
+  job->in = s;
+  job->out = out;
+  job->n = n;
+  if (maru::enqueue_job(q, job)) {
+    delete job;
+    return 1;
+  }
+  *t = reinterpret_cast<maru_ticket*>(job);
+  return 0;
+}
+
+int maru_queue_poll(maru_queue* q, maru_ticket* t, int* done) {
+  if (q == nullptr || t == nullptr || done == nullptr) {
+    maru::set_error("maru_queue_poll: bad argument");
+    return 1;
+  }
+  auto* job = reinterpret_cast<maru::Job*>(t);
+  std::lock_guard<std::mutex> l(job->mu);
+  *done = job->done ? 1 : 0;
+  return 0;
+}
+
+int maru_queue_wait(maru_queue* q, maru_ticket* t) {
+  if (q == nullptr || t == nullptr) {
+    maru::set_error("maru_queue_wait: bad argument");
+    return 1;
+  }
+  auto* job = reinterpret_cast<maru::Job*>(t);
+  {
+    std::unique_lock<std::mutex> l(job->mu);
+    job->cv.wait(l, [job] { return job->done; });
+  }
+  const int rc = job->rc;
+  if (rc) maru::set_error(job->err);
+  delete job;
+  return rc;
+}
+
+int maru_queue_set_coalesce(maru_queue* q, int min_rows, int max_wait_us) {
+  if (q == nullptr || min_rows < 0 || max_wait_us < 0) {
+    maru::set_error("maru_queue_set_coalesce: bad argument");
+    return 1;
+  }
+  q->coalesce_rows.store(min_rows);
+  q->coalesce_us.store(max_wait_us);
+  return 0;
 }
 
 int maru_queue_get_stats(maru_queue* q, maru_queue_stats* st) {

@@ -1,0 +1,416 @@
+// search.h — native tree search of ONE game over the flat host board.
+//
+// The reference runs one descent per thread-pool task: Player::_run hands every visit to a worker
+// (reference src/deepgo/native/cpp/Player.cpp:282-313), the worker walks Node::evaluate from the root
+// (Player.cpp:319-368, Node.cpp:71-225) and BLOCKS inside Evaluator::evaluate until the leaf's batch
+// has come back; every expanded node deep-copies a std::set-based Board (Node.cpp:588-598).
+// Here a game is a resumable state machine: `GameSearch::advance` walks descents until one of them
+// needs the network, writes that leaf's 448-byte record and returns; `deliver` hands the result back
+// and the same descent continues.  One host thread can therefore interleave hundreds of games and
+// submit their leaves as ONE asynchronous batch (selfplay.cpp) — no thread hand-off per visit, no
+// condition variable per leaf, ~0.6 KB copied per expansion.
+//
+// What is kept EXACTLY (tests/test_search.py plays the unmodified reference Player and this search on
+// the same evaluator and compares every move and every root statistic at threads = 1):
+//   * progressive widening: a candidate's priority is prior^t * e^Gumbel / (times picked + 1); the
+//     best one joins a FIFO waiting list if it is not a child yet                 Node.cpp:92-154
+//   * a waiting candidate becomes a child (new leaf) before any existing child is revisited, and
+//     the first child of a node reports playouts = -1                             Node.cpp:159-181
+//   * root-only switches: `equally` (even visits, 1 / (n + 1 - q/2)), `width` (only the best
+//     `width` children by value LCB stay eligible), UCB1 instead of PUCB          Node.cpp:183-224
+//   * PUCB with c = log((1 + N + 19652) / 19652) + 1.25 and exploration doubled  Node.cpp:476-486
+//   * value LCB = q - 1.96 * 0.5 / sqrt(n + 1) in the mover's favour              Node.cpp:460-469
+//   * backup: the leaf's value is added to every node of the path, playouts too   Player.cpp:332-346
+//   * Player::play keeps the chosen child's subtree, drops the rest               Player.cpp:93-115
+//   * candidates, policy fallback and pass                                         Player.cpp:229-261
+// All arithmetic is done in the same types (float / double promotions) as the reference's
+// expressions, so a deterministic evaluator gives bit-identical trees.
+// Not kept: the per-node shared_mutexes (one descent in flight per game: the reference's threads = 1)
+// and the process-wide random engine (one seeded engine per game: self-play is reproducible).
+#pragma once
+
+#include <cmath>
+#include <cstdint>
+#include <deque>
+#include <random>
+#include <utility>
+#include <vector>
+
+#include "../dropin/lean_game.h"
+#include "maru_b200.h"
+
+namespace maru {
+
+struct SearchSetup {
+  int width = 19, height = 19;
+  float komi = 7.5f;
+  int rule = MARU_RULE_CH;
+  bool superko = false;
+  bool eval_leaf_only = false;          // Player::_evalLeafOnly (Player.cpp:337-341)
+};
+
+// arguments of Node::evaluate that apply to the root only (Player.cpp:358-363 resets them below it)
+struct RootMode {
+  bool equally = false;
+  int width = 0;
+  bool use_ucb1 = false;
+  float temperature = 1.0f;
+  float noise = 0.0f;
+};
+
+struct Prior {                          // deepgo::Policy (Policy.h:10-39)
+  int16_t x, y;
+  float p;
+  int32_t picked;                       // Policy::visits: how often widening chose this move
+};
+
+struct TreeNode {
+  maru_b200::LeanGame pos;              // position AFTER the move (x, y) of `color`
+  int32_t x = -1, y = -1;
+  int32_t color = MARU_WHITE;           // colour of the stone that led here (root of a game: WHITE)
+  int32_t captured = 0;
+  float prior = 0.0f;
+  bool evaluated = false;
+  float net_value = 0.0f;               // Evaluator::getValue(): black's point of view, in [-1, 1]
+  std::vector<Prior> moves;             // Node::_childPolicies
+  struct Edge {
+    int32_t cell, node;
+  };
+  std::vector<Edge> kids;               // Node::_children, insertion order
+  std::vector<Prior> waiting;           // Node::_waitingQueue / _waitingSet (FIFO, at most a few)
+  int32_t visits = 0, playouts = 0, count = 0;
+  float value_sum = 0.0f;
+
+  float mean() const { return count == 0 ? 0.0f : value_sum / count; }           // Node::getValue
+  int kid_of(int cell) const {
+    for (const Edge& e : kids)
+      if (e.cell == cell) return e.node;
+    return -1;
+  }
+  bool is_waiting(int cell, int board_w) const {
+    for (const Prior& q : waiting)
+      if (q.y * board_w + q.x == cell) return true;
+    return false;
+  }
+  void reset_stats() {                                                            // Node::_reset
+    evaluated = false;
+    net_value = 0.0f;
+    moves.clear();
+    kids.clear();
+    waiting.clear();
+    visits = playouts = count = 0;
+    value_sum = 0.0f;
+  }
+};
+
+struct Candidate {                      // deepgo::Candidate as Player::getCandidates fills it
+  int32_t x, y, color, visits, playouts;
+  float prior, value;
+};
+
+class GameSearch {
+ public:
+  enum Status { WANT_LEAF, MOVE_READY };
+
+  void init(const SearchSetup& s, uint64_t seed) {
+    setup_ = s;
+    rng_.seed((std::minstd_rand0::result_type)(seed % 2147483646u + 1u));
+    pool_.clear();
+    free_.clear();
+    root_ = alloc();
+    TreeNode& r = pool_[root_];
+    r.pos.init(s.width, s.height);
+    r.x = r.y = -1;
+    r.color = MARU_WHITE;
+    r.captured = 0;
+    r.prior = 0.0f;
+    r.reset_stats();
+    path_.clear();
+    pending_ = -1;
+    want_root_eval_ = false;
+  }
+
+  const TreeNode& root() const { return pool_[root_]; }
+  int to_move() const { return -pool_[root_].color; }                             // Player::getColor
+  size_t nodes_in_use() const { return pool_.size() - free_.size(); }
+
+  // Arm a search: descents are made until the ROOT's visit count reaches `target`
+  // (Player::startEvaluation / waitEvaluation, Player.cpp:180-223).
+  void start(const RootMode& m, int target) {
+    mode_ = m;
+    target_ = target;
+  }
+
+  // Run descents.  WANT_LEAF: `*st` holds the record of the node that needs the network; call
+  // deliver() and then advance() again.  MOVE_READY: the root has reached the target.
+  Status advance(maru_state* st) {
+    for (;;) {
+      if (path_.empty()) {
+        if (pool_[root_].visits >= target_) return MOVE_READY;
+        path_.push_back(root_);
+        cur_ = mode_;
+      }
+      const int id = path_.back();
+      TreeNode& n = pool_[id];
+      if (!n.evaluated) {                                                         // Node::_evaluate
+        request(id, st);
+        return WANT_LEAF;
+      }
+      int next = -1, playouts = 0;
+      step(n, cur_, &next, &playouts);
+      const float v = n.net_value;
+      if (playouts == 1) {
+        for (int p : path_) {
+          pool_[p].count += 1;
+          pool_[p].value_sum += v;
+        }
+      } else if (playouts == -1 && setup_.eval_leaf_only) {
+        for (int p : path_) {
+          pool_[p].count -= 1;
+          pool_[p].value_sum -= v;
+        }
+      }
+      for (int p : path_) pool_[p].playouts += playouts;
+      if (next < 0) {
+        path_.clear();
+        descents_++;
+        continue;
+      }
+      path_.push_back(next);
+      cur_ = RootMode();
+    }
+  }
+
+  // The network's answer for the record advance() / need_root() produced last.
+  void deliver(const maru_state& st, const maru_leaf& leaf) {
+    TreeNode& n = pool_[pending_];
+    const int w = st.width, cells = st.width * st.height;
+    n.moves.clear();
+    for (int cell = 0; cell < cells; cell++)
+      if ((st.move_mask[cell >> 3] >> (cell & 7)) & 1u)
+        n.moves.push_back(Prior{(int16_t)(cell % w), (int16_t)(cell / w), leaf.prior[cell], 0});
+    const float win = leaf.value;                                                 // Evaluator.cpp:75-80
+    n.net_value = (st.color == MARU_WHITE) ? 1.0f - 2.0f * win : 2.0f * win - 1.0f;
+    n.evaluated = true;
+    pending_ = -1;
+    want_root_eval_ = false;
+    evals_++;
+  }
+
+  // Player::getCandidates needs the root's priors when the root has no child yet (Player.cpp:246-254):
+  // true -> `*st` holds the root's record, deliver() its result before calling candidates().
+  bool need_root(maru_state* st) {
+    TreeNode& r = pool_[root_];
+    if (!r.kids.empty() || r.evaluated) return false;
+    request(root_, st);
+    want_root_eval_ = true;
+    return true;
+  }
+
+  void candidates(std::vector<Candidate>* out) const {
+    const TreeNode& r = pool_[root_];
+    out->clear();
+    for (const TreeNode::Edge& e : r.kids) {
+      const TreeNode& c = pool_[e.node];
+      out->push_back(Candidate{c.x, c.y, c.color, c.visits, c.playouts, c.prior, c.mean()});
+    }
+    if (!out->empty()) return;
+    int bx = -1, by = -1;                                                         // Node::getPolicyMove
+    if (!r.moves.empty()) {
+      const Prior* best = &r.moves[0];
+      for (const Prior& q : r.moves)
+        if (best->p < q.p) best = &q;
+      bx = best->x;
+      by = best->y;
+    }
+    out->push_back(Candidate{bx, by, -r.color, 1, 1, 1.0f, r.mean()});
+  }
+
+  // Player::play: the child at (x, y) becomes the root with its subtree, or a fresh node does
+  // (Node::getChild); everything else goes back to the pool.  Returns the stones captured.
+  int play(int x, int y) {
+    const int old = root_;
+    const int cell = y * setup_.width + x;
+    int keep = pool_[old].kid_of(cell);
+    if (keep < 0) {
+      keep = alloc();
+      follow(pool_[keep], pool_[old], x, y, 1.0f);
+    }
+    root_ = keep;
+    release_except(old, keep);
+    path_.clear();
+    pending_ = -1;
+    return pool_[root_].captured;
+  }
+
+  uint64_t descents() const { return descents_; }
+  uint64_t evals() const { return evals_; }
+
+ private:
+  SearchSetup setup_;
+  RootMode mode_, cur_;
+  int target_ = 0;
+  std::deque<TreeNode> pool_;           // stable addresses; recycled through free_
+  std::vector<int> free_;
+  int root_ = -1;
+  std::vector<int> path_;
+  int pending_ = -1;
+  bool want_root_eval_ = false;
+  uint64_t descents_ = 0, evals_ = 0;
+  std::minstd_rand0 rng_;               // the reference's std::default_random_engine (Node.cpp:11-12)
+  std::vector<std::pair<int, float>> scratch_;
+
+  int alloc() {
+    if (!free_.empty()) {
+      const int id = free_.back();
+      free_.pop_back();
+      return id;
+    }
+    pool_.emplace_back();
+    return (int)pool_.size() - 1;
+  }
+
+  void release_except(int from, int keep) {
+    std::vector<int> stack{from};
+    while (!stack.empty()) {
+      const int id = stack.back();
+      stack.pop_back();
+      if (id == keep) continue;
+      for (const TreeNode::Edge& e : pool_[id].kids) stack.push_back(e.node);
+      pool_[id].kids.clear();
+      free_.push_back(id);
+    }
+  }
+
+  void follow(TreeNode& n, const TreeNode& prev, int x, int y, float prior) {     // Node::_setAsNextNode
+    n.x = x;
+    n.y = y;
+    n.color = -prev.color;
+    n.prior = prior;
+    n.pos = prev.pos;
+    n.captured = n.pos.play(x, y, n.color);
+    n.reset_stats();
+  }
+
+  void request(int id, maru_state* st) {
+    const TreeNode& n = pool_[id];
+    n.pos.to_state(-n.color, setup_.komi, setup_.rule, setup_.superko, /*with_move_mask=*/true, st);
+    pending_ = id;
+  }
+
+  float lcb(const TreeNode& c) const {                                            // Node::getValueLCB
+    if (c.count == 0) return 0.0f;
+    const float q = c.value_sum / c.count;
+    const float half = 1.96 * 0.5 / std::sqrt(c.visits + 1);
+    return q - (half * c.color);
+  }
+  float pucb(const TreeNode& c, int total) const {                                // Node::getPriorityByPUCB
+    if (c.count == 0) return -99.0f;
+    const float c_puct = std::log((1 + total + 19652.0) / 19652.0) + 1.25;
+    const float q = (c.value_sum / c.count) * c.color;
+    const float u = c_puct * c.prior * std::sqrt(total) / (1 + c.visits);
+    return q + 2 * u;
+  }
+  float ucb1(const TreeNode& c, int total) const {                                // Node::getPriorityByUCB1
+    if (c.count == 0) return -99.0f;
+    const float q = (c.value_sum / c.count) * c.color;
+    const float u = 0.5 * std::sqrt(std::log(total) / (c.visits + 1));
+    return q + u;
+  }
+
+  // One Node::evaluate on an evaluated node: *next = node to descend into (-1: the descent ends here),
+  // *playouts = NodeResult::getPlayouts.
+  void step(TreeNode& n, const RootMode& m, int* next, int* playouts) {
+    n.visits += 1;
+    *next = -1;
+    *playouts = 1;
+    if (n.visits == 1 || n.moves.empty()) return;
+    const int bw = setup_.width;
+
+    // --- widening: which move deserves to be a child next
+    const int have = (int)(n.kids.size() + n.waiting.size());
+    if (have < (int)n.moves.size() && (m.width < 1 || have < m.width)) {
+      int best = 0, best_class = 0;
+      float best_pri = 0.0f;
+      const float win = n.mean() * (-n.color) * 0.5 + 0.5;
+      const float power = win + (1.0 / m.temperature) * (1 - win);
+      const float scale = (have <= 4) ? 0.0f : m.noise;
+      // pow(p, 1) == p and p * e^0 == p exactly: the two transcendental calls per candidate are only
+      // made when they can change the result (below the root the reference always passes t = 1, noise = 0)
+      const bool tempered = power != 1.0f, noisy = scale != 0.0f;
+      std::extreme_value_distribution<float> gumbel(0.0f, noisy ? scale : 1.0f);
+      for (int i = 0; i < (int)n.moves.size(); i++) {
+        const Prior& q = n.moves[i];
+        float pr = q.p;
+        if (tempered) pr = std::pow(pr, power);
+        if (noisy) pr *= std::exp(gumbel(rng_));
+        int cls = 1;
+        const float pri = pr / (q.picked + 1);
+        if (m.equally) {
+          const int cell = q.y * bw + q.x;
+          if (n.kid_of(cell) >= 0 || n.is_waiting(cell, bw)) cls = 0;
+        }
+        if (cls > best_class || (cls == best_class && pri > best_pri)) {
+          best = i;
+          best_class = cls;
+          best_pri = pri;
+        }
+      }
+      Prior& chosen = n.moves[best];
+      const int cell = chosen.y * bw + chosen.x;
+      if (n.kid_of(cell) < 0 && !n.is_waiting(cell, bw)) n.waiting.push_back(chosen);
+      chosen.picked += 1;
+    }
+
+    // --- a waiting move becomes a new leaf
+    if (!n.waiting.empty() && (m.width <= 0 || (int)n.kids.size() < m.width)) {
+      const Prior q = n.waiting.front();
+      n.waiting.erase(n.waiting.begin());
+      const int cell = q.y * bw + q.x;
+      if (n.kid_of(cell) < 0) {
+        const bool first = n.kids.empty();
+        const int id = alloc();                       // (deque: `n` stays valid)
+        follow(pool_[id], n, q.x, q.y, q.p);
+        n.kids.push_back(TreeNode::Edge{cell, id});
+        *next = id;
+        *playouts = first ? -1 : 0;
+        return;
+      }
+    }
+
+    // --- otherwise revisit the most promising child
+    scratch_.clear();
+    for (const TreeNode::Edge& e : n.kids) {
+      const TreeNode& c = pool_[e.node];
+      scratch_.emplace_back(e.node, lcb(c) * c.color);
+    }
+    if (m.width > 0 && (int)scratch_.size() > m.width) {
+      std::sort(scratch_.begin(), scratch_.end(),
+                [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.second > b.second; });
+      scratch_.resize(m.width);
+    }
+    int pick = scratch_[0].first;
+    float top = -1.0;
+    for (const auto& kv : scratch_) {
+      const TreeNode& c = pool_[kv.first];
+      float pri;
+      if (m.equally) {
+        const float cv = c.visits;
+        const float q = c.mean() * c.color;
+        pri = 1.0 / (cv + 1 - q * 0.5);
+      } else if (m.use_ucb1) {
+        pri = ucb1(c, n.visits);
+      } else {
+        pri = pucb(c, n.visits);
+      }
+      if (top < pri) {
+        pick = kv.first;
+        top = pri;
+      }
+    }
+    *next = pick;
+    *playouts = 0;
+  }
+};
+
+}  // namespace maru

@@ -195,13 +195,17 @@ def randomize_(net: nn.Module, seed: int = 0) -> nn.Module:
 PEAKED_PRIOR = ((24, 1.0), (11, 0.72), (25, 0.52), (12, 0.37), (26, 0.25), (13, 0.15))
 
 
-def sharpen_policy_(net: MaruNet, scale: float = 0.5) -> MaruNet:
+def sharpen_policy_(net: MaruNet, scale: float = 0.3) -> MaruNet:
     """Turn the near-uniform policy of a random-init net (logit sigma ~0.02-0.1: argmax decided by bf16
     round-off) into a PEAKED one, the way a trained net's policy is, without training: one trunk channel
     is wired to carry `sum_p A_p * plane_p` from the stem's centre tap through the residual stream, one
     head feature reads it, and policy planes 0/1 read that feature. Every other weight stays random, so the
     signal travels through (and is perturbed by) every layer of the trunk, attention included.
-    Used by the parity tests that gate top-1 agreement on ALL positions (north_star: >= 99 %)."""
+    Used by the parity tests that gate top-1 agreement on ALL positions (north_star: >= 99 %).
+    `scale` sets the logit amplitude of the prior.  The bf16 path's logit error grows with it (the prior rides
+    the residual stream and is re-rounded to bf16 after every block: measured max-abs 1.9e-2..2.3e-2 for the
+    15 residual layers of b10c256 at scale 0.5, ~6e-3 for b4c128), so the default keeps b10c256 inside the
+    2e-2 logit tolerance with margin while the reference's top-2 gap (1 % quantile ~0.1) stays 5x the error."""
     with torch.no_grad():
         k = net.stem_conv.out_channels - 1                 # trunk channel that carries the prior
         j = net.heads.g.conv.out_channels - 1              # head feature that reads it

@@ -19,6 +19,12 @@ passes them through.  This module is the missing driver:
 Multi-GPU: games are sharded statically (game g -> rank g % world, `maru_b200.shard`), one process
 per GPU, no data-path collective; only the counters are reduced at report time.
 
+`NativeSelfPlay` is the product scheduler: the same move decision and the same tree policy in C++
+(maru_b200/csrc/search.h, selfplay.cpp behind `maru_selfplay_*`), hundreds of games per host thread,
+leaves submitted asynchronously in batches.  `SelfPlayScheduler` + `PlayerAdapter` below drive ANY
+reference-style player (the reference's own `deepgo::Player` in the tests and in bench's reference
+arm) through the identical schedule, which is what the native scheduler is checked against.
+
 Players are duck-typed after the reference's `deepgo.player.Player`:
     initialize(); evaluate(visits=, equally=, width=, noise=, temperature=) -> candidates; play(move)
 A candidate is either a reference `Candidate` (`.pos`, `.visits`, `.value`, `.color`) or a mapping
@@ -62,6 +68,9 @@ class Move:
     y: int
     visits: int
     value: float
+    color: int = 1
+    playouts: int = 0
+    policy: float = 0.0
 
     @property
     def is_pass(self) -> bool:
@@ -81,9 +90,11 @@ class PlayerAdapter:
         out = []
         for c in self.player.evaluate(**kw):
             if isinstance(c, dict):
-                out.append(Move(int(c['x']), int(c['y']), int(c['visits']), float(c['value'])))
+                out.append(Move(int(c['x']), int(c['y']), int(c['visits']), float(c['value']),
+                                int(c.get('color', 1)), int(c.get('playouts', 0)), float(c.get('policy', 0.0))))
             else:                                    # reference deepgo.player.Candidate
-                out.append(Move(int(c.pos[0]), int(c.pos[1]), int(c.visits), float(c.value)))
+                out.append(Move(int(c.pos[0]), int(c.pos[1]), int(c.visits), float(c.value),
+                                int(c.color), int(c.playouts), float(c.policy)))
         return out
 
     def play(self, mv: Move) -> None:
@@ -93,54 +104,62 @@ class PlayerAdapter:
             self.player.play(mv.x, mv.y)             # native-shim style play(x, y)
 
 
-def _lcb(mv: Move, color_sign: float = 1.0) -> float:
-    """Candidate ordering of the reference (player.py:92-93, 349-352): win chance LCB."""
-    win = mv.value * color_sign * 0.5 + 0.5
+def _lcb(mv: Move) -> float:
+    """Candidate ordering of the reference (player.py:92-93, 349-352): LCB of the MOVER's win chance
+    (value is black's point of view, color the colour of the candidate stone)."""
+    win = mv.value * mv.color * 0.5 + 0.5
     return win - 1.96 * 0.25 / math.sqrt(mv.visits + 1)
 
 
-def gumbel_root_search(player: PlayerAdapter, visits: int, width: int = 16, noise: float = 1.0,
-                       temperature: float = 1.0, criterion: str = 'visits') -> Tuple[Optional[Move], int]:
-    """One move decision by sequential halving at the root.
-    Returns (move or None, visits now held by the root's children).
+def _best(cands: List[Move], criterion: str) -> Move:
+    return max(cands, key=(lambda c: c.visits) if criterion == 'visits' else _lcb)   # first of equals
 
-    Phase k calls evaluate(visits=n_1+...+n_k, equally=True, width=m_k, noise=noise): the reference's
-    `visits` is a target for the ROOT's visit count (Player.cpp:190, 214-216) and the tree persists
-    between calls (startEvaluation only re-arms the search, Player.cpp:180-203), so phase k continues
-    from phase k-1 and Node::evaluate's LCB cut (Node.cpp:191-198) drops the worse half of the
-    survivors."""
+
+def gumbel_root_search(player: PlayerAdapter, visits: int, width: int = 16, noise: float = 1.0,
+                       temperature: float = 1.0, criterion: str = 'visits', base: int = 0
+                       ) -> Tuple[Optional[Move], List[Move]]:
+    """One move decision by sequential halving at the root.  Returns (move, candidate list).
+
+    The reference's `visits` is a target for the ROOT's visit count (Player.cpp:189, 214-219) and the
+    tree persists between calls (startEvaluation only re-arms the search, Player.cpp:180-203).  `base`
+    is the visit count the root inherited with its subtree, so phase k asks for
+    base + n_1 + ... + n_k: exactly `visits` descents per move, phase k continuing phase k-1's tree
+    with equally=True and half the root width — Node::evaluate's LCB cut (Node.cpp:191-198) drops the
+    worse half of the survivors."""
     cands: List[Move] = []
-    target = 0
+    target = base
     for w, n in halving_schedule(visits, width):
         target += n
         cands = player.evaluate(visits=target, equally=True, width=w, noise=noise, temperature=temperature)
         if not cands:
             break
     if not cands:
-        return None, 0
-    best = max(cands, key=(lambda c: c.visits) if criterion == 'visits' else _lcb)
-    return best, sum(c.visits for c in cands)
+        return None, []
+    return _best(cands, criterion), cands
 
 
 def pucb_root_search(player: PlayerAdapter, visits: int, temperature: float = 1.0,
-                     criterion: str = 'visits') -> Tuple[Optional[Move], int]:
-    """The reference's default search (PUCB everywhere, run.py / gtp.py genmove)."""
-    cands = player.evaluate(visits=visits, equally=False, width=0, noise=0.0, temperature=temperature)
+                     criterion: str = 'visits', base: int = 0) -> Tuple[Optional[Move], List[Move]]:
+    """The reference's default search (PUCB everywhere, run.py / gtp.py genmove): `visits` descents on
+    top of the `base` visits the root inherited."""
+    cands = player.evaluate(visits=base + visits, equally=False, width=0, noise=0.0, temperature=temperature)
     if not cands:
-        return None, 0
-    best = max(cands, key=(lambda c: c.visits) if criterion == 'visits' else _lcb)
-    return best, sum(c.visits for c in cands)
+        return None, []
+    return _best(cands, criterion), cands
 
 
 @dataclass
 class GameRecord:
     moves: List[Tuple[int, int]] = field(default_factory=list)
+    candidates: List[List[Move]] = field(default_factory=list)
+    overshoot: List[bool] = field(default_factory=list)   # the player made more descents than asked (see _play_game)
     visits: int = 0
     finished: bool = False
 
 
 class SelfPlayScheduler:
-    """Runs this rank's shard of `n_games` concurrent self-play games.
+    """Runs this rank's shard of `n_games` concurrent self-play games over reference-style players
+    (one host thread per game; the oracle / reference arm of the native scheduler below).
 
     make_player(game_index) -> a reference-style player bound to this rank's leaf-batch queue."""
 
@@ -162,18 +181,30 @@ class SelfPlayScheduler:
         try:
             p.initialize()
             passes = 0
-            carried = 0          # visits the new root inherited from the previous search (tree reuse)
+            base = 0             # visits the root inherited with its subtree (tree reuse, Player.cpp:104)
             for _ in range(self.max_moves):
                 if self.root == 'gumbel':
-                    mv, spent = gumbel_root_search(p, self.visits, self.width, self.noise,
-                                                   self.temperature, self.criterion)
+                    mv, cands = gumbel_root_search(p, self.visits, self.width, self.noise,
+                                                   self.temperature, self.criterion, base)
                 else:
-                    mv, spent = pucb_root_search(p, self.visits, self.temperature, self.criterion)
-                rec.visits += max(0, spent - carried)    # only the descents made for THIS move
-                carried = max(0, mv.visits - 1) if mv is not None else 0
+                    mv, cands = pucb_root_search(p, self.visits, self.temperature, self.criterion, base)
+                rec.visits += self.visits if cands else 0    # descents made for THIS move
                 if mv is None:
                     mv = Move(PASS[0], PASS[1], 0, 0.0)
+                # the chosen child becomes the root and brings its visit count; the policy / pass
+                # fallback of a childless root (ONE candidate reported with visits = playouts = 1 and
+                # policy 1.0, Player.cpp:246-254) starts from a fresh node instead
+                fallback = len(cands) <= 1 and (not cands or (cands[0].visits == 1 and cands[0].playouts == 1
+                                                              and cands[0].policy == 1.0))
+                # The reference only stops when its waiter thread has seen the target (Player.cpp:212-223) while
+                # its control thread keeps launching descents (Player.cpp:282-313): with a very fast evaluator
+                # one extra descent can slip in.  Recorded so that comparisons can tell (root visits = 1 + sum
+                # of the children's visits).
+                rec.overshoot.append(bool(cands) and not fallback and
+                                     sum(c.visits for c in cands) + 1 != base + self.visits)
+                base = 0 if fallback else mv.visits
                 rec.moves.append((mv.x, mv.y))
+                rec.candidates.append(cands)
                 p.play(mv)
                 passes = passes + 1 if mv.is_pass else 0
                 if passes >= 2:
@@ -193,6 +224,80 @@ class SelfPlayScheduler:
         return shard.RankStats(visits=sum(r.visits for r in self.records),
                                batches=sum(len(r.moves) for r in self.records),
                                wall_s=time.perf_counter() - t0)
+
+
+class NativeSelfPlay:
+    """The product scheduler: `maru_selfplay_*` (maru_b200/csrc/selfplay.cpp, search.h).
+
+    queue: a `LeafQueue` on this rank's GPU, or `leaf_fn` = a C function pointer of type maru_leaf_fn
+    (another evaluator: the CPU tests pass the oracle's synthetic one).  Games are this rank's shard."""
+
+    ROOTS = {'pucb': 0, 'gumbel': 1}
+    CRITERIA = {'lcb': 0, 'visits': 1}
+
+    def __init__(self, queue=None, *, leaf_fn=None, games: int, size: int | Tuple[int, int] = 19, visits: int = 50,
+                 threads: int = 1, max_moves: int = 400, root: str = 'pucb', width: int = 16, noise: float = 0.0,
+                 temperature: float = 1.0, criterion: str = 'lcb', komi: float = 7.5, rule: int = 0,
+                 superko: bool = False, eval_leaf_only: bool = False, opening_moves: int = 0,
+                 restart: bool = False, seed: int = 0, cpus: Optional[Sequence[int]] = None, lanes: int = 2,
+                 record: bool = False):
+        import ctypes as C
+        from . import capi
+        self.lib = capi.load_library()
+        w, h = (size, size) if isinstance(size, int) else size
+        cfg = capi.SelfPlayConfig(
+            width=w, height=h, komi=komi, rule=rule, superko=int(superko), games=games, threads=threads,
+            visits=visits, max_moves=max_moves, root=self.ROOTS[root], root_width=width, noise=noise,
+            temperature=temperature, criterion=self.CRITERIA[criterion], eval_leaf_only=int(eval_leaf_only),
+            opening_moves=opening_moves, restart=int(restart), seed=seed,
+            cpu_first=(min(cpus) if cpus else 0), cpu_count=(len(cpus) if cpus else 0), lanes=lanes,
+            record=int(record))
+        self.games = games
+        self._keep = (queue, leaf_fn)
+        h_ = C.c_void_p()
+        if queue is not None:
+            rc = self.lib.maru_selfplay_create(queue.handle, C.byref(cfg), C.byref(h_))
+        else:
+            rc = self.lib.maru_selfplay_create_fn(C.cast(leaf_fn, C.c_void_p), None, C.byref(cfg), C.byref(h_))
+        capi._check(self.lib, rc, 'maru_selfplay_create')
+        self.handle = h_
+
+    def close(self) -> None:
+        if getattr(self, 'handle', None):
+            self.lib.maru_selfplay_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        self.close()
+
+    def play(self, game: int, x: int, y: int) -> int:
+        return self.lib.maru_selfplay_play(self.handle, game, x, y)
+
+    def run(self, moves: int) -> None:
+        """Every unfinished game searches and plays `moves` more moves (blocking)."""
+        from . import capi
+        capi._check(self.lib, self.lib.maru_selfplay_run(self.handle, moves), 'maru_selfplay_run')
+
+    def stats(self):
+        import ctypes as C
+        from . import capi
+        st = capi.SelfPlayStats()
+        self.lib.maru_selfplay_get_stats(self.handle, C.byref(st))
+        return st
+
+    def moves(self, game: int) -> List[Tuple[int, int]]:
+        import numpy as np
+        n = self.lib.maru_selfplay_get_moves(self.handle, game, None, 0)
+        xy = np.zeros((max(n, 1), 2), np.int16)
+        self.lib.maru_selfplay_get_moves(self.handle, game, xy.ctypes.data, n)
+        return [(int(xy[i, 0]), int(xy[i, 1])) for i in range(n)]
+
+    def candidates(self, game: int, move: int) -> List[Move]:
+        from . import capi
+        arr = (capi.CandidateRec * 400)()
+        n = self.lib.maru_selfplay_get_candidates(self.handle, game, move, arr, 400)
+        return [Move(arr[i].x, arr[i].y, arr[i].visits, arr[i].value, arr[i].color, arr[i].playouts, arr[i].prior)
+                for i in range(max(n, 0))]
 
 
 def visits_per_sec(agg) -> float:

@@ -90,7 +90,8 @@ def load(kind: str = 'board'):
     """kind: 'board' (no libtorch), 'nn' (reference libtorch runtime), 'dropin' (reference search
     and queue linked against the substitute deepgo::Model that calls libmaru_b200.so) or
     'dropin_states' (reference search + Evaluator.h with the substitute Processor / Evaluator.cpp
-    that send compact maru_state records)."""
+    that send compact maru_state records) or 'search_synth' (the same reference search objects over the
+    synthetic CPU evaluator of oracle/synth_eval.c: the oracle of the native search)."""
     if kind in _libs:
         return _libs[kind]
     path = REF_DIR / f'libmaru_ref_{kind}.so'
@@ -242,12 +243,13 @@ class RefPlayer:
     def evaluate(self, visits: int, playouts: int = 0, timelimit: float = 600.0,
                  equally: bool = False, use_ucb1: bool = False, width: int = 0,
                  temperature: float = 1.0, noise: float = 0.0):
-        ints = np.zeros((512, 4), np.int32)
+        ints = np.zeros((512, 5), np.int32)
         floats = np.zeros((512, 2), np.float32)
         n = self.lib.ref_player_evaluate(self.ptr, visits, playouts, timelimit, int(equally),
                                          int(use_ucb1), width, temperature, noise, ints, floats, 512)
         return [dict(x=int(ints[i, 0]), y=int(ints[i, 1]), visits=int(ints[i, 2]),
-                     playouts=int(ints[i, 3]), policy=float(floats[i, 0]), value=float(floats[i, 1]))
+                     playouts=int(ints[i, 3]), color=int(ints[i, 4]), policy=float(floats[i, 0]),
+                     value=float(floats[i, 1]))
                 for i in range(n)]
 
 

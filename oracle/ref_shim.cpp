@@ -118,7 +118,7 @@ void ref_player_initialize(void* p) { ((deepgo::Player*)p)->initialize(); }
 int ref_player_play(void* p, int x, int y) { return ((deepgo::Player*)p)->play(x, y); }
 int ref_player_get_color(void* p) { return ((deepgo::Player*)p)->getColor(); }
 // One search: startEvaluation + waitEvaluation(visits) + getCandidates (player.py:295-366).
-// Writes up to max_c candidates as (x, y, visits, playouts) int32 and (policy, value) float.
+// Writes up to max_c candidates as (x, y, visits, playouts, color) int32 and (policy, value) float.
 int ref_player_evaluate(void* pp, int visits, int playouts, float timelimit, int equally,
                         int use_ucb1, int width, float temperature, float noise, int32_t* ints,
                         float* floats, int max_c) {
@@ -129,10 +129,11 @@ int ref_player_evaluate(void* pp, int visits, int playouts, float timelimit, int
   int n = 0;
   for (auto& c : cands) {
     if (n >= max_c) break;
-    ints[n * 4 + 0] = c.getX();
-    ints[n * 4 + 1] = c.getY();
-    ints[n * 4 + 2] = c.getVisits();
-    ints[n * 4 + 3] = c.getPlayouts();
+    ints[n * 5 + 0] = c.getX();
+    ints[n * 5 + 1] = c.getY();
+    ints[n * 5 + 2] = c.getVisits();
+    ints[n * 5 + 3] = c.getPlayouts();
+    ints[n * 5 + 4] = c.getColor();
     floats[n * 2 + 0] = c.getPolicy();
     floats[n * 2 + 1] = c.getValue();
     n++;

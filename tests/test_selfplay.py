@@ -62,7 +62,8 @@ class ScriptedPlayer:
 def test_gumbel_root_picks_the_best_and_halves():
     p = ScriptedPlayer(32, seed=1, game_len=10)
     p.initialize()
-    mv, total = selfplay.gumbel_root_search(selfplay.PlayerAdapter(p), visits=80, width=16, noise=1.0)
+    mv, cands = selfplay.gumbel_root_search(selfplay.PlayerAdapter(p), visits=80, width=16, noise=1.0)
+    total = sum(c.visits for c in cands)
     widths = [c[3] for c in p.calls]
     targets = [c[1] for c in p.calls]
     assert widths == [16, 8, 4, 2, 1] and targets == [16, 32, 48, 64, 80]
@@ -86,8 +87,8 @@ def test_scheduler_runs_sharded_games_and_counts_new_visits():
         stats.append(st)
         for rec in s.records:
             assert rec.finished and len(rec.moves) == 8 and rec.moves[-2:] == [(-1, -1), (-1, -1)]
-            # 6 searched moves; tree reuse: every move after the first inherits best.visits - 1
-            assert 0 < rec.visits <= 6 * 40
+            # 6 searched moves of exactly 40 descents each, on top of the inherited subtree
+            assert rec.visits == 6 * 40
     assert sorted(made) == [0, 1, 2, 3, 4]
     agg = shard.reduce_stats(shard.RankStats(visits=sum(s.visits for s in stats),
                                              wall_s=max(s.wall_s for s in stats)))
@@ -99,8 +100,8 @@ def test_scheduler_runs_sharded_games_and_counts_new_visits():
 def test_pucb_root_and_error_propagation():
     p = ScriptedPlayer(8, seed=3, game_len=2)
     p.initialize()
-    mv, total = selfplay.pucb_root_search(selfplay.PlayerAdapter(p), visits=20)
-    assert p.calls[-1][2] is False and p.calls[-1][3] == 0 and total == 20 and mv is not None
+    mv, cands = selfplay.pucb_root_search(selfplay.PlayerAdapter(p), visits=20)
+    assert p.calls[-1][2] is False and p.calls[-1][3] == 0 and sum(c.visits for c in cands) == 20 and mv is not None
 
     class Broken(ScriptedPlayer):
         def evaluate(self, **kw):
