@@ -303,6 +303,8 @@ typedef struct maru_selfplay_config {
 typedef struct maru_selfplay_stats {
   uint64_t visits;                      /* root descents (Player.cpp:300)                              */
   uint64_t evals;                       /* leaves evaluated by the network                             */
+  uint64_t expansions;                  /* nodes visited twice: their candidate filter (seki-aware legality +
+                                           territory, Evaluator.cpp:60-68) ran; the other leaves never needed it */
   uint64_t moves, games_finished;
   uint64_t submits;                     /* asynchronous batches handed to the queue                    */
   uint64_t max_submit;                  /* largest of them                                             */

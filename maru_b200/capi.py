@@ -57,7 +57,7 @@ class SelfPlayConfig(C.Structure):
 
 
 class SelfPlayStats(C.Structure):
-    _fields_ = [('visits', C.c_uint64), ('evals', C.c_uint64), ('moves', C.c_uint64),
+    _fields_ = [('visits', C.c_uint64), ('evals', C.c_uint64), ('expansions', C.c_uint64), ('moves', C.c_uint64),
                 ('games_finished', C.c_uint64), ('submits', C.c_uint64), ('max_submit', C.c_uint64),
                 ('run_s', C.c_double), ('host_s', C.c_double), ('stall_s', C.c_double)]
 

@@ -23,10 +23,18 @@
 //   * backup: the leaf's value is added to every node of the path, playouts too   Player.cpp:332-346
 //   * Player::play keeps the chosen child's subtree, drops the rest               Player.cpp:93-115
 //   * candidates, policy fallback and pass                                         Player.cpp:229-261
+//   * the candidate moves of a node = legal (seki-checked) and not decided territory, with the
+//     network's prior of that cell, not renormalised                                Evaluator.cpp:55-72
 // All arithmetic is done in the same types (float / double promotions) as the reference's
 // expressions, so a deterministic evaluator gives bit-identical trees.
 // Not kept: the per-node shared_mutexes (one descent in flight per game: the reference's threads = 1)
 // and the process-wide random engine (one seeded engine per game: self-play is reproducible).
+// LAZY LEGALITY: Evaluator::evaluate filters the candidate moves of every evaluated node (seki-aware
+// legality + Benson territory, Evaluator.cpp:60-68; ~80 % of the host time per leaf even on the flat
+// board), but a node's candidates are only ever read on its SECOND visit (Node.cpp:81-89) and most leaves
+// of a 50-visit search are visited once.  A leaf is therefore sent WITHOUT a move mask, the network's
+// whole prior plane is parked in the node, and the filter runs when the node is first expanded.  The
+// priors are not renormalised by the reference, so the candidate list is bit-identical either way.
 #pragma once
 
 #include <cmath>
@@ -72,7 +80,9 @@ struct TreeNode {
   float prior = 0.0f;
   bool evaluated = false;
   float net_value = 0.0f;               // Evaluator::getValue(): black's point of view, in [-1, 1]
-  std::vector<Prior> moves;             // Node::_childPolicies
+  std::vector<Prior> moves;             // Node::_childPolicies (built on the second visit, see below)
+  std::vector<float> plane;             // the network's prior of every cell, until `moves` is built
+  bool moves_built = false;
   struct Edge {
     int32_t cell, node;
   };
@@ -96,6 +106,8 @@ struct TreeNode {
     evaluated = false;
     net_value = 0.0f;
     moves.clear();
+    plane.clear();
+    moves_built = false;
     kids.clear();
     waiting.clear();
     visits = playouts = count = 0;
@@ -127,7 +139,6 @@ class GameSearch {
     r.reset_stats();
     path_.clear();
     pending_ = -1;
-    want_root_eval_ = false;
   }
 
   const TreeNode& root() const { return pool_[root_]; }
@@ -184,16 +195,14 @@ class GameSearch {
   // The network's answer for the record advance() / need_root() produced last.
   void deliver(const maru_state& st, const maru_leaf& leaf) {
     TreeNode& n = pool_[pending_];
-    const int w = st.width, cells = st.width * st.height;
+    const int cells = st.width * st.height;
     n.moves.clear();
-    for (int cell = 0; cell < cells; cell++)
-      if ((st.move_mask[cell >> 3] >> (cell & 7)) & 1u)
-        n.moves.push_back(Prior{(int16_t)(cell % w), (int16_t)(cell / w), leaf.prior[cell], 0});
+    n.plane.assign(leaf.prior, leaf.prior + cells);
+    n.moves_built = false;
     const float win = leaf.value;                                                 // Evaluator.cpp:75-80
     n.net_value = (st.color == MARU_WHITE) ? 1.0f - 2.0f * win : 2.0f * win - 1.0f;
     n.evaluated = true;
     pending_ = -1;
-    want_root_eval_ = false;
     evals_++;
   }
 
@@ -203,12 +212,11 @@ class GameSearch {
     TreeNode& r = pool_[root_];
     if (!r.kids.empty() || r.evaluated) return false;
     request(root_, st);
-    want_root_eval_ = true;
     return true;
   }
 
-  void candidates(std::vector<Candidate>* out) const {
-    const TreeNode& r = pool_[root_];
+  void candidates(std::vector<Candidate>* out) {
+    TreeNode& r = pool_[root_];
     out->clear();
     for (const TreeNode::Edge& e : r.kids) {
       const TreeNode& c = pool_[e.node];
@@ -216,6 +224,7 @@ class GameSearch {
     }
     if (!out->empty()) return;
     int bx = -1, by = -1;                                                         // Node::getPolicyMove
+    build_moves(r);
     if (!r.moves.empty()) {
       const Prior* best = &r.moves[0];
       for (const Prior& q : r.moves)
@@ -245,6 +254,7 @@ class GameSearch {
 
   uint64_t descents() const { return descents_; }
   uint64_t evals() const { return evals_; }
+  uint64_t masks() const { return masks_; }     // nodes whose candidate filter actually ran
 
  private:
   SearchSetup setup_;
@@ -255,8 +265,7 @@ class GameSearch {
   int root_ = -1;
   std::vector<int> path_;
   int pending_ = -1;
-  bool want_root_eval_ = false;
-  uint64_t descents_ = 0, evals_ = 0;
+  uint64_t descents_ = 0, evals_ = 0, masks_ = 0;
   std::minstd_rand0 rng_;               // the reference's std::default_random_engine (Node.cpp:11-12)
   std::vector<std::pair<int, float>> scratch_;
 
@@ -294,8 +303,25 @@ class GameSearch {
 
   void request(int id, maru_state* st) {
     const TreeNode& n = pool_[id];
-    n.pos.to_state(-n.color, setup_.komi, setup_.rule, setup_.superko, /*with_move_mask=*/true, st);
+    n.pos.to_state(-n.color, setup_.komi, setup_.rule, setup_.superko, /*with_move_mask=*/false, st);
     pending_ = id;
+  }
+
+  // Evaluator.cpp:55-72, deferred to the node's first expansion: candidate = legal with the seki veto and
+  // outside decided territory; prior = the network's output at that cell, in cell order, not renormalised.
+  void build_moves(TreeNode& n) {
+    if (n.moves_built) return;
+    n.moves_built = true;
+    const int w = setup_.width, cells = setup_.width * setup_.height;
+    uint8_t mask[48];
+    maru_b200::LeanRules rules(n.pos.board);
+    rules.move_mask(-n.color, mask);
+    n.moves.clear();
+    for (int cell = 0; cell < cells; cell++)
+      if ((mask[cell >> 3] >> (cell & 7)) & 1u)
+        n.moves.push_back(Prior{(int16_t)(cell % w), (int16_t)(cell / w), n.plane[(size_t)cell], 0});
+    n.plane.clear();
+    masks_++;
   }
 
   float lcb(const TreeNode& c) const {                                            // Node::getValueLCB
@@ -324,7 +350,9 @@ class GameSearch {
     n.visits += 1;
     *next = -1;
     *playouts = 1;
-    if (n.visits == 1 || n.moves.empty()) return;
+    if (n.visits == 1) return;
+    build_moves(n);
+    if (n.moves.empty()) return;
     const int bw = setup_.width;
 
     // --- widening: which move deserves to be a child next

@@ -425,6 +425,7 @@ int maru_selfplay_get_stats(maru_selfplay* sp, maru_selfplay_stats* st) {
   for (auto& r : sp->games) {
     st->visits += r->visits_done;
     st->evals += r->search.evals();
+    st->expansions += r->search.masks();
     st->moves += r->moves_done;
     st->games_finished += r->games_done + (r->finished ? 1 : 0);
   }

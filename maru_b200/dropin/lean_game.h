@@ -56,8 +56,18 @@ struct LeanGame {
     st->komi = komi;
 
     LeanRules rules(board);                       // group labelling: liberties per stone
+    // Board::_updateShicho: only groups in atari are read out (Board.cpp:1045-1067); the labelling above
+    // already knows them, so the board is not flood-filled a second time (LeanBoard::ladder_flags does)
     uint8_t ladder[361];
-    board.ladder_flags(ladder);
+    std::memset(ladder, 0, (size_t)(w * h));
+    for (int idx = 0; idx < board.N; idx++) {
+      if (rules.gid[idx] != idx || rules.n_libs[idx] != 1) continue;
+      if (!board.ladder(idx)) continue;
+      for (int i = 0; i < rules.n_stones[idx]; i++) {
+        const int p = rules.stone_pool[rules.stone_off[idx] + i];
+        ladder[(p / board.W - 1) * w + (p % board.W - 1)] = 1;
+      }
+    }
     for (int y = 0; y < h; y++) {
       for (int x = 0; x < w; x++) {
         const int idx = board.index(x, y);

@@ -97,7 +97,7 @@ struct LeanRules {
   int16_t gid[LeanBoard::MAXN];
   int16_t n_libs[LeanBoard::MAXN];       // per group id
   int16_t n_stones[LeanBoard::MAXN];
-  int32_t lib_off[LeanBoard::MAXN];      // per group id: offset of its sorted liberty list in lib_pool
+  int32_t lib_off[LeanBoard::MAXN];      // per group id: offset of its liberty list in lib_pool (unordered)
   int32_t stone_off[LeanBoard::MAXN];
   int16_t lib_pool[4 * 361 + 8];
   int16_t stone_pool[361 + 8];
@@ -107,21 +107,43 @@ struct LeanRules {
     d[1] = -b.W;
     d[2] = 1;
     d[3] = b.W;
-    for (int i = 0; i < b.N; i++) gid[i] = (b.c[i] == LeanBoard::kEdge) ? -2 : -1;
-    int lp = 0, sp = 0;
-    LeanBoard::Group g;
+    // One pass over the board: cells are scanned in ascending order, so the first unlabelled stone of a group
+    // is its smallest cell = its id.  lib_mark[q] == id says "q is already counted as a liberty of this group".
+    int16_t lib_mark[LeanBoard::MAXN];
     for (int i = 0; i < b.N; i++) {
-      if ((b.c[i] != LeanBoard::kBlack && b.c[i] != LeanBoard::kWhite) || gid[i] >= 0) continue;
-      b.group(i, g);
-      int id = g.stones[0];
-      for (int k = 1; k < g.n_stones; k++) id = std::min<int>(id, g.stones[k]);
-      for (int k = 0; k < g.n_stones; k++) gid[g.stones[k]] = (int16_t)id;
-      n_libs[id] = (int16_t)g.n_libs;
-      n_stones[id] = (int16_t)g.n_stones;
+      gid[i] = (b.c[i] == LeanBoard::kEdge) ? -2 : -1;
+      lib_mark[i] = -1;
+    }
+    int lp = 0, sp = 0;
+    int16_t stack[361];
+    for (int i = 0; i < b.N; i++) {
+      const int8_t col = b.c[i];
+      if ((col != LeanBoard::kBlack && col != LeanBoard::kWhite) || gid[i] >= 0) continue;
+      const int id = i;
       lib_off[id] = lp;
       stone_off[id] = sp;
-      for (int k = 0; k < g.n_libs; k++) lib_pool[lp++] = g.libs[k];
-      for (int k = 0; k < g.n_stones; k++) stone_pool[sp++] = g.stones[k];
+      int top = 0;
+      stack[top++] = (int16_t)i;
+      gid[i] = (int16_t)id;
+      while (top > 0) {
+        const int p = stack[--top];
+        stone_pool[sp++] = (int16_t)p;
+        for (int k = 0; k < 4; k++) {
+          const int q = p + d[k];
+          const int8_t cq = b.c[q];
+          if (cq == LeanBoard::kEmpty) {
+            if (lib_mark[q] != id) {
+              lib_mark[q] = (int16_t)id;
+              lib_pool[lp++] = (int16_t)q;
+            }
+          } else if (cq == col && gid[q] < 0) {
+            gid[q] = (int16_t)id;
+            stack[top++] = (int16_t)q;
+          }
+        }
+      }
+      n_libs[id] = (int16_t)(lp - lib_off[id]);
+      n_stones[id] = (int16_t)(sp - stone_off[id]);
     }
   }
   int color_of(int cell) const { return b.c[cell]; }     // kEmpty / kBlack / kWhite / kEdge
@@ -371,17 +393,21 @@ struct LeanRules {
           if (checks[pos]) continue;
           checks[pos] = true;
           area_id[c][pos] = (int16_t)index;
-          Ids4 around;
-          for (int a : d) {
-            const int t = pos + a;
-            if (gid[t] >= 0 && b.c[t] == col) around.insert(gid[t]);
+          // once the area is known to be undecided only the labelling is left (flags of other cells of the
+          // area are never read: area_flag is looked up through area_id, i.e. at `index` only)
+          if (area_flag[c][index]) {
+            Ids4 around;
+            for (int a : d) {
+              const int t = pos + a;
+              if (gid[t] >= 0 && b.c[t] == col) around.insert(gid[t]);
+            }
+            if (around.n == 0) area_flag[c][pos] = false;
+            if (around != connected) area_flag[c][index] = false;
           }
-          if (around.n == 0) area_flag[c][pos] = false;
-          if (around != connected) area_flag[c][index] = false;
           for (int a : d) {
             const int t = pos + a;
             const int tc = b.c[t];
-            if (tc == LeanBoard::kEmpty || tc == op) stack[sp++] = (int16_t)t;
+            if ((tc == LeanBoard::kEmpty || tc == op) && !checks[t]) stack[sp++] = (int16_t)t;
           }
         }
         if (area_flag[c][index]) {
