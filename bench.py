@@ -60,8 +60,8 @@ def parse():
     ap.add_argument('--sustained-s', type=float, default=2.0)
     ap.add_argument('--sp-board', type=int, default=19)
     ap.add_argument('--sp-visits', type=int, default=50, help='descents per move (reference default --visits 50)')
-    ap.add_argument('--sp-moves', type=int, default=4, help='timed moves per game (after 1 untimed move)')
-    ap.add_argument('--sp-games-per-thread', type=int, default=64)
+    ap.add_argument('--sp-moves', type=int, default=8, help='timed moves per game (after 1 untimed move)')
+    ap.add_argument('--sp-games-per-thread', type=int, default=128)
     ap.add_argument('--sp-opening', type=int, default=-1, help='random opening moves (-1: board*board/6)')
     ap.add_argument('--sp-root', default='pucb', choices=['pucb', 'gumbel'])
     ap.add_argument('--sp-threads', type=int, default=0, help='search threads per rank (0: this rank\'s cores - 1)')
