@@ -13,7 +13,7 @@
 // ladder read-out is lean.  This header restates them over LeanBoard (lean_ladder.h): groups are labelled
 // once per position, sets are small sorted arrays.  The result must be IDENTICAL on every cell (it decides
 // which moves the search may expand), so every quirk is kept: the 9-cell cut-offs, the exact nakade
-// vital-point count with its corner rule, "an area is decided only if EVERY cell of it touches exactly the
+// vital-point count with its corner rule (as a lookup over 4x4 window masks), "an area is decided only if EVERY cell of it touches exactly the
 // own groups its first cell touches", and the iteration that un-decides groups with fewer than two
 // decided areas.  tests/test_lean_rules.py compares against the compiled reference.
 #pragma once
@@ -149,53 +149,76 @@ struct LeanRules {
   int color_of(int cell) const { return b.c[cell]; }     // kEmpty / kBlack / kWhite / kEdge
 
   // ---------------------------------------------------------------- Board::_isNakade (Board.cpp:1480-1591)
+  // "Is there a vital point": the shape (<= 6 cells inside a 4x4 window) is a 16-bit mask and the answer for
+  // shapes that touch no board corner comes from a table over all 65 536 masks (NakadeTable below, filled
+  // once by the same rule); shapes with a corner cell are evaluated directly.
   bool is_nakade(const IdxSet& positions) const {
-    const int length = 5;
-    const int arounds[4] = {1, -1, length, -length};
-    const int horizontals[4] = {1, -1, 1, -1};
-    const int verticals[4] = {length, length, -length, -length};
     if (positions.n == 0 || positions.n >= 7) return false;
-    int start_x = b.w, start_y = b.h, end_x = 0, end_y = 0;
+    int x0 = b.w, y0 = b.h, x1 = 0, y1 = 0;
     for (int k = 0; k < positions.n; k++) {
       const int x = positions.v[k] % b.W - 1, y = positions.v[k] / b.W - 1;
-      start_x = std::min(x, start_x);
-      start_y = std::min(y, start_y);
-      end_x = std::max(x, end_x);
-      end_y = std::max(y, end_y);
+      x0 = std::min(x0, x);
+      y0 = std::min(y0, y);
+      x1 = std::max(x1, x);
+      y1 = std::max(y1, y);
     }
-    if (end_x - start_x > 3 || end_y - start_y > 3) return false;
-    int board[length * length] = {0};
-    int corner[length * length] = {0};
+    if (x1 - x0 > 3 || y1 - y0 > 3) return false;
+    uint32_t shape = 0, corners = 0;
     for (int k = 0; k < positions.n; k++) {
-      const int sx = positions.v[k] % b.W - 1, sy = positions.v[k] / b.W - 1;
-      const int dx = sx - start_x + 1, dy = sy - start_y + 1;
-      // the reference writes board[dy*5+dx] with dx, dy up to 4: inside its 25-cell scratch board
-      board[dy * length + dx] = 1;
-      if ((sx == 0 || sx == b.w - 1) && (sy == 0 || sy == b.h - 1)) corner[dy * length + dx] = 1;
+      const int x = positions.v[k] % b.W - 1, y = positions.v[k] / b.W - 1;
+      const uint32_t bit = 1u << ((y - y0) * 4 + (x - x0));
+      shape |= bit;
+      if ((x == 0 || x == b.w - 1) && (y == 0 || y == b.h - 1)) corners |= bit;
     }
-    for (int y = 1; y < length - 1; y++) {
-      for (int x = 1; x < length - 1; x++) {
-        const int p = y * length + x;
-        if (board[p] != 1) continue;
-        int direct = 0;
-        for (int a : arounds) direct += board[p + a];
-        int skew = 0, corner_conn = 0;
-        for (int i = 0; i < 4; i++) {
-          const int v = verticals[i], h = horizontals[i];
-          if (board[p + v + h] != 1) continue;
-          if (corner_conn == 0 && corner[p + v] == 1 && board[p + v] == 1) {
-            corner_conn = 1;
-          } else if (corner_conn == 0 && corner[p + h] == 1 && board[p + h] == 1) {
-            corner_conn = 1;
-          } else if (skew == 0 && board[p + v] == 1 && board[p + h] == 1) {
-            skew = 1;
+    return corners == 0 ? NakadeTable::get().test(shape) : nakade_shape(shape, corners);
+  }
+
+  // The reference's vital-point rule on a window mask.  A cell of the window's upper-left 3x3 part is vital if
+  // (orthogonal neighbours in the shape) + (one diagonal neighbour reached around a filled elbow, counted
+  // once) + (one diagonal neighbour reached through a board-corner cell, counted once) >= size - 1.  The
+  // diagonals are visited in the reference's order (down-right, down-left, up-right, up-left) because a
+  // diagonal is booked as "corner" before it may be booked as "elbow" (Board.cpp:1557-1576).
+  static bool nakade_shape(uint32_t shape, uint32_t corners) {
+    const auto at = [](uint32_t m, int x, int y) -> bool {
+      return x >= 0 && x < 4 && y >= 0 && y < 4 && ((m >> (y * 4 + x)) & 1u);
+    };
+    const int need = __builtin_popcount(shape) - 1;
+    static const int diag[4][2] = {{1, 1}, {-1, 1}, {1, -1}, {-1, -1}};      // (dx, dy)
+    for (int y = 0; y < 3; y++) {
+      for (int x = 0; x < 3; x++) {
+        if (!at(shape, x, y)) continue;
+        int links = at(shape, x + 1, y) + at(shape, x - 1, y) + at(shape, x, y + 1) + at(shape, x, y - 1);
+        bool elbow = false, via_corner = false;
+        for (const auto& dg : diag) {
+          const int dx = dg[0], dy = dg[1];
+          if (!at(shape, x + dx, y + dy)) continue;
+          if (!via_corner && at(corners, x, y + dy)) {
+            via_corner = true;
+          } else if (!via_corner && at(corners, x + dx, y)) {
+            via_corner = true;
+          } else if (!elbow && at(shape, x, y + dy) && at(shape, x + dx, y)) {
+            elbow = true;
           }
         }
-        if (direct + skew + corner_conn >= positions.n - 1) return true;
+        if (links + (elbow ? 1 : 0) + (via_corner ? 1 : 0) >= need) return true;
       }
     }
     return false;
   }
+
+  struct NakadeTable {
+    uint64_t bits[1024];
+    NakadeTable() {
+      std::memset(bits, 0, sizeof bits);
+      for (uint32_t m = 1; m < 65536u; m++)
+        if (__builtin_popcount(m) < 7 && nakade_shape(m, 0)) bits[m >> 6] |= 1ull << (m & 63);
+    }
+    bool test(uint32_t m) const { return (bits[m >> 6] >> (m & 63)) & 1ull; }
+    static const NakadeTable& get() {
+      static const NakadeTable t;
+      return t;
+    }
+  };
 
   // ---------------------------------------------------------------- Board::_isSingleArea (Board.cpp:1599-1631)
   bool is_single_area(const IdxSet& positions, int color, int excluded) const {
