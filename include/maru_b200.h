@@ -155,16 +155,15 @@ int  maru_eval_debug_planes(maru_eval* e, int which, float* out, int n, int chan
 /* Pre-softmax policy logits of the last forward: [n][2][361] fp32 (north_star tolerance is on logits). */
 int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 /* Debug knobs. key 0: stop the launch sequence after `value` trunk launches (<0: run everything;
- * the heads then do not run). key 1: bit0 = disable programmatic dependent launch (A/B timing), bit2 = use the legacy
- * mma.sync attention kernel instead of the tcgen05 one (A/B), bit3 = enable the experimental
- * per-tile cross-layer flags (a conv waits only for the producer tiles it reads; measured slower),
+ * the heads then do not run). key 1 (bit mask): bit0 = disable programmatic dependent launch (A/B timing),
  * bit4 = conv_gemm instead of the K-split (3x3, 128 input channels) and wide (1x1, 256 -> k*256) kernels (A/B),
  * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
  * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
- * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on 148 SMs), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B),
- * bits 8-17 = timing experiments inside the flow kernels (tools/flow_ab.py; results are WRONG with any of
- * them set): 8 fence in the storing warps, 10 no dependency waits, 11 no slab loads, 12 no neighbour-flag waits,
- * 13 no MMAs, 14 no stores, 15 no epilogue work at all. */
+ * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on
+ * 148 SMs), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B).
+ * Only in -DMARU_EXPERIMENTS builds of the library (not the product build): bit2 = the v1 mma.sync attention
+ * kernel, bit3 = per-tile cross-layer flags in conv_gemm (measured slower), bits 8-17 = timing experiments inside
+ * the flow kernels (tools/flow_ab.py; results are WRONG with any of them set). */
 #define MARU_DBG_STOP_AFTER 0
 #define MARU_DBG_DESC_BITS 1
 #define MARU_DBG_TRACE_LAUNCH 2       /* index of the trunk launch whose pipeline is traced (-1: off) */

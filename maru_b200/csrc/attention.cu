@@ -6,7 +6,8 @@
 // src/deepgo/native/cpp/Model.cpp:96).  Q is pre-scaled by log2(e)/sqrt(d) in the folded QKV
 // weights (maru_b200/convert.py) so the softmax is a bare exp2.
 //
-// v1 implementation: warp-level online softmax with QK^T / PV on the tensor cores through
+// The product kernel is attention_tc_kernel below (tcgen05 / TMEM).  The v1 implementation it replaced is kept
+// for A/B measurements in -DMARU_EXPERIMENTS builds only: warp-level online softmax with QK^T / PV through
 // mma.sync.m16n8k16 (bf16 in, fp32 accumulate).  One CTA = (position, head): the head's K and V
 // planes (400 padded rows x d) are bulk-copied to shared memory once — in the chunk-planar layout a
 // plane slice of one position is a single contiguous 6 400-byte run — and 5 warps sweep the 25
@@ -18,6 +19,7 @@
 
 namespace maru {
 
+#ifdef MARU_EXPERIMENTS   // v1 (mma.sync) kernel: A/B reference for the tcgen05 kernel below, not in the product build
 constexpr int ATT_WARPS = 5;
 constexpr int ATT_THREADS = ATT_WARPS * 32;
 constexpr int ATT_KB = 80;  // keys per online-softmax block (10 n8 tiles)
@@ -200,6 +202,8 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
     }
   }
 }
+
+#endif  // MARU_EXPERIMENTS
 
 // =============================================================================================
 // v2: tcgen05 / TMEM attention for head_dim 32.
@@ -602,38 +606,38 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
   }
 }
 
+#ifdef MARU_EXPERIMENTS
 template <int D>
 static constexpr int attn_smem_bytes() { return 2 * (D / 8) * POS_ROWS * 16 + 512 + 16; }
+#endif
 
 cudaError_t configure_attention() {
-  cudaError_t e = cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       attn_smem_bytes<32>());
+  cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A2_SMEM);
-  if (e != cudaSuccess) return e;
-  cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+#ifdef MARU_EXPERIMENTS
+  cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<32>());
   cudaFuncSetAttribute(attention_kernel<32>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-  return cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              attn_smem_bytes<64>());
+  cudaFuncSetAttribute(attention_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, attn_smem_bytes<64>());
+#endif
+  return e;
 }
 
+// head_dim 32 only (every BASELINE.json config): the engine refuses other packs at load time.
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   const int heads = p.channels / p.head_dim;
-  if (p.head_dim == 32 && !(p.dbg & 2)) {  // dbg bit1: legacy mma.sync kernel (A/B)
-    return launch_kernel(attention_tc_kernel, dim3(p.n * heads), dim3(A2_THREADS), A2_SMEM, stream,
+#ifdef MARU_EXPERIMENTS
+  if (p.head_dim == 32 && (p.dbg & 2))     // dbg bit1: v1 mma.sync kernel (A/B)
+    return launch_kernel(attention_kernel<32>, dim3(p.n * heads), dim3(ATT_THREADS), attn_smem_bytes<32>(), stream,
                          p.pdl != 0, p);
-  } else if (p.head_dim == 32) {
-    return launch_kernel(attention_kernel<32>, dim3(p.n * heads), dim3(ATT_THREADS), attn_smem_bytes<32>(),
-                         stream, p.pdl != 0, p);
-  } else if (p.head_dim == 64) {
-    return launch_kernel(attention_kernel<64>, dim3(p.n * heads), dim3(ATT_THREADS), attn_smem_bytes<64>(),
-                         stream, p.pdl != 0, p);
-  } else {
-    return cudaErrorInvalidValue;
-  }
-  return cudaGetLastError();
+  if (p.head_dim == 64)
+    return launch_kernel(attention_kernel<64>, dim3(p.n * heads), dim3(ATT_THREADS), attn_smem_bytes<64>(), stream,
+                         p.pdl != 0, p);
+#endif
+  if (p.head_dim != 32) return cudaErrorInvalidValue;
+  return launch_kernel(attention_tc_kernel, dim3(p.n * heads), dim3(A2_THREADS), A2_SMEM, stream, p.pdl != 0, p);
 }
 
 }  // namespace maru

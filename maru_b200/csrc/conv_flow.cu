@@ -26,10 +26,20 @@
 // is only issued when a CTA starts its last layer, so no later kernel can occupy an SM before every CTA of
 // the chain is resident.  All waits are bounded (MARU_SPIN_LIMIT) and trap instead of hanging.
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "conv_cfg.cuh"
 
 namespace maru {
+
+// Timing experiments inside the kernel (FlowParams::dbg, tools/flow_ab.py: no dependency waits, no MMAs, no
+// stores, ... — results are WRONG with any of them) exist only in -DMARU_EXPERIMENTS builds; the product
+// build folds the bits to 0 and the branches disappear.
+#ifdef MARU_EXPERIMENTS
+#define FLOW_DBG(fp) ((fp).dbg)
+#else
+#define FLOW_DBG(fp) 0
+#endif
 
 constexpr int FLOW_THREADS = 448;     // warp 0 producer, 1 and 10 MMA issue, 2..9 epilogue, 11 weights, 12 and 13 publishers
 constexpr int FLOW_SMEM = 232448;     // 227 KB
@@ -179,7 +189,7 @@ __device__ __noinline__ void flow_producer(const FlowParams& fp, uint32_t c_smem
   const unsigned flag_base = fp.flag_base;
   const uint32_t area_bytes = (uint32_t)fp.area;
   const size_t pstride = (size_t)fp.rows_alloc * 8;
-  const int dbg = fp.dbg;
+  const int dbg = FLOW_DBG(fp);
   long long* const stamps = (c.cta == 0) ? fp.stamps : nullptr;
   uint32_t g = 0, head = 0;
   uint32_t o1 = 0, e1 = 0, o2 = 0, e2 = 0, o3 = 0, e3 = 0;
@@ -297,7 +307,7 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, uint32_t c_smem, uin
   const uint32_t r_hi = (uint32_t)(r_d >> 32);
   const uint32_t ones_lo = (uint32_t)r_d + (ones >> 4);
   const int n_layers = fp.n_layers;
-  const int dbg = fp.dbg;
+  const int dbg = FLOW_DBG(fp);
   const uint32_t w_region = (uint32_t)fp.w_region;
   long long* const stamps = (c.cta == 0 && mw == 0) ? fp.stamps : nullptr;
   uint32_t g = 0;
@@ -507,7 +517,7 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
   const uint32_t mask = c.ctrl + FLOW_CTRL_BYTES + FLOW_ONES_BYTES;
   const int n_layers = fp.n_layers;
   const size_t rows_alloc = (size_t)fp.rows_alloc;
-  const int dbg = fp.dbg;
+  const int dbg = FLOW_DBG(fp);
   long long* const stamps = (c.cta == 0 && warp == 2 && lane == 0) ? fp.stamps : nullptr;
   uint32_t g = 0;
   for (int l = 0; l < n_layers; l++) {
@@ -713,8 +723,29 @@ cudaError_t launch_conv_flow(FlowParams& fp, int sm_count, cudaStream_t stream) 
   }
   const int n_tiles = (fp.m_rows + TILE_M - 1) / TILE_M;
   if ((n_tiles + sm_count - 1) / sm_count > FLOW_MAX_TILES) return cudaErrorInvalidConfiguration;
-  return launch_kernel(conv_flow_kernel, dim3(sm_count), dim3(FLOW_THREADS), (size_t)FLOW_SMEM, stream,
-                       fp.pdl != 0, fp);
+  // The CTAs wait for each other, so the grid is launched COOPERATIVELY: the runtime makes all of it resident
+  // at once or fails the launch (another process through MPS, an SM-limited context, a long kernel of another
+  // stream holding SMs) and the engine falls back to one launch per layer — instead of a partially resident grid
+  // spinning until its bounded waits give up.  MARU_B200_FLOW_COOP: 2 = cooperative + programmatic dependent launch
+  // (default), 1 = cooperative only, 0 = plain launch (A/B).
+  static const int coop = [] {
+    const char* v = getenv("MARU_B200_FLOW_COOP");
+    return v != nullptr ? atoi(v) : 2;
+  }();
+  if (coop == 0)
+    return launch_kernel(conv_flow_kernel, dim3(sm_count), dim3(FLOW_THREADS), (size_t)FLOW_SMEM, stream, fp.pdl != 0, fp);
+  return launch_kernel_coop(conv_flow_kernel, dim3(sm_count), dim3(FLOW_THREADS), (size_t)FLOW_SMEM, stream,
+                            fp.pdl != 0 && coop == 2, fp);
+}
+
+// how many CTAs of the flow kernel fit one SM right now (0: the kernel cannot run on this device / context)
+int conv_flow_ctas_per_sm() {
+  int n = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, conv_flow_kernel, FLOW_THREADS, (size_t)FLOW_SMEM) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
 }
 
 }  // namespace maru

@@ -341,12 +341,18 @@ static cudaError_t configure_pair_cfg() {
 }
 cudaError_t configure_conv_pair() {
   cudaError_t e = configure_pair_cfg<128, 128>();
+#ifdef MARU_EXPERIMENTS
   if (e != cudaSuccess) return e;
-  return configure_pair_cfg<64, 64>();
+  e = configure_pair_cfg<64, 64>();
+#endif
+  return e;
 }
 
 bool conv_pair_supports(int cin, int cout, int taps) {
-  return taps == CP_TAPS && ((cin == 128 && cout == 128) || (cin == 64 && cout == 64));
+#ifdef MARU_EXPERIMENTS
+  if (taps == CP_TAPS && cin == 64 && cout == 64) return true;
+#endif
+  return taps == CP_TAPS && cin == 128 && cout == 128;
 }
 int conv_pair_blob_nt(int cout) { return cout / 2; }      // output channels per CTA of the pair = blob group width
 
@@ -361,9 +367,11 @@ cudaError_t launch_conv_pair(ConvParams p, int cin, int sm_count, cudaStream_t s
   if (cin == 128 && p.cout_total == 128)
     return launch_kernel(conv_pair_kernel<128, 128>, dim3(2 * clusters), dim3(CP_THREADS), (size_t)PairCfg<128, 128>::SMEM,
                          stream, p.pdl != 0, p);
+#ifdef MARU_EXPERIMENTS   // the 64 -> 64 instantiation is correct but slower than conv_gemm<64,64,9> at every batch size
   if (cin == 64 && p.cout_total == 64)
     return launch_kernel(conv_pair_kernel<64, 64>, dim3(2 * clusters), dim3(CP_THREADS), (size_t)PairCfg<64, 64>::SMEM,
                          stream, p.pdl != 0, p);
+#endif
   return cudaErrorInvalidValue;
 }
 

@@ -16,9 +16,27 @@
 #include <vector>
 
 #include "engine.h"
+#include <nvtx3/nvToolsExt.h>   // header-only; ranges cost nothing unless a profiler is attached
 #include <stdlib.h>
 
 namespace maru {
+
+// NVTX range over a host-side phase (tracing).  Visible in Nsight Systems / ncu --nvtx; the kernels of a
+// forward are captured into a graph, so the ranges mark capture / enqueue / blocking spans, not kernel time.
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+
+// attention_tc_kernel is written for 32-channel heads (every BASELINE.json config); the v1 kernel that also ran
+// 64-channel heads exists in -DMARU_EXPERIMENTS builds only
+static bool head_dim_supported(int d) {
+#ifdef MARU_EXPERIMENTS
+  return d == 32 || d == 64;
+#else
+  return d == 32;
+#endif
+}
 
 thread_local std::string g_last_error;
 void set_error(const std::string& s) { g_last_error = s; }
@@ -277,10 +295,12 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     return 1;
   }
   gpu_id = gpu;
+#ifdef MARU_EXPERIMENTS
   if (const char* pe = getenv("MARU_B200_PAIR64")) {      // "0": never, "N": from batch N up
     pair64_on = pe[0] != '0' || pe[1] != 0;
     if (pair64_on) pair64_min_batch = atoi(pe);
   }
+#endif
   if (const char* ff = getenv("MARU_B200_FLOW")) {
     // "1": the persistent flow kernels at every batch size, "0": never (default: for 249..354 positions on 148 SMs)
     if (ff[0] == '1') dbg_desc |= 128;
@@ -300,6 +320,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   sm_count = prop.multiProcessorCount;
   CK(configure_conv_gemm());
   CK(configure_conv_flow());
+  if (conv_flow_ctas_per_sm() < 1) flow_broken = true;   // the persistent kernels cannot be resident here: per-layer launches
   CK(configure_conv_ksplit());
   CK(configure_conv_wide());
   CK(configure_conv_pair());
@@ -317,7 +338,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   head_dim = pk.hdr.arch[3];
   Ch = pk.hdr.arch[4];
   Cv = pk.hdr.arch[5];
-  if (blocks < 1 || blocks > 64 || C < 64 || C % 64 != 0 || C > 256 || (head_dim != 32 && head_dim != 64) || Ch != 32 ||
+  if (blocks < 1 || blocks > 64 || C < 64 || C % 64 != 0 || C > 256 || !head_dim_supported(head_dim) || Ch != 32 ||
       Cv < 1 || Cv > 128 || attn_every < 0 || attn_every > blocks) {
     set_error("unsupported architecture in weight pack");
     return 1;
@@ -485,7 +506,11 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   // Per-tile cross-layer flags are an EXPERIMENT that lost ("what did not work"): the forward
   // is ~20 % slower with them than with plain grid dependencies, so they are off unless debug bit 3
   // is set; never while profiling (repeated launches of one layer).
+#ifdef MARU_EXPERIMENTS
   const bool use_flags = p.pdl && prof == nullptr && (dbg_desc & 8);
+#else
+  const bool use_flags = false;             // per-tile cross-layer flags: experiment builds only
+#endif
   p.in_flags = (use_flags && in.flagged) ? in.flags : nullptr;
   p.in_expect = in.version;
   p.out_flags = use_flags ? out.flags : nullptr;
@@ -742,6 +767,7 @@ bool Engine::flow_enabled() {
   return flow_live && flow_device_ok();
 }
 bool Engine::flow_device_ok() {
+  if (flow_broken) return false;
   if ((dbg_desc & 32) || dbg_stop_after >= 0 || dbg_timeline || dbg_trace_launch >= 0) return false;
   std::lock_guard<std::mutex> lock(g_dev_mu);
   return gpu_id >= 0 && gpu_id < 64 && g_engines_on_device[gpu_id] == 1;
@@ -842,6 +868,9 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
 int Engine::launch_all(int kind, const void* d_in, void* d_out, int n, const int* n_dev,
                        cudaStream_t st) {
   n_launched = 1;   // the encode / ingest kernel
+  NvtxRange whole("maru.forward.enqueue");
+  {
+  NvtxRange enc("maru.encode");
   if (kind != KIND_PLANES) {
     prof_begin("encode", 0, 0, IN_PLANES, 0, 0.0,
                ((double)sizeof(maru_state) + (double)CELLS * IN_PLANES * 2.0) * n, st);
@@ -854,6 +883,8 @@ int Engine::launch_all(int kind, const void* d_in, void* d_out, int n, const int
     CK(launch_ingest_rows(static_cast<const float*>(d_in), x0.p, mask, rows_alloc, n, n_dev, st));
     prof_end(st);
   }
+  }
+  NvtxRange trunk("maru.trunk+heads");
   const int rc = launch_trunk(kind, d_in, d_out, n, n_dev, st);
   if (rc == 0 && prof == nullptr && dbg_stop_after < 0) launches_per_forward = n_launched;
   return rc;
@@ -872,45 +903,62 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
     set_error("batch larger than max_batch");
     return 1;
   }
-  if (flags & MARU_FLAG_NO_GRAPH) {
-    flow_live = flow_pays(n);
-    if (launch_all(kind, d_in, d_out, n, nullptr, stream)) return 1;
-  } else {
-    // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
-    const int bucket = bucket_for(n, max_batch);
-    flow_live = flow_pays(n);             // by the LIVE batch size: a bucket has a flow graph and a per-layer graph
-    GraphKey key{kind, bucket, d_in, d_out, flow_enabled()};
-    auto it = graphs.find(key);
-    if (it == graphs.end()) {
-      // The cache is keyed by the caller's buffers: a device-API caller that rotates buffers must not grow it
-      // without bound. Graphs still in flight keep running (a cudaGraphExec_t may be destroyed once launched work
-      // has been submitted only after it completes, hence the sync).
-      if (graphs.size() >= 64) {
-        CK(cudaStreamSynchronize(stream));
-        clear_graphs();
-      }
-      cudaGraph_t gr = nullptr;
-      cudaGraphExec_t ex = nullptr;
-      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-      const int rc = launch_all(kind, d_in, d_out, bucket, d_n, stream);
-      cudaError_t ce = cudaStreamEndCapture(stream, &gr);
-      if (rc || ce != cudaSuccess) {
+  // Two attempts: if the persistent flow kernels cannot be launched (the cooperative launch does not fit: the
+  // device is shared), the engine gives them up for good and the forward is enqueued again with one launch per layer.
+  for (int attempt = 0; attempt < 2; attempt++) {
+    flow_live = flow_pays(n);               // by the LIVE batch size: a bucket has a flow graph and a per-layer graph
+    const bool with_flow = flow_enabled();
+    bool ok = true;
+    if (flags & MARU_FLAG_NO_GRAPH) {
+      ok = launch_all(kind, d_in, d_out, n, nullptr, stream) == 0;
+    } else {
+      // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
+      const int bucket = bucket_for(n, max_batch);
+      GraphKey key{kind, bucket, d_in, d_out, with_flow};
+      auto it = graphs.find(key);
+      if (it == graphs.end()) {
+        // The cache is keyed by the caller's buffers: a device-API caller that rotates buffers must not grow it
+        // without bound. Graphs still in flight keep running (a cudaGraphExec_t may be destroyed once launched work
+        // has been submitted only after it completes, hence the sync).
+        if (graphs.size() >= 64) {
+          CK(cudaStreamSynchronize(stream));
+          clear_graphs();
+        }
+        cudaGraph_t gr = nullptr;
+        cudaGraphExec_t ex = nullptr;
+        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = launch_all(kind, d_in, d_out, bucket, d_n, stream);
+        cudaError_t ce = cudaStreamEndCapture(stream, &gr);
+        if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&ex, gr, 0);
         if (gr != nullptr) cudaGraphDestroy(gr);
-        if (rc) return 1;
+        if (rc != 0 || ce != cudaSuccess) {
+          if (rc == 0) set_error(std::string("forward graph: ") + cudaGetErrorString(ce));
+          ok = false;
+        } else {
+          it = graphs.emplace(key, ex).first;
+        }
       }
-      CK(ce);
-      const cudaError_t ie = cudaGraphInstantiate(&ex, gr, 0);
-      if (ie != cudaSuccess) cudaGraphDestroy(gr);
-      CK(ie);
-      cudaGraphDestroy(gr);
-      it = graphs.emplace(key, ex).first;
+      if (ok) {
+        // The live batch size travels BY VALUE as a kernel parameter (fixed at enqueue time): any number of forwards
+        // with different n may be in flight on the stream. (A pinned staging int read by an async copy at execution
+        // time was overwritten by later calls once more than a handful of forwards were outstanding.)
+        set_live_n_kernel<<<1, 1, 0, stream>>>(d_n, n);
+        CK(cudaGetLastError());
+        const cudaError_t le = cudaGraphLaunch(it->second, stream);
+        if (le != cudaSuccess) {
+          set_error(std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
+          cudaGraphExecDestroy(it->second);
+          graphs.erase(it);
+          ok = false;
+        }
+      }
     }
-    // The live batch size travels BY VALUE as a kernel parameter (fixed at enqueue time): any number of forwards
-    // with different n may be in flight on the stream. (A pinned staging int read by an async copy at execution
-    // time was overwritten by later calls once more than a handful of forwards were outstanding.)
-    set_live_n_kernel<<<1, 1, 0, stream>>>(d_n, n);
-    CK(cudaGetLastError());
-    CK(cudaGraphLaunch(it->second, stream));
+    if (ok) break;
+    if (!with_flow || attempt == 1) return 1;
+    cudaGetLastError();                     // launch-configuration errors are not sticky
+    flow_broken = true;                     // flow_device_ok() is false from here on
+    fprintf(stderr, "maru_b200: persistent conv kernels unavailable on GPU %d (%s); using one launch per layer\n",
+            gpu_id, g_last_error.c_str());
   }
   n_forward++;
   n_positions += n;
@@ -920,6 +968,7 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
 // Blocking forward on host buffers: H2D, kernels, D2H (Model::forward, Model.cpp:88-100).
 // `in` / `out` may be pageable (the reference passes stack arrays, Evaluator.cpp:48-49).
 int Engine::forward_host(int kind, const void* in, void* out, int n) {
+  NvtxRange range("maru.forward_host");
   std::lock_guard<std::mutex> lock(mu);
   CK(cudaSetDevice(gpu_id));
   const size_t in_row = in_row_bytes(kind), out_row = out_row_bytes(kind);
@@ -943,6 +992,7 @@ int Engine::forward_host(int kind, const void* in, void* out, int n) {
 }
 
 int Engine::enqueue_slot(int kind, int slot_idx, int n) {
+  NvtxRange range("maru.queue.batch.enqueue");
   std::lock_guard<std::mutex> lock(mu);
   CK(cudaSetDevice(gpu_id));
   Slot& sl = slot[slot_idx];
@@ -959,6 +1009,7 @@ int Engine::enqueue_slot(int kind, int slot_idx, int n) {
 }
 
 int Engine::wait_slot(int slot_idx, float* device_ms) {
+  NvtxRange range("maru.queue.batch.wait");
   Slot& sl = slot[slot_idx];
   CK(cudaEventSynchronize(sl.done));
   if (device_ms) {

@@ -156,6 +156,7 @@ struct Engine {
   int pair64_min_batch = 1;
   bool flow_pays(int n) const;      // enough tiles per CTA for the persistent kernels to win
   bool flow_live = true;            // flow_pays(live batch size) of the forward being enqueued
+  bool flow_broken = false;         // a flow launch failed (cooperative grid does not fit: shared device): never again
   void device_ref(int delta);
   long long* d_stamps = nullptr;    // per-layer %globaltimer stamps of the chains (profiling)
   int stamps_used = 0;

@@ -100,6 +100,7 @@ int conv_flow_area(int w_region);
 bool conv_flow_fits(int cin, int nt, int taps, int w_region);
 // fills w_region / area; returns cudaErrorInvalidConfiguration when a layer does not fit
 cudaError_t launch_conv_flow(FlowParams& fp, int sm_count, cudaStream_t stream);
+int conv_flow_ctas_per_sm();
 
 // ---- 3x3, 128 input channels, half-slab pipeline (conv_ksplit.cu) -----------------------------------
 cudaError_t configure_conv_ksplit();

@@ -24,7 +24,11 @@
 #include <thread>
 #include <vector>
 
+#ifdef MARU_TSAN_STUB_ENGINE
+#include "engine_stub.h"   // `make tsan`: host-only stand-in, see tests/tsan_queue_selfplay.cpp
+#else
 #include "engine.h"
+#endif
 
 namespace maru {
 
