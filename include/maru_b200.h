@@ -133,6 +133,13 @@ int  maru_eval_forward_leaves(maru_eval* e, const maru_state* s, maru_leaf* out,
 int  maru_eval_forward_states_device(maru_eval* e, const maru_state* d_states, float* d_out, int n);
 int  maru_eval_forward_planes_device(maru_eval* e, const float* d_in, float* d_out, int n);
 int  maru_eval_forward_leaves_device(maru_eval* e, const maru_state* d_states, maru_leaf* d_out, int n);
+/* Small boards: a batch whose records all hold the same w x h board (< 19x19) is evaluated on a COMPACT frame after
+ * the stem — (w + 1)(h + 1) rows per position instead of the reference's 400 (it computes all 19x19 cells of the model
+ * frame for every board size, Board.cpp:496-497) — with results equal to the 19x19-frame evaluation up to fp32
+ * summation order.  The host entry points (forward_states / forward_leaves, the queue) read the sizes from the records;
+ * the *_device entry points cannot, so the caller states them here (0, 0 = unknown / mixed: the 19x19 frame).
+ * MARU_B200_COMPACT=0 or debug bit 21 disables the compact frame. */
+int  maru_eval_set_device_board(maru_eval* e, int width, int height);
 int  maru_eval_sync(maru_eval* e);
 void* maru_eval_stream(maru_eval* e);   /* the evaluator's cudaStream_t (for CUDA-event timing)      */
 
@@ -160,7 +167,8 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
  * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
  * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on
- * 148 SMs), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B).
+ * 148 SMs), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B), bit21 = always the 19x19 frame (no
+ * compact frame for small boards, A/B and parity).
  * Only in -DMARU_EXPERIMENTS builds of the library (not the product build): bit2 = the v1 mma.sync attention
  * kernel, bit3 = per-tile cross-layer flags in conv_gemm (measured slower), bits 8-17 = timing experiments inside
  * the flow kernels (tools/flow_ab.py; results are WRONG with any of them set). */

@@ -82,7 +82,7 @@ ABI_SYMBOLS = [
     'maru_queue_get_stats', 'maru_ladder_flags', 'maru_rules_eval', 'maru_game_create', 'maru_game_clone',
     'maru_game_destroy', 'maru_game_play', 'maru_game_state', 'maru_last_error', 'maru_abi_version',
     'maru_queue_submit_leaves', 'maru_queue_poll', 'maru_queue_wait', 'maru_queue_set_coalesce',
-    'maru_selfplay_create', 'maru_selfplay_create_fn', 'maru_selfplay_destroy', 'maru_selfplay_play',
+    'maru_eval_set_device_board', 'maru_selfplay_create', 'maru_selfplay_create_fn', 'maru_selfplay_destroy', 'maru_selfplay_play',
     'maru_selfplay_run', 'maru_selfplay_get_stats', 'maru_selfplay_get_moves', 'maru_selfplay_get_candidates',
 ]
 
@@ -118,6 +118,7 @@ def load_library():
     lib.maru_queue_execute_leaves.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_forward_planes_device.argtypes = [vp, vp, vp, ci]
     lib.maru_eval_sync.argtypes = [vp]
+    lib.maru_eval_set_device_board.argtypes = [vp, ci, ci]
     lib.maru_eval_stream.argtypes = [vp]
     lib.maru_eval_stream.restype = vp
     lib.maru_encode_planes.argtypes = [vp, vp, vp, ci]
@@ -375,6 +376,11 @@ class Evaluator:
         return [dict(name=arr[i].name.decode(), kind=arr[i].kind, cin=arr[i].cin, cout=arr[i].cout,
                      taps=arr[i].taps, ms=arr[i].ms, flops=arr[i].flops, bytes=arr[i].bytes)
                 for i in range(min(cnt.value, 256))]
+
+    def set_device_board(self, width: int, height: int) -> None:
+        """Board size of the records the *_device entry points will be given (0, 0: unknown -> 19x19 frame)."""
+        _check(self.lib, self.lib.maru_eval_set_device_board(self.handle, width, height),
+               'maru_eval_set_device_board')
 
     def sync(self) -> None:
         _check(self.lib, self.lib.maru_eval_sync(self.handle), 'maru_eval_sync')

@@ -235,8 +235,6 @@ constexpr int A2_K_BYTES = A2_DCH * A2_PLANE;
 constexpr int A2_V_BYTES = (A2_DCH + 1) * A2_PLANE;   // + ones plane; the 6th plane aliases P (unused cols)
 constexpr int A2_PN = 80;                   // keys per step
 constexpr int A2_NP = POS_ROWS / A2_PN;     // 5 parts
-constexpr int A2_NT = 3;                    // query tiles
-constexpr int A2_Q0 = PITCH;                // first query row: skip the top halo row of the position
 constexpr int A2_P_BYTES = (A2_PN / 8) * TILE_M * 16; // 20 480 per buffer
 constexpr int A2_Q_BYTES = A2_DCH * TILE_M * 16;
 constexpr int A2_SMEM = A2_K_BYTES + A2_V_BYTES + 2 * A2_P_BYTES + 2 * A2_Q_BYTES + 416 + 32 + 112;
@@ -327,7 +325,15 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
   const int head = blockIdx.x - pos * heads;
   if (pos >= ((p.n_dev != nullptr) ? *p.n_dev : p.n)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const size_t prow0 = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS;
+  // frame geometry (common.cuh): 20 / 400 for the 19x19 frame; a compact frame of a small board has fewer rows, hence
+  // fewer key parts and query tiles (9x9: 100 rows = 2 parts x 1 tile instead of 5 x 3)
+  const int pos_rows = p.pos_rows, q0 = p.pitch;
+  const int kp = (pos_rows + A2_PN - 1) / A2_PN;          // key parts of 80 rows
+  const int plane_rows = kp * A2_PN;                       // rows of one 8-channel plane image in shared memory
+  const int plane_b = plane_rows * 16;                     // (rows >= pos_rows are zero: they are keys like any other)
+  const int nt = (pos_rows - q0 + TILE_M - 1) / TILE_M;   // query tiles, the first starts after the top halo row
+  const bool full = pos_rows == POS_ROWS;
+  const size_t prow0 = (size_t)GUARD_ROWS + (size_t)pos * pos_rows;
   const int cch = p.channels / 8;
   const int q_chunk0 = head * A2_DCH, k_chunk0 = cch + head * A2_DCH, v_chunk0 = 2 * cch + head * A2_DCH;
 
@@ -356,29 +362,29 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     // =========================== control warp: bulk loads + MMA issue ===========================
     auto load_q = [&](int tile) {
       const int buf = tile & 1;
-      const int r0 = A2_Q0 + tile * TILE_M;
+      const int r0 = q0 + tile * TILE_M;
       mbar_expect_tx(&q_full[buf], A2_Q_BYTES);
       for (int c = 0; c < A2_DCH; c++)
         bulk_load_1d(s_q + buf * A2_Q_BYTES + c * TILE_M * 16,
                      p.qkv + ((size_t)(q_chunk0 + c) * p.rows_alloc + prow0 + r0) * 8, TILE_M * 16, &q_full[buf]);
     };
     if (elect_one()) {
-      mbar_expect_tx(kv_full, A2_K_BYTES + A2_DCH * A2_PLANE);
+      mbar_expect_tx(kv_full, 2 * A2_DCH * pos_rows * 16);
       for (int c = 0; c < A2_DCH; c++) {
-        bulk_load_1d(s_k + c * A2_PLANE, p.qkv + ((size_t)(k_chunk0 + c) * p.rows_alloc + prow0) * 8, A2_PLANE, kv_full);
-        bulk_load_1d(s_v + c * A2_PLANE, p.qkv + ((size_t)(v_chunk0 + c) * p.rows_alloc + prow0) * 8, A2_PLANE, kv_full);
+        bulk_load_1d(s_k + c * plane_b, p.qkv + ((size_t)(k_chunk0 + c) * p.rows_alloc + prow0) * 8, pos_rows * 16, kv_full);
+        bulk_load_1d(s_v + c * plane_b, p.qkv + ((size_t)(v_chunk0 + c) * p.rows_alloc + prow0) * 8, pos_rows * 16, kv_full);
       }
       load_q(0);
-      load_q(1);
+      if (nt > 1) load_q(1);
     }
     __syncwarp();
     constexpr uint32_t idesc_qk = umma_idesc_bf16(TILE_M, A2_PN, 0, 0);
     constexpr uint32_t idesc_pv = umma_idesc_bf16(TILE_M, A2_NV, 0, 1);   // B = V is MN-major
     const uint64_t q_d = umma_desc(0, TILE_M * 16, 128);      // Q, P tiles: K-major, LBO = 128 rows
-    const uint64_t k_d = umma_desc(0, A2_PLANE, 128);         // K image:    K-major, LBO = plane
+    const uint64_t k_d = umma_desc(0, plane_b, 128);          // K image:    K-major, LBO = plane
     // V image read transposed (MN-major): SBO = distance between 8-channel planes (N direction),
     // LBO = distance between 8-key groups (K direction)
-    const uint64_t v_d = umma_desc(0, 128, A2_PLANE);
+    const uint64_t v_d = umma_desc(0, 128, plane_b);
     const uint32_t q_hi = (uint32_t)(q_d >> 32), k_hi = (uint32_t)(k_d >> 32), v_hi = (uint32_t)(v_d >> 32);
     const uint32_t k_lo = (uint32_t)k_d + (smem_u32(s_k) >> 4);
     const uint32_t v_lo = (uint32_t)v_d + (smem_u32(s_v) >> 4);
@@ -386,12 +392,25 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     const uint32_t q_lo = (uint32_t)q_d + (smem_u32(s_q) >> 4);
     int np;
     uint32_t plist;
-    {
+    if (full) {
       uint4 m16 = make_uint4(0u, 0u, 0u, 0u);
       if (lane < POS_ROWS / 16) m16 = reinterpret_cast<const uint4*>(p.mask + (size_t)pos * POS_ROWS)[lane];
       a2_active_parts(m16, lane, np, plist);
+    } else {                      // a compact frame has no empty key part
+      np = kp;
+      plist = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
     }
-    const int n_steps = A2_NT * np;
+    const int n_steps = nt * np;
+    // rows past the position in the last key part (compact frames only: 400 = 5 x 80) must be ZERO keys before the
+    // first QK reads them — whatever the previous kernel left there could be Inf / NaN bit patterns, and Inf * 0 (their
+    // V rows are zero) would poison O.  Written here, by the warp that issues the MMAs, and fenced for the async proxy.
+    if (plane_rows > pos_rows) {
+      const int pad = plane_rows - pos_rows;
+      for (int i = lane; i < pad * A2_DCH; i += 32)
+        *reinterpret_cast<uint4*>(s_k + (i / pad) * plane_b + (pos_rows + i % pad) * 16) = make_uint4(0u, 0u, 0u, 0u);
+      fence_async_smem();
+      __syncwarp();
+    }
     mbar_wait(kv_full, 0);
 
     // S[step & 1] = Q(tile) K(part)^T ; the first QK of a tile waits for its Q buffer
@@ -412,13 +431,13 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         const uint32_t qa = q_lo + (tile & 1) * (A2_Q_BYTES >> 4);
         const uint32_t kb = k_lo + part * A2_PN;
         umma_bf16_lohi<0>(t_s, qa, q_hi, kb, k_hi, idesc_qk);
-        umma_bf16_lohi<1>(t_s, qa + 2 * TILE_M, q_hi, kb + 2 * POS_ROWS, k_hi, idesc_qk);
+        umma_bf16_lohi<1>(t_s, qa + 2 * TILE_M, q_hi, kb + 2 * plane_rows, k_hi, idesc_qk);
         umma_commit(&s_full[step & 1]);
       }
       __syncwarp();
     };
     issue_qk(0);
-    issue_qk(1);
+    if (n_steps > 1) issue_qk(1);
     int m_tile = 0, m_pi = 0;
 #pragma unroll 1
     for (int step = 0; step < n_steps; step++) {
@@ -445,7 +464,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       }
       __syncwarp();
       // the last QK of this tile completed before p_full(step): its Q buffer can take tile+2
-      if (pi == np - 1 && tile + 2 < A2_NT && elect_one()) load_q(tile + 2);
+      if (pi == np - 1 && tile + 2 < nt && elect_one()) load_q(tile + 2);
       __syncwarp();
       // QK(step+2) is issued AFTER PV(step): its commit (s_full) then also covers PV(step), which is
       // what allows the softmax group to overwrite P[sb] at step+2. (Issuing it earlier, as soon as S[sb]
@@ -457,30 +476,43 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     const int lg = warp & 3, grp = warp >> 2;               // grp g handles steps s with (s & 1) == g
     const int trow = lg * 32 + lane;                        // TMEM lane = row within the tile
     const int st = threadIdx.x;                             // 0..255
-    if (st < POS_ROWS / 16)                                 // 400 mask bytes = 25 16-byte vectors
-      reinterpret_cast<uint4*>(s_mask)[st] = reinterpret_cast<const uint4*>(p.mask + (size_t)pos * POS_ROWS)[st];
+    if (full) {
+      if (st < POS_ROWS / 16)                               // 400 mask bytes = 25 16-byte vectors
+        reinterpret_cast<uint4*>(s_mask)[st] = reinterpret_cast<const uint4*>(p.mask + (size_t)pos * POS_ROWS)[st];
+    } else {                                                // compact frames: pos * pos_rows is not 16-byte aligned
+      for (int r = st; r < pos_rows; r += 256) s_mask[r] = p.mask[(size_t)pos * pos_rows + r];
+    }
     asm volatile("bar.sync 1, 256;\n" ::: "memory");
     int np;
     uint32_t plist;
-    {
+    if (full) {
       uint4 m16 = make_uint4(0u, 0u, 0u, 0u);
       if (lane < POS_ROWS / 16) m16 = reinterpret_cast<const uint4*>(s_mask)[lane];
       a2_active_parts(m16, lane, np, plist);       // the same list the control warp derives from global memory
+    } else {
+      np = kp;
+      plist = 0u | (1u << 3) | (2u << 6) | (3u << 9) | (4u << 12);
     }
-    const int n_steps = A2_NT * np;
+    const int n_steps = nt * np;
     // ones plane of V: 1.0 for on-board keys, 0 otherwise (row sums + key mask in one column)
-    for (int r = st; r < POS_ROWS; r += 256)
-      *reinterpret_cast<uint4*>(s_v + A2_DCH * A2_PLANE + r * 16) =
-          make_uint4(s_mask[r] ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    for (int r = st; r < plane_rows; r += 256)
+      *reinterpret_cast<uint4*>(s_v + A2_DCH * plane_b + r * 16) =
+          make_uint4((r < pos_rows && s_mask[r]) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    // rows past the position in the last key part (compact frames only): zero values (the control warp zeroes the keys);
+    // ordered before the first PV by this group's p_full arrival, like the ones plane
+    for (int i = st; i < (plane_rows - pos_rows) * A2_DCH; i += 256) {
+      const int c = i / (plane_rows - pos_rows), r = pos_rows + i % (plane_rows - pos_rows);
+      *reinterpret_cast<uint4*>(s_v + c * plane_b + r * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
     fence_async_smem();
     mbar_wait(kv_full, 0);
     // max_j |k_j|^2
     float mk = 0.0f;
-    for (int r = st; r < POS_ROWS; r += 256) {
+    for (int r = st; r < pos_rows; r += 256) {
       float ss = 0.0f;
 #pragma unroll
       for (int c = 0; c < A2_DCH; c++) {
-        const uint4 u = *reinterpret_cast<const uint4*>(s_k + c * A2_PLANE + r * 16);
+        const uint4 u = *reinterpret_cast<const uint4*>(s_k + c * plane_b + r * 16);
         const float f[8] = {bf16_lo(u.x), bf16_hi(u.x), bf16_lo(u.y), bf16_hi(u.y),
                             bf16_lo(u.z), bf16_hi(u.z), bf16_lo(u.w), bf16_hi(u.w)};
 #pragma unroll
@@ -500,7 +532,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     // O / l, query mask, store; both groups take part, each owns 16 of the head's 32 channels
     auto epilogue = [&](int tile) {
       const int ob = tile & 1;
-      const int row = A2_Q0 + tile * TILE_M + trow;
+      const int row = q0 + tile * TILE_M + trow;
       mbar_wait(&o_full[ob], (tile >> 1) & 1);
       tc_fence_after();
       uint32_t o[16];
@@ -510,7 +542,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
-      if (row < POS_ROWS) {
+      if (row < pos_rows) {
         const bool on = s_mask[row] != 0;
         const float inv = on ? 1.0f / __uint_as_float(lbits) : 0.0f;
 #pragma unroll
@@ -521,7 +553,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
           w.z = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 4]) * inv, __uint_as_float(o[ch * 8 + 5]) * inv) : 0u;
           w.w = on ? pack_bf16x2(__uint_as_float(o[ch * 8 + 6]) * inv, __uint_as_float(o[ch * 8 + 7]) * inv) : 0u;
           const int plane = q_chunk0 + grp * 2 + ch;
-          const size_t off = p.out_blocked ? blocked_offset(cch, plane, pos * POS_ROWS + row)
+          const size_t off = p.out_blocked ? blocked_offset(cch, plane, pos * pos_rows + row)
                                            : ((size_t)plane * p.rows_alloc + prow0 + row) * 8;
           *reinterpret_cast<uint4*>(p.out + off) = w;
         }
@@ -593,7 +625,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         epi_done++;
       }
     }
-    while (epi_done < A2_NT) {
+    while (epi_done < nt) {
       epilogue(epi_done);
       epi_done++;
     }

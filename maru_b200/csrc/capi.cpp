@@ -114,7 +114,7 @@ int maru_eval_forward_leaves_device(maru_eval* ev, const maru_state* d_states, m
   CKC(cudaSetDevice(e->gpu_id));
   for (int off = 0; off < n; off += e->max_batch) {
     const int m = n - off < e->max_batch ? n - off : e->max_batch;
-    if (e->forward_device(maru::KIND_LEAVES, d_states + off, d_out + off, m)) return 1;
+    if (e->forward_device(maru::KIND_LEAVES, d_states + off, d_out + off, m, e->dev_w, e->dev_h)) return 1;
   }
   return 0;
 }
@@ -129,7 +129,7 @@ int maru_eval_forward_states_device(maru_eval* ev, const maru_state* d_states, f
   CKC(cudaSetDevice(e->gpu_id));
   for (int off = 0; off < n; off += e->max_batch) {
     const int m = n - off < e->max_batch ? n - off : e->max_batch;
-    if (e->forward_device(maru::KIND_STATES, d_states + off, d_out + (size_t)off * maru::OUT_ROW, m))
+    if (e->forward_device(maru::KIND_STATES, d_states + off, d_out + (size_t)off * maru::OUT_ROW, m, e->dev_w, e->dev_h))
       return 1;
   }
   return 0;
@@ -146,7 +146,7 @@ int maru_eval_forward_planes_device(maru_eval* ev, const float* d_in, float* d_o
   for (int off = 0; off < n; off += e->max_batch) {
     const int m = n - off < e->max_batch ? n - off : e->max_batch;
     if (e->forward_device(maru::KIND_PLANES, d_in + (size_t)off * maru::IN_ROW,
-                          d_out + (size_t)off * maru::OUT_ROW, m))
+                          d_out + (size_t)off * maru::OUT_ROW, m, e->dev_w, e->dev_h))
       return 1;
   }
   return 0;
@@ -194,8 +194,11 @@ int maru_eval_debug_planes(maru_eval* ev, int which, float* out, int n, int chan
   float* d = nullptr;
   const size_t bytes = (size_t)n * channels * maru::CELLS * 4;
   CKC(cudaMalloc(&d, bytes));
+  // x0 always lives on the 19x19 frame; the other tensors on the frame of the last forward (compact for small boards)
+  const maru::Geom gm = (which == MARU_BUF_X0) ? maru::Geom() : e->last;
   cudaError_t le = maru::launch_planes_to_nchw(acts[which]->p, e->rows_alloc, channels, acts[which]->channels,
-                                               acts[which]->blocked ? 1 : 0, d, n, e->stream);
+                                               acts[which]->blocked ? 1 : 0, d, n, gm.pitch, gm.pos_rows, gm.w, gm.h,
+                                               e->stream);
   if (le == cudaSuccess) le = cudaMemcpyAsync(out, d, bytes, cudaMemcpyDeviceToHost, e->stream);
   if (le == cudaSuccess) le = cudaStreamSynchronize(e->stream);
   cudaFree(d);
@@ -313,6 +316,18 @@ int maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int
   maru_b200::LeanBoard b;
   fill_lean_board(b, colors, width, height, ko_x, ko_y, ko_color);
   b.ladder_flags(flags);
+  return 0;
+}
+
+int maru_eval_set_device_board(maru_eval* ev, int width, int height) {
+  if (ev == nullptr || width < 0 || height < 0 || width > 19 || height > 19 || ((width == 0) != (height == 0))) {
+    maru::set_error("maru_eval_set_device_board: bad argument");
+    return 1;
+  }
+  Engine* e = E(ev);
+  std::lock_guard<std::mutex> lock(e->mu);
+  e->dev_w = width;
+  e->dev_h = height;
   return 0;
 }
 

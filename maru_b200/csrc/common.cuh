@@ -29,6 +29,12 @@ constexpr int TILE_M = 128;                  // rows per MMA tile (UMMA M)
 
 __host__ __device__ inline int flat_row(int y, int x) { return (y + 1) * PITCH + x; }
 __host__ __device__ inline int total_rows(int n) { return n * POS_ROWS + TAIL_ROWS; }
+// The same flat geometry with another frame: a w x h board needs pitch = w + 1 and (w + 1) * (h + 1) rows per
+// position (top halo row + h board rows, each followed by the shared halo cell).  After the stem (which must see
+// the reference's 19x19 frame, see engine.cu) the trunk of a batch of small boards runs on that COMPACT frame:
+// 100 rows per 9x9 position instead of 400.  Every kernel takes (pitch, pos_rows) as parameters; the full frame
+// is pitch = PITCH, pos_rows = POS_ROWS.
+__host__ __device__ inline int total_rows_g(int n, int pos_rows) { return n * pos_rows + TAIL_ROWS; }
 
 // element offset of (plane, row m) in a tile-blocked tensor with `planes` planes
 __host__ __device__ inline size_t blocked_offset(int planes, int plane, int m) {

@@ -277,7 +277,7 @@ __device__ __noinline__ void flow_producer(const FlowParams& fp, uint32_t c_smem
 // immediates, the B descriptor advances by 2*NT 16-byte units per MMA ([tap][k-chunk][nt][8] weight image).
 template <int CIN, int NT, int TAPS>
 __device__ __forceinline__ void flow_issue(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t w_lo, uint32_t b_hi,
-                                           uint32_t ones_lo, uint32_t r_hi, uint32_t biasb_lo) {
+                                           uint32_t ones_lo, uint32_t r_hi, uint32_t biasb_lo, int pitch) {
   constexpr int LEAD = (TAPS == 9) ? 24 : 0;
   constexpr int SLAB_ROWS = TILE_M + 2 * LEAD;
   constexpr int KCH = CIN / 8;
@@ -285,7 +285,7 @@ __device__ __forceinline__ void flow_issue(uint32_t d_tmem, uint32_t a_lo, uint3
   umma_bf16_lohi<0>(d_tmem, ones_lo, r_hi, biasb_lo, b_hi, idesc);           // D = bias
 #pragma unroll
   for (int t = 0; t < TAPS; t++) {
-    const int toff = (TAPS == 9) ? ((t / 3 - 1) * PITCH + (t % 3 - 1)) : 0;
+    const int toff = (TAPS == 9) ? ((t / 3 - 1) * pitch + (t % 3 - 1)) : 0;
 #pragma unroll
     for (int jj = 0; jj < CIN / 16; jj++) {
       const uint32_t a16 = (2 * jj) * SLAB_ROWS + LEAD + toff;   // in 16-byte units
@@ -308,6 +308,7 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, uint32_t c_smem, uin
   const uint32_t ones_lo = (uint32_t)r_d + (ones >> 4);
   const int n_layers = fp.n_layers;
   const int dbg = FLOW_DBG(fp);
+  const int pitch = fp.pitch;
   const uint32_t w_region = (uint32_t)fp.w_region;
   long long* const stamps = (c.cta == 0 && mw == 0) ? fp.stamps : nullptr;
   uint32_t g = 0;
@@ -351,7 +352,7 @@ __device__ __noinline__ void flow_mma(const FlowParams& fp, uint32_t c_smem, uin
         asm volatile("" : "+r"(w_lo_i), "+r"(biasb_lo_i), "+r"(ones_lo_i));
 #define X(CIN_, NT_, TAPS_)                                \
         else if (cin == CIN_ && nt == NT_ && taps == TAPS_) \
-          flow_issue<CIN_, NT_, TAPS_>(d_tmem, a_lo, a_hi, w_lo_i, b_hi, ones_lo_i, r_hi, biasb_lo_i);
+          flow_issue<CIN_, NT_, TAPS_>(d_tmem, a_lo, a_hi, w_lo_i, b_hi, ones_lo_i, r_hi, biasb_lo_i, pitch);
         if (dbg & 32) {}      // timing experiment: no MMAs at all
         MARU_FLOW_CASES(X)
 #undef X
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) conv_flow_kernel(const __grid
   c.tmem_base = *reinterpret_cast<volatile uint32_t*>(ctrl_p + CB_TMEM);
 
   // tile range of this CTA (the live batch size is written before the graph starts, not by the previous kernel)
-  c.m_rows = (fp.n_dev != nullptr) ? total_rows(*fp.n_dev) : fp.m_rows;
+  c.m_rows = (fp.n_dev != nullptr) ? total_rows_g(*fp.n_dev, fp.pos_rows) : fp.m_rows;
   c.n_tiles = (c.m_rows + TILE_M - 1) / TILE_M;
   const int n_ctas = ((int)gridDim.x < c.n_tiles) ? (int)gridDim.x : c.n_tiles;
   c.cta = (int)blockIdx.x;

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
     tl = p.timeline + ((size_t)p.seq * 2 + (blockIdx.x == 0 ? 0 : 1)) * 8;
   if (tl && threadIdx.x == 0) tl[0] = globaltimer_ns();
   const int group = blockIdx.y;                 // output-channel group of NT channels
-  const int m_rows = (p.n_dev != nullptr) ? total_rows(*p.n_dev) : p.m_rows;
+  const int m_rows = (p.n_dev != nullptr) ? total_rows_g(*p.n_dev, p.pos_rows) : p.m_rows;
   const int n_tiles = (m_rows + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
@@ -300,7 +300,7 @@ __global__ void __launch_bounds__(CONV_THREADS, 1) conv_gemm_kernel(const ConvPa
         }
 #pragma unroll
         for (int t = 0; t < TAPS; t++) {
-          const int off = (TAPS == 9) ? ((t / 3 - 1) * PITCH + (t % 3 - 1)) : 0;
+          const int off = (TAPS == 9) ? ((t / 3 - 1) * p.pitch + (t % 3 - 1)) : 0;
 #pragma unroll
           for (int j = 0; j < CIN / 16; j++) {
             const uint32_t a16 = (2 * j) * Cfg::SLAB_ROWS + Cfg::LEAD + off;   // in 16-byte units

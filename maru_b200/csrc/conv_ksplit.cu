@@ -66,7 +66,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1) conv_ksplit_kernel(const ConvPa
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int group = blockIdx.y;
-  const int m_rows = (p.n_dev != nullptr) ? total_rows(*p.n_dev) : p.m_rows;
+  const int m_rows = (p.n_dev != nullptr) ? total_rows_g(*p.n_dev, p.pos_rows) : p.m_rows;
   const int n_tiles = (m_rows + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {
@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(KS_THREADS, 1) conv_ksplit_kernel(const ConvPa
           const uint32_t wh = w_lo + (uint32_t)half * (KS_KCH / 2) * KS_NT;            // this half's K chunks
 #pragma unroll
           for (int t = 0; t < KS_TAPS; t++) {
-            const int off = (t / 3 - 1) * PITCH + (t % 3 - 1);
+            const int off = (t / 3 - 1) * p.pitch + (t % 3 - 1);
 #pragma unroll
             for (int j = 0; j < KS_CIN / 32; j++) {
               const uint32_t a16 = (2 * j) * KS_SLAB_ROWS + KS_LEAD + off;              // in 16-byte units

@@ -127,7 +127,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cp_cluster_rank();
-  const int m_rows = (p.n_dev != nullptr) ? total_rows(*p.n_dev) : p.m_rows;
+  const int m_rows = (p.n_dev != nullptr) ? total_rows_g(*p.n_dev, p.pos_rows) : p.m_rows;
   const int n_tiles = (m_rows + TILE_M - 1) / TILE_M;
   const int n_pairs = (n_tiles + 1) / 2;
   const int n_clusters = (int)gridDim.x / 2;
@@ -239,7 +239,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CP_THREADS, 1) conv_
           const uint32_t wh = w_lo + (uint32_t)half * CP_HALF_PLANES * CP_NH;                  // this half's K chunks
 #pragma unroll
           for (int t = 0; t < CP_TAPS; t++) {
-            const int off = (t / 3 - 1) * PITCH + (t % 3 - 1);
+            const int off = (t / 3 - 1) * p.pitch + (t % 3 - 1);
 #pragma unroll
             for (int j = 0; j < CP_HALF_PLANES / 2; j++) {
               const uint32_t a16 = (2 * j) * CP_SLAB_ROWS + CP_LEAD + off;                     // in 16-byte units

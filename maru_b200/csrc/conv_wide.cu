@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(CW_THREADS, 1) conv_wide_kernel(const ConvPara
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int group = blockIdx.y;
-  const int m_rows = (p.n_dev != nullptr) ? total_rows(*p.n_dev) : p.m_rows;
+  const int m_rows = (p.n_dev != nullptr) ? total_rows_g(*p.n_dev, p.pos_rows) : p.m_rows;
   const int n_tiles = (m_rows + TILE_M - 1) / TILE_M;
 
   if (threadIdx.x == 0) {

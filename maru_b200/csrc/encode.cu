@@ -281,21 +281,82 @@ __global__ void __launch_bounds__(416) ingest_rows_kernel(const float* __restric
   mask[(size_t)pos * POS_ROWS + r] = on ? 1 : 0;
 }
 
-// planes -> fp32 [n][channels][361] (parity/debug only)
+// planes -> fp32 [n][channels][361] (parity/debug only); (pitch, pos_rows, bw, bh) = frame geometry of the tensor
+// (bw = 0: the 19x19 frame; else the compact frame of a bw x bh board, reported centred in 19x19, zeros around it)
 __global__ void planes_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, int rows_alloc,
                                       int channels, int total_channels, int blocked,
-                                      float* __restrict__ out, int n) {
+                                      float* __restrict__ out, int n, int pitch, int pos_rows, int bw, int bh) {
   const size_t total = (size_t)n * channels * CELLS;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total;
        i += (size_t)gridDim.x * blockDim.x) {
     const int cell = i % CELLS;
     const int c = (i / CELLS) % channels;
     const int pos = i / ((size_t)CELLS * channels);
-    const int my = cell / BOARD, mx = cell - my * BOARD;
-    const int m = pos * POS_ROWS + flat_row(my, mx);
+    int my = cell / BOARD, mx = cell - my * BOARD;
+    if (bw > 0) {
+      mx -= (BOARD - bw) / 2;
+      my -= (BOARD - bh) / 2;
+      if (mx < 0 || my < 0 || mx >= bw || my >= bh) {
+        out[i] = 0.0f;
+        continue;
+      }
+    }
+    const int m = pos * pos_rows + (my + 1) * pitch + mx;
     const size_t off = blocked ? blocked_offset(total_channels / 8, c / 8, m)
                                : ((size_t)(c / 8) * rows_alloc + GUARD_ROWS + m) * 8;
     out[i] = __bfloat162float(x[off + (c % 8)]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ crop to the compact frame
+// The reference embeds a w x h board centred in its 19x19 model frame (Board.cpp:496-497) and computes all 361
+// cells.  Everything outside the board is zero after every layer (board mask), so the trunk of a batch of small
+// boards can run on a frame that holds just the board: pitch w + 1, (w + 1)(h + 1) rows per position — 100 rows for
+// 9x9 instead of 400.  Only the STEM needs the reference's frame: its input carries the ko plane at UN-centred
+// coordinates on small boards (Board.cpp:587-593), possibly in the ring around the board.  So the stem runs on the
+// 19x19 frame and this kernel moves its (masked) output, and the board mask, to the compact frame.
+// One CTA per position (+ one for the zero tail rows), one thread per compact row, 16-byte moves per plane.
+constexpr int CROP_THREADS = 416;
+__global__ void __launch_bounds__(CROP_THREADS) crop_kernel(const __nv_bfloat16* __restrict__ src,
+                                                            __nv_bfloat16* __restrict__ dst,
+                                                            const uint8_t* __restrict__ mask_src,
+                                                            uint8_t* __restrict__ mask_dst, int planes, int src_blocked,
+                                                            int dst_blocked, int rows_alloc, int w, int h, int n,
+                                                            const int* __restrict__ n_dev) {
+  pdl_launch_dependents();
+  const int live = (n_dev != nullptr) ? *n_dev : n;
+  const int pos = blockIdx.x;
+  if (pos > live) return;
+  pdl_wait();
+  const int pitch = w + 1, pos_rows = (w + 1) * (h + 1);
+  const int r = threadIdx.x;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  if (pos == live) {                                   // zero rows after the last position
+    if (r < TAIL_ROWS) {
+      const int m = live * pos_rows + r;
+      for (int c = 0; c < planes; c++) {
+        const size_t off = dst_blocked ? blocked_offset(planes, c, m) : ((size_t)c * rows_alloc + GUARD_ROWS + m) * 8;
+        *reinterpret_cast<uint4*>(dst + off) = zero;
+      }
+      mask_dst[m] = 0;
+    }
+    return;
+  }
+  if (r >= pos_rows) return;
+  const int gy = r / pitch, x = r - gy * pitch;
+  const bool cell = gy >= 1 && x < w;
+  const int ms = pos * POS_ROWS + flat_row((BOARD - h) / 2 + gy - 1, (BOARD - w) / 2 + x);   // row in the 19x19 frame
+  const int md = pos * pos_rows + r;
+  const uint8_t on = cell ? mask_src[ms] : 0;
+  mask_dst[md] = on;
+  for (int c = 0; c < planes; c++) {
+    uint4 v = zero;
+    if (on) {
+      const size_t so = src_blocked ? blocked_offset(planes, c, ms) : ((size_t)c * rows_alloc + GUARD_ROWS + ms) * 8;
+      v = *reinterpret_cast<const uint4*>(src + so);
+    }
+    const size_t off = dst_blocked ? blocked_offset(planes, c, md) : ((size_t)c * rows_alloc + GUARD_ROWS + md) * 8;
+    *reinterpret_cast<uint4*>(dst + off) = v;
   }
 }
 
@@ -329,10 +390,21 @@ cudaError_t launch_ingest_rows(const float* rows, __nv_bfloat16* x0, uint8_t* ma
   return cudaGetLastError();
 }
 cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, int total_channels,
-                                  int blocked, float* out, int n, cudaStream_t stream) {
+                                  int blocked, float* out, int n, int pitch, int pos_rows, int bw, int bh,
+                                  cudaStream_t stream) {
   if (n <= 0) return cudaSuccess;
-  planes_to_nchw_kernel<<<256, 256, 0, stream>>>(x, rows_alloc, channels, total_channels, blocked, out, n);
+  planes_to_nchw_kernel<<<256, 256, 0, stream>>>(x, rows_alloc, channels, total_channels, blocked, out, n, pitch,
+                                                 pos_rows, bw, bh);
   return cudaGetLastError();
+}
+
+cudaError_t launch_crop(const __nv_bfloat16* src, __nv_bfloat16* dst, const uint8_t* mask_src, uint8_t* mask_dst,
+                        int channels, int src_blocked, int dst_blocked, int rows_alloc, int w, int h, int n,
+                        const int* n_dev, int pdl, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  if (w < 1 || h < 1 || w > BOARD || h > BOARD || (w + 1) * (h + 1) > CROP_THREADS) return cudaErrorInvalidValue;
+  return launch_kernel(crop_kernel, dim3(n + 1), dim3(CROP_THREADS), 0, stream, pdl != 0, src, dst, mask_src, mask_dst,
+                       channels / 8, src_blocked, dst_blocked, rows_alloc, w, h, n, n_dev);
 }
 
 }  // namespace maru

@@ -401,6 +401,10 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
   CK(cudaMalloc(&mask, (size_t)rows_alloc));
   CK(cudaMemset(mask, 0, (size_t)rows_alloc));
   allocs.push_back(mask);
+  CK(cudaMalloc(&mask_c, (size_t)rows_alloc));
+  CK(cudaMemset(mask_c, 0, (size_t)rows_alloc));
+  allocs.push_back(mask_c);
+  if (const char* cc = getenv("MARU_B200_COMPACT")) compact_on = cc[0] != '0';
   CK(cudaMalloc(&d_trace, (size_t)256 * TRACE_TILES * TRACE_SLOTS * 8));
   CK(cudaMemset(d_trace, 0, (size_t)256 * TRACE_TILES * TRACE_SLOTS * 8));
   allocs.push_back(d_trace);
@@ -495,9 +499,11 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
   p.res_chunk0 = 0;
   p.out = out.p;
   p.out_chunk0 = 0;
-  p.mask = mask;
+  p.mask = cur_mask();
   p.rows_alloc = rows_alloc;
-  p.m_rows = total_rows(n);
+  p.pitch = geom.pitch;
+  p.pos_rows = geom.pos_rows;
+  p.m_rows = total_rows_g(n, geom.pos_rows);
   p.cout_total = L.cout;
   p.relu = relu;
   p.n_dev = n_dev;
@@ -560,6 +566,9 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
           pending_single = p;
           pending_first = &L;
           pending.m_rows = p.m_rows;
+          pending.pitch = p.pitch;
+          pending.pos_rows = p.pos_rows;
+          pending.mask = p.mask;
           pending.n_dev = n_dev;
           pending.pdl = p.pdl;
           pending_flops = pending_bytes = 0.0;
@@ -668,6 +677,7 @@ int Engine::profile_states(const maru_state* d_states, float* d_out, int n, maru
     set_error("maru_eval_profile_states: n out of range");
     return 1;
   }
+  fwd = (compact_on && !(dbg_desc & (1 << 21))) ? Geom::board(dev_w, dev_h) : Geom();
   flow_live = flow_pays(n);
   std::vector<maru_launch_time> rec;
   rec.reserve(256);
@@ -714,7 +724,6 @@ int Engine::flush_chain(cudaStream_t st) {
     return 0;
   }
   pending.n_layers = nl;
-  pending.mask = mask;
   pending.rows_alloc = rows_alloc;
   pending.flags = d_sync;
   pending.stamps = (dbg_desc & 64) && stamps_used + 4 * nl + 4 <= 512 ? d_stamps + stamps_used : nullptr;
@@ -753,7 +762,7 @@ void Engine::device_ref(int delta) {
 // Measured (b4c128, forward in us, flow / per-layer): batch 1: 186 / 159, 64: 246 / 222, 128: 323 / 305, 192: 415 / 401,
 // 224: 444 / 433, 256: 448-458 / 466, 320: 544 / 562, 384: 666 / 659, 512: 838 / 824, 1024: 1710 / 1617.
 bool Engine::flow_pays(int n) const {
-  const int n_tiles = (total_rows(n) + TILE_M - 1) / TILE_M;
+  const int n_tiles = (total_rows_g(n, fwd.pos_rows) + TILE_M - 1) / TILE_M;
   // C = 256 nets: only the 128 -> 256 expansions fit a chain (two-layer launches, measured 0.7 % slower at batch 256)
   return C <= 128 && 4 * n_tiles >= 21 * sm_count && 2 * n_tiles < 15 * sm_count;     // 5.25 <= tiles per CTA < 7.5: batch 249..354
 }
@@ -796,7 +805,27 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
       a->flagged = false;
     }
   }
-  if (conv(stem, x0, nullptr, h, 1, n, n_dev, st)) return 1;
+  // The stem always runs on the reference's 19x19 frame (its input planes are laid out there, ko quirk included). A batch
+  // of small boards then moves to the compact frame: the stem writes into `o` (free until the first attention layer)
+  // and the crop kernel moves the board's rows to `h`; every later layer sees (w + 1)(h + 1) rows per position.
+  geom = Geom();
+  if (fwd.compact()) {
+    if (conv(stem, x0, nullptr, o, 1, n, n_dev, st)) return 1;
+    if (flush_chain(st)) return 1;
+    if (!(dbg_stop_after >= 0 && launches_done >= dbg_stop_after)) {
+      launches_done++;
+      n_launched++;
+      prof_begin("crop", 0, C, C, 0, 0.0, (double)fwd.w * fwd.h * C * 2.0 * 2.0 * n, st);
+      for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
+        CK(launch_crop(o.p, h.p, mask, mask_c, C, o.blocked ? 1 : 0, h.blocked ? 1 : 0, rows_alloc, fwd.w, fwd.h, n, n_dev,
+                       (dbg_desc & 1) ? 0 : 1, st));
+      prof_end(st);
+    }
+    geom = fwd;
+  } else {
+    if (conv(stem, x0, nullptr, h, 1, n, n_dev, st)) return 1;
+  }
+  last = fwd;
   int ai = 0;
   for (int i = 0; i < blocks; i++) {
     Block& B = blk[i];
@@ -813,8 +842,10 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
       ap.qkv = qkv.p;
       ap.out = o.p;
       ap.out_blocked = o.blocked;
-      ap.mask = mask;
+      ap.mask = cur_mask();
       ap.rows_alloc = rows_alloc;
+      ap.pitch = geom.pitch;
+      ap.pos_rows = geom.pos_rows;
       ap.n = n;
       ap.channels = C;
       ap.head_dim = head_dim;
@@ -838,7 +869,11 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
   if (conv(headg, h, nullptr, g, 1, n, n_dev, st)) return 1;
   HeadParams hp;
   hp.g = g.p;
-  hp.mask = mask;
+  hp.mask = cur_mask();
+  hp.pitch = geom.pitch;
+  hp.pos_rows = geom.pos_rows;
+  hp.board_w = geom.w;
+  hp.board_h = geom.h;
   hp.w_planes = w_planes;
   hp.b_planes = b_planes;
   hp.w_fc1 = w_fc1;
@@ -897,8 +932,43 @@ static int bucket_for(int n, int max_batch) {
 }
 
 // Enqueue one forward of n <= max_batch positions on `stream` (no host sync).
-int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
+void Engine::uniform_board(const maru_state* s, int n, int* bw, int* bh) {
+  *bw = *bh = 0;
+  if (s == nullptr || n <= 0) return;
+  const int w = s[0].width, h = s[0].height;
+  for (int i = 1; i < n; i++)
+    if (s[i].width != w || s[i].height != h) return;     // mixed sizes: the 19x19 frame serves them all
+  *bw = w;
+  *bh = h;
+}
+
+// Plane 32 of a reference row is 1 on the w x h board centred in the 19x19 frame (Board.cpp:496-497, 596-601): the middle
+// frame row always crosses the board, so w = its number of ones and h = (all ones) / w.
+void Engine::uniform_board_rows(const float* rows, int n, int* bw, int* bh) {
+  *bw = *bh = 0;
+  int w0 = 0, h0 = 0;
+  for (int i = 0; i < n; i++) {
+    const float* m = rows + (size_t)i * IN_ROW + (size_t)(IN_PLANES - 1) * CELLS;
+    int w = 0, total = 0;
+    for (int x = 0; x < BOARD; x++) w += m[(BOARD / 2) * BOARD + x] != 0.0f;
+    for (int c = 0; c < CELLS; c++) total += m[c] != 0.0f;
+    if (w == 0 || total % w != 0) return;                 // not a board mask: the 19x19 frame is always right
+    const int h = total / w;
+    if (i == 0) {
+      w0 = w;
+      h0 = h;
+    } else if (w != w0 || h != h0) {
+      return;
+    }
+  }
+  *bw = w0;
+  *bh = h0;
+}
+
+int Engine::forward_device(int kind, const void* d_in, void* d_out, int n, int bw, int bh) {
   if (n <= 0) return 0;
+  // a batch whose positions all hold the same small board runs on that board's compact frame after the stem
+  fwd = (compact_on && !(dbg_desc & (1 << 21))) ? Geom::board(bw, bh) : Geom();
   if (n > max_batch) {
     set_error("batch larger than max_batch");
     return 1;
@@ -914,7 +984,7 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n) {
     } else {
       // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
       const int bucket = bucket_for(n, max_batch);
-      GraphKey key{kind, bucket, d_in, d_out, with_flow};
+      GraphKey key{kind, bucket, d_in, d_out, with_flow, fwd.w, fwd.h};
       auto it = graphs.find(key);
       if (it == graphs.end()) {
         // The cache is keyed by the caller's buffers: a device-API caller that rotates buffers must not grow it
@@ -979,7 +1049,10 @@ int Engine::forward_host(int kind, const void* in, void* out, int n) {
     CK(cudaMemcpyAsync(d_in, static_cast<const uint8_t*>(in) + (size_t)off * in_row, (size_t)m * in_row,
                        cudaMemcpyHostToDevice, stream));
     CK(cudaEventRecord(sl.t0, stream));
-    if (forward_device(kind, d_in, sl.d_out, m)) return 1;
+    int bw = 0, bh = 0;
+    if (kind != KIND_PLANES) uniform_board(static_cast<const maru_state*>(in) + off, m, &bw, &bh);
+    else uniform_board_rows(static_cast<const float*>(in) + (size_t)off * IN_ROW, m, &bw, &bh);
+    if (forward_device(kind, d_in, sl.d_out, m, bw, bh)) return 1;
     CK(cudaEventRecord(sl.t1, stream));
     CK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + (size_t)off * out_row, sl.d_out, (size_t)m * out_row,
                        cudaMemcpyDeviceToHost, stream));
@@ -1001,7 +1074,10 @@ int Engine::enqueue_slot(int kind, int slot_idx, int n) {
   const void* h_in = kind != KIND_PLANES ? (const void*)sl.h_states : (const void*)sl.h_rows;
   CK(cudaMemcpyAsync(d_in, h_in, (size_t)n * in_row, cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(sl.t0, stream));
-  if (forward_device(kind, d_in, sl.d_out, n)) return 1;
+  int bw = 0, bh = 0;
+  if (kind != KIND_PLANES) uniform_board(sl.h_states, n, &bw, &bh);
+  else uniform_board_rows(sl.h_rows, n, &bw, &bh);
+  if (forward_device(kind, d_in, sl.d_out, n, bw, bh)) return 1;
   CK(cudaEventRecord(sl.t1, stream));
   CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)n * out_row_bytes(kind), cudaMemcpyDeviceToHost, stream));
   CK(cudaEventRecord(sl.done, stream));

@@ -65,13 +65,31 @@ struct Slot {
   cudaEvent_t t0 = nullptr, t1 = nullptr;  // kernel span of the batch (timing events)
 };
 
+// frame geometry of the layers being enqueued (common.cuh): the reference's 19x19 frame, or the compact frame of a
+// batch of w x h boards (after the stem)
+struct Geom {
+  int pitch = PITCH, pos_rows = POS_ROWS, w = 0, h = 0;
+  bool compact() const { return w != 0; }
+  static Geom board(int bw, int bh) {
+    Geom g;
+    if (bw > 0 && bh > 0 && (bw < BOARD || bh < BOARD)) {
+      g.pitch = bw + 1;
+      g.pos_rows = (bw + 1) * (bh + 1);
+      g.w = bw;
+      g.h = bh;
+    }
+    return g;
+  }
+};
+
 struct GraphKey {
   int kind, bucket;
   const void* in;
   const void* out;
-  bool flow;   // captured with the persistent flow kernels (only while the engine has the device to itself)
+  bool flow;
+  int w = 0, h = 0;   // compact-frame board of the forward (0, 0: the 19x19 frame)   // captured with the persistent flow kernels (only while the engine has the device to itself)
   bool operator<(const GraphKey& o) const {
-    return std::tie(kind, bucket, in, out, flow) < std::tie(o.kind, o.bucket, o.in, o.out, o.flow);
+    return std::tie(kind, bucket, in, out, flow, w, h) < std::tie(o.kind, o.bucket, o.in, o.out, o.flow, o.w, o.h);
   }
 };
 
@@ -91,7 +109,14 @@ struct Engine {
         *w_fc2 = nullptr, *b_fc2 = nullptr;
 
   Act x0, h, r, s, qkv, o, g;
-  uint8_t* mask = nullptr;
+  uint8_t* mask = nullptr;          // board mask on the 19x19 frame (written by encode / ingest)
+  uint8_t* mask_c = nullptr;        // the same on the compact frame of the forward (written by the crop kernel)
+  Geom geom;                        // geometry of the layers being enqueued right now
+  Geom fwd;                         // trunk geometry of the forward being enqueued (compact for a batch of small boards)
+  Geom last;                        // ... of the last forward enqueued (debug_planes)
+  bool compact_on = true;           // MARU_B200_COMPACT=0 / debug bit 21: always the 19x19 frame
+  int dev_w = 0, dev_h = 0;         // board size of the records of the *_device entry points (0: unknown -> 19x19 frame)
+  const uint8_t* cur_mask() const { return geom.compact() ? mask_c : mask; }
   int* d_n = nullptr;
   int* h_n = nullptr;
   unsigned n_seq = 0;
@@ -164,7 +189,12 @@ struct Engine {
   int flush_chain(cudaStream_t st);
   int launch_trunk(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st);
   int launch_all(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st);
-  int forward_device(int kind, const void* d_in, void* d_out, int n);  // async on `stream`
+  // async on `stream`; (bw, bh) = board size of ALL n records when the caller knows it (0: 19x19 frame)
+  int forward_device(int kind, const void* d_in, void* d_out, int n, int bw = 0, int bh = 0);
+  // the board size shared by all n host records, or (0, 0)
+  static void uniform_board(const maru_state* s, int n, int* bw, int* bh);
+  // the same for fp32 rows (Board::getInputs layout): the board is read off plane 32, the on-board mask
+  static void uniform_board_rows(const float* rows, int n, int* bw, int* bh);
   int forward_host(int kind, const void* in, void* out, int n);        // blocking, host buffers
   // leaf-queue pipeline: inputs already gathered in slot.h_*; enqueue H2D + forward + D2H (async)
   int enqueue_slot(int kind, int slot_idx, int n);

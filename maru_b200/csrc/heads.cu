@@ -67,18 +67,24 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   if (tid < 6) s_bp[tid] = p.b_planes[tid];
   pdl_wait();   // g and mask come from the previous kernels
 
+  // frame geometry: the 19x19 frame, or the compact frame of a board_w x board_h board whose outputs are written at the
+  // cells the reference uses for it (centred in 19x19, Evaluator.cpp:57-69); everything around the board is zero
+  const int pitch = p.pitch, pos_rows = p.pos_rows;
+  const bool compact = p.board_w > 0;
+  const int fw = compact ? p.board_w : BOARD;            // cells per frame row
+  const int ox = compact ? (BOARD - p.board_w) / 2 : 0, oy = compact ? (BOARD - p.board_h) / 2 : 0;
   const int r = tid;                                     // padded row of this thread
-  const bool in_pos = r < POS_ROWS;
-  const int gy = r / PITCH, x = r - gy * PITCH;
-  const bool cell_ok = in_pos && gy >= 1 && x < BOARD;   // a real 19x19 cell (maybe off-board)
-  const int cell = (gy - 1) * BOARD + x;
-  const bool on = in_pos && (p.mask[(size_t)pos * POS_ROWS + (in_pos ? r : 0)] != 0);
+  const bool in_pos = r < pos_rows;
+  const int gy = r / pitch, x = r - gy * pitch;
+  const bool cell_ok = in_pos && gy >= 1 && x < fw;      // a cell of the frame (maybe off-board)
+  const int cell = (gy - 1 + oy) * BOARD + x + ox;       // its index in the 19x19 model frame
+  const bool on = in_pos && (p.mask[(size_t)pos * pos_rows + (in_pos ? r : 0)] != 0);
   float gv[HEAD_MAX_CH];
 #pragma unroll
   for (int c8 = 0; c8 < HEAD_MAX_CH / 8; c8++) {
     uint4 v = make_uint4(0u, 0u, 0u, 0u);
     if (in_pos && c8 < n_chunks) {
-      const size_t grow = (size_t)GUARD_ROWS + (size_t)pos * POS_ROWS + r;
+      const size_t grow = (size_t)GUARD_ROWS + (size_t)pos * pos_rows + r;
       v = *reinterpret_cast<const uint4*>(p.g + ((size_t)c8 * p.rows_alloc + grow) * 8);
     }
     gv[c8 * 8 + 0] = bf16_lo(v.x); gv[c8 * 8 + 1] = bf16_hi(v.x);
@@ -100,6 +106,13 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
     }
   }
   float* out = (p.out != nullptr) ? p.out + (size_t)pos * OUT_ROW : nullptr;
+  if (compact) {                                         // model cells outside the board are not visited below
+    if (out != nullptr)
+      for (int i = tid; i < 6 * CELLS; i += HEAD_THREADS) out[i] = 0.0f;
+    if (p.logits != nullptr)
+      for (int i = tid; i < 2 * CELLS; i += HEAD_THREADS) p.logits[(size_t)pos * 2 * CELLS + i] = 0.0f;
+    __syncthreads();
+  }
   if (cell_ok && p.logits != nullptr) {
     p.logits[((size_t)pos * 2 + 0) * CELLS + cell] = z[0];
     p.logits[((size_t)pos * 2 + 1) * CELLS + cell] = z[1];
@@ -185,7 +198,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
     const maru_state* st = p.states + pos;
     const int w = st->width, h = st->height;
     if (cell_ok && on) {
-      const int bx = x - (BOARD - w) / 2, by = (gy - 1) - (BOARD - h) / 2;
+      const int bx = compact ? x : x - (BOARD - w) / 2, by = compact ? gy - 1 : (gy - 1) - (BOARD - h) / 2;
       const int idx = by * w + bx;
       const bool allowed = !(st->flags & MARU_STATE_HAS_MASK) || ((st->move_mask[idx >> 3] >> (idx & 7)) & 1u);
       lf->prior[idx] = allowed ? e0 / t0 : 0.0f;

@@ -31,7 +31,8 @@ struct ConvParams {
   int out_chunk0;
   const uint8_t* mask;       // [m_rows] 1 = on-board cell
   int rows_alloc;            // plane stride in rows (same for in/res/out)
-  int m_rows;                // total_rows(n)
+  int m_rows;                // total_rows_g(n, pos_rows)
+  int pitch, pos_rows;       // frame geometry (common.cuh): 20 / 400 for the 19x19 frame, w + 1 / (w + 1)(h + 1) compact
   int cout_total;
   int relu;
   int stages;                // pipeline depth (filled by the launcher from the smem budget)
@@ -81,6 +82,7 @@ struct FlowParams {
   const uint8_t* mask;
   int rows_alloc;
   int m_rows;
+  int pitch, pos_rows;         // frame geometry, as in ConvParams
   const int* n_dev;
   int w_region;                // shared-memory bytes of ONE weight region (two regions, double-buffered)
   int area;                    // bytes of the slab ring
@@ -136,7 +138,12 @@ cudaError_t launch_ingest_rows(const float* rows, __nv_bfloat16* x0, uint8_t* ma
                                int n, const int* n_dev, cudaStream_t stream);
 // trunk input planes -> fp32 [n][channels][361] (debug / parity)
 cudaError_t launch_planes_to_nchw(const __nv_bfloat16* x, int rows_alloc, int channels, int total_channels,
-                                  int blocked, float* out, int n, cudaStream_t stream);
+                                  int blocked, float* out, int n, int pitch, int pos_rows, int bw, int bh,
+                                  cudaStream_t stream);
+// stem output + mask on the 19x19 frame -> compact frame of a w x h board (encode.cu: crop_kernel)
+cudaError_t launch_crop(const __nv_bfloat16* src, __nv_bfloat16* dst, const uint8_t* mask_src, uint8_t* mask_dst,
+                        int channels, int src_blocked, int dst_blocked, int rows_alloc, int w, int h, int n,
+                        const int* n_dev, int pdl, cudaStream_t stream);
 
 // ---- K4: attention core (attention.cu) -------------------------------------------------------
 struct AttnParams {
@@ -148,6 +155,7 @@ struct AttnParams {
   int n;                     // positions
   int channels;              // C
   int head_dim;              // 32 or 64
+  int pitch, pos_rows;       // frame geometry (20 / 400, or the compact frame of a small board)
   const int* n_dev;
   int pdl;
   int dbg;                   // bit0: swap LBO/SBO of the MN-major V descriptor, bit1: legacy mma.sync kernel
@@ -170,6 +178,8 @@ struct HeadParams {
   const maru_state* states;  // records of the batch (board geometry + move_mask), needed with `leaf`
   float* logits;             // optional [n][2][361] pre-softmax policy logits
   int rows_alloc;
+  int pitch, pos_rows;       // frame geometry of g / mask
+  int board_w, board_h;      // compact frame: the board it holds (outputs are written centred in 19x19); 0 = full frame
   int n;
   int ch;                    // head channels (32)
   int cv;                    // value channels (<= 128)

@@ -97,7 +97,12 @@ def test_compact_record_dropin_matches_plane_dropin(libs, built_lib, model_dir):
         xa, ya, pa_, va = pa.evaluate(*boards[0])
         xb, yb, pb_, vb = pb.evaluate(*boards[1])
         assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
-        assert np.array_equal(pa_, pb_) and va == vb          # same trunk input -> identical bits
+        if size == 19:
+            assert np.array_equal(pa_, pb_) and va == vb      # same trunk input -> identical bits
+        else:
+            # records of a small board run on the compact frame after the stem, fp32 rows (whose board size the
+            # evaluator cannot see without a scan) on the reference's 19x19 frame: equal up to summation order
+            assert np.abs(pa_ - pb_).max() <= 2e-3 and abs(va - vb) <= 2e-3
     pl = ref.RefPlayer(pb, threads=8, width=9, height=9)
     pl.initialize()
     cands = pl.evaluate(visits=100)

@@ -109,7 +109,14 @@ def test_empty_and_ragged_batches(ev):
     states = np.concatenate([load_positions(t)[1][:7] for t in ('9', '19', '5x7', '13', '9x13')])
     mixed = ev.forward_states(states)
     assert np.array_equal(mixed, ev.forward(rows))
-    for i in (0, 8, 20, 34):                                  # each position alone == in the mixed batch
-        assert np.array_equal(ev.forward_states(states[i:i + 1])[0], mixed[i])
+    # A mixed batch runs on the reference's 19x19 frame; a position alone (or any batch of ONE board size) runs on
+    # the compact frame of its board after the stem: identical for 19x19, equal up to fp32 summation order otherwise
+    for i in (0, 8, 20, 34):
+        alone = ev.forward_states(states[i:i + 1])[0]
+        if states[i, 368] == 19 and states[i, 369] == 19:
+            assert np.array_equal(alone, mixed[i])
+        else:
+            assert np.abs(alone - mixed[i]).max() <= 2e-3
+        assert np.array_equal(alone, ev.forward(rows[i:i + 1])[0])     # records and fp32 rows agree bit for bit
     with pytest.raises(ValueError):
         ev.forward(np.zeros((3, 100), np.float32))

@@ -10,8 +10,12 @@ from conftest import load_positions
 pytestmark = pytest.mark.gpu
 
 
-def test_queue_matches_direct_and_batches(built_lib, model_dir):
+def test_queue_matches_direct_and_batches(built_lib, model_dir, monkeypatch):
     import maru_b200
+    # 19x19 and 9x9 positions travel in whatever batches the queue forms: with the compact frame for uniform batches
+    # of small boards a 9x9 result would depend (in the last bits) on its batch mates, and this test compares bit for
+    # bit — so every batch stays on the reference's 19x19 frame here (tests/test_compact_gpu.py covers the other one)
+    monkeypatch.setenv('MARU_B200_COMPACT', '0')
     path = model_dir('b2c64')
     rows, states = load_positions('19')
     rows = np.concatenate([rows, load_positions('9')[0]])
