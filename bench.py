@@ -57,6 +57,7 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-selfplay', action='store_true')
     ap.add_argument('--no-gpu-reference', action='store_true')
+    ap.add_argument('--no-small-boards', action='store_true')
     ap.add_argument('--sustained-s', type=float, default=2.0)
     ap.add_argument('--sp-board', type=int, default=19)
     ap.add_argument('--sp-visits', type=int, default=50, help='descents per move (reference default --visits 50)')
@@ -64,6 +65,7 @@ def parse():
     ap.add_argument('--sp-games-per-thread', type=int, default=128)
     ap.add_argument('--sp-opening', type=int, default=-1, help='random opening moves (-1: board*board/6)')
     ap.add_argument('--sp-root', default='pucb', choices=['pucb', 'gumbel'])
+    ap.add_argument('--sp-max-batch', type=int, default=1024)
     ap.add_argument('--sp-threads', type=int, default=0, help='search threads per rank (0: this rank\'s cores - 1)')
     return ap.parse_args()
 
@@ -352,6 +354,44 @@ def gpu_reference_leg(model_path: Path, rows: np.ndarray, ours: np.ndarray, B: i
     return out
 
 
+def small_boards_leg(args, model_path: Path, local: int, dev, batch: int = 1024, steps: int = 10) -> dict:
+    """evals/s (device-resident records, CUDA events, L2 flushed) of 9x9 and 13x13 positions next to 19x19 at the
+    same batch size: small boards run on a compact frame after the stem (100 / 196 rows per position instead of the
+    reference's 400; maru_eval_set_device_board tells the device entry point the size the host ones read off the
+    records), so they cost less — the reference evaluates all 361 model cells for every board size."""
+    import torch
+    import maru_b200
+    from maru_b200 import synth
+    ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=batch)
+    stream = torch.cuda.ExternalStream(ev.stream(), device=dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    d_out = torch.empty((batch, maru_b200.OUTPUT_SIZE), dtype=torch.float32, device=dev)
+    out = dict(batch=batch, steps=steps, l2='flushed between steps (256 MiB write)')
+    for board in (9, 13, 19):
+        ev.set_device_board(board if board < 19 else 0, board if board < 19 else 0)
+        d_states = torch.from_numpy(synth.random_states(batch, board, seed=77 + board)).to(dev)
+        for _ in range(3):
+            ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), batch)
+        ev.sync()
+        e0 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        e1 = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+        for i in range(steps):
+            with torch.cuda.stream(stream):
+                flush.zero_()
+                e0[i].record(stream)
+            ev.forward_states_device(d_states.data_ptr(), d_out.data_ptr(), batch)
+            with torch.cuda.stream(stream):
+                e1[i].record(stream)
+        torch.cuda.synchronize(dev)
+        ms = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / steps
+        out[f'{board}x{board}'] = dict(value=batch / (ms / 1e3), unit=UNIT, ms_per_step=ms,
+                                       launches_per_step=ev.info().launches_per_forward)
+    for b in ('9x9', '13x13'):
+        out[b]['vs_19x19'] = out[b]['value'] / out['19x19']['value']
+    ev.close()
+    return out
+
+
 def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist, dev) -> dict:
     """Self-play visits/s of the native scheduler on this rank's GPU; whole job = sum of visits over ranks /
     slowest rank's wall time (barrier + synchronize on both sides)."""
@@ -362,8 +402,8 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
     cpus = rank_cpus(local)
     threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus) - 1)
     games = threads * args.sp_games_per_thread
-    ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=1024)
-    q = maru_b200.LeafQueue([ev], batch_size=1024)
+    ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=args.sp_max_batch)
+    q = maru_b200.LeafQueue([ev], batch_size=args.sp_max_batch)
     sp = selfplay.NativeSelfPlay(q, games=games, size=args.sp_board, visits=args.sp_visits, threads=threads,
                                  max_moves=10 ** 6, root=args.sp_root, width=16,
                                  noise=1.0 if args.sp_root == 'gumbel' else 0.0, criterion='lcb',
@@ -440,6 +480,8 @@ def run_b200(args):
     ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=B)
     if os.environ.get('MARU_DBG_BITS'):
         ev.debug_set(1, int(os.environ['MARU_DBG_BITS']))
+    if args.board < 19:
+        ev.set_device_board(args.board, args.board)    # device-resident records: the evaluator cannot read their size
     info = ev.info()
     stream = torch.cuda.ExternalStream(ev.stream(), device=dev)
     states = synth.random_states(B, args.board, seed=1234 + rank)
@@ -570,6 +612,11 @@ def run_b200(args):
         except Exception as exc:
             gpu_ref = dict(error=str(exc))
 
+    # ---------------- small boards (north_star: 9x9 / 13x13 / 19x19 throughput), N = 1 ----------------------
+    small = None
+    if world == 1 and not args.no_small_boards and args.board == 19:
+        small = small_boards_leg(args, model_path, local, dev)
+
     # ---------------- selfplay: every rank plays its shard of the games ---------------------------------
     sp_block = None
     if not args.no_selfplay:
@@ -666,7 +713,7 @@ def run_b200(args):
             gpu_launches=info.launches_per_forward * args.steps,
             clocks=clock, roofline=roofline, cpu_baseline=cpu, kernels=table,
             wall_ms_per_step=t_wall / args.steps * 1e3, sustained=sustained,
-            gpu_reference=gpu_ref, selfplay=sp_block)
+            gpu_reference=gpu_ref, small_boards=small, selfplay=sp_block)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
