@@ -62,11 +62,12 @@ def parse():
     ap.add_argument('--sp-board', type=int, default=19)
     ap.add_argument('--sp-visits', type=int, default=50, help='descents per move (reference default --visits 50)')
     ap.add_argument('--sp-moves', type=int, default=8, help='timed moves per game (after 1 untimed move)')
-    ap.add_argument('--sp-games-per-thread', type=int, default=128)
+    ap.add_argument('--sp-games', type=int, default=1920, help='concurrent games per GPU (split over the search threads)')
     ap.add_argument('--sp-opening', type=int, default=-1, help='random opening moves (-1: board*board/6)')
     ap.add_argument('--sp-root', default='pucb', choices=['pucb', 'gumbel'])
     ap.add_argument('--sp-max-batch', type=int, default=1024)
-    ap.add_argument('--sp-threads', type=int, default=0, help='search threads per rank (0: this rank\'s cores - 1)')
+    ap.add_argument('--sp-threads', type=int, default=0,
+                    help='search threads per rank (0: this rank\'s cores, minus one for the queue thread when there are > 8)')
     return ap.parse_args()
 
 
@@ -400,8 +401,9 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
     from maru_b200 import selfplay
     cfg = selfplay_config(args)
     cpus = rank_cpus(local)
-    threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus) - 1)
-    games = threads * args.sp_games_per_thread
+    # the queue's worker thread (gather, launch, scatter: a few % of a core) gets a core of its own only when cores are plenty
+    threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus) - 1 if len(cpus) > 8 else len(cpus))
+    games = max(threads, args.sp_games // threads * threads)      # per GPU, independent of the thread count
     ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=args.sp_max_batch)
     q = maru_b200.LeafQueue([ev], batch_size=args.sp_max_batch)
     sp = selfplay.NativeSelfPlay(q, games=games, size=args.sp_board, visits=args.sp_visits, threads=threads,

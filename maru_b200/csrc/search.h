@@ -83,6 +83,10 @@ struct TreeNode {
   std::vector<Prior> moves;             // Node::_childPolicies (built on the second visit, see below)
   std::vector<float> plane;             // the network's prior of every cell, until `moves` is built
   bool moves_built = false;
+  // widening bookkeeping (see GameSearch::step): the moves picked at least once, and the best never-picked move
+  std::vector<int16_t> picked_list;
+  int32_t best_free = -1;               // index into `moves`, -1 = none left
+  bool best_free_valid = false;
   struct Edge {
     int32_t cell, node;
   };
@@ -108,6 +112,9 @@ struct TreeNode {
     moves.clear();
     plane.clear();
     moves_built = false;
+    picked_list.clear();
+    best_free = -1;
+    best_free_valid = false;
     kids.clear();
     waiting.clear();
     visits = playouts = count = 0;
@@ -317,6 +324,8 @@ class GameSearch {
     maru_b200::LeanRules rules(n.pos.board);
     rules.move_mask(-n.color, mask);
     n.moves.clear();
+    n.picked_list.clear();
+    n.best_free_valid = false;
     for (int cell = 0; cell < cells; cell++)
       if ((mask[cell >> 3] >> (cell & 7)) & 1u)
         n.moves.push_back(Prior{(int16_t)(cell % w), (int16_t)(cell / w), n.plane[(size_t)cell], 0});
@@ -366,6 +375,29 @@ class GameSearch {
       // pow(p, 1) == p and p * e^0 == p exactly: the two transcendental calls per candidate are only
       // made when they can change the result (below the root the reference always passes t = 1, noise = 0)
       const bool tempered = power != 1.0f, noisy = scale != 0.0f;
+      if (!tempered && !noisy && !m.equally) {
+        // The common case (every node below the root, and a PUCB root at temperature 1): priority = p / (picked + 1),
+        // first index wins among equals (Node.cpp:109-140).  A never-picked move has priority p exactly, so the winner
+        // is either the best never-picked move (cached; rescanned only after it has been picked) or one of the few moves
+        // picked before — O(children) instead of O(legal moves) per visited node, same result bit for bit.
+        if (!n.best_free_valid) {
+          n.best_free = -1;
+          for (int i = 0; i < (int)n.moves.size(); i++)
+            if (n.moves[i].picked == 0 && (n.best_free < 0 || n.moves[i].p > n.moves[n.best_free].p)) n.best_free = i;
+          n.best_free_valid = true;
+        }
+        bool have_best = false;
+        auto consider = [&](int i, float pri) {
+          if (!have_best || pri > best_pri || (pri == best_pri && i < best)) {
+            best = i;
+            best_pri = pri;
+            have_best = true;
+          }
+        };
+        if (n.best_free >= 0) consider(n.best_free, n.moves[n.best_free].p / (0 + 1));
+        for (int16_t i : n.picked_list) consider(i, n.moves[i].p / (n.moves[i].picked + 1));
+        if (!have_best) best = 0;
+      } else {
       std::extreme_value_distribution<float> gumbel(0.0f, noisy ? scale : 1.0f);
       for (int i = 0; i < (int)n.moves.size(); i++) {
         const Prior& q = n.moves[i];
@@ -384,9 +416,14 @@ class GameSearch {
           best_pri = pri;
         }
       }
+      }
       Prior& chosen = n.moves[best];
       const int cell = chosen.y * bw + chosen.x;
       if (n.kid_of(cell) < 0 && !n.is_waiting(cell, bw)) n.waiting.push_back(chosen);
+      if (chosen.picked == 0) {
+        n.picked_list.push_back((int16_t)best);
+        if (best == n.best_free) n.best_free_valid = false;
+      }
       chosen.picked += 1;
     }
 
