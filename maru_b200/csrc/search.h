@@ -49,6 +49,13 @@
 
 namespace maru {
 
+// bring-up only: cycle counters around the phases of a visit (tools/search_prof.cpp defines the T_* globals)
+#ifdef MARU_SEARCH_PROFILE
+#define MARU_PROF(var, stmt) do { const unsigned long long _t = __rdtsc(); stmt; var += __rdtsc() - _t; } while (0)
+#else
+#define MARU_PROF(var, stmt) do { stmt; } while (0)
+#endif
+
 struct SearchSetup {
   int width = 19, height = 19;
   float komi = 7.5f;
@@ -303,14 +310,13 @@ class GameSearch {
     n.y = y;
     n.color = -prev.color;
     n.prior = prior;
-    n.pos = prev.pos;
-    n.captured = n.pos.play(x, y, n.color);
+    MARU_PROF(T_follow, n.pos = prev.pos; n.captured = n.pos.play(x, y, n.color));
     n.reset_stats();
   }
 
   void request(int id, maru_state* st) {
     const TreeNode& n = pool_[id];
-    n.pos.to_state(-n.color, setup_.komi, setup_.rule, setup_.superko, /*with_move_mask=*/false, st);
+    MARU_PROF(T_req, n.pos.to_state(-n.color, setup_.komi, setup_.rule, setup_.superko, /*with_move_mask=*/false, st));
     pending_ = id;
   }
 
@@ -321,8 +327,7 @@ class GameSearch {
     n.moves_built = true;
     const int w = setup_.width, cells = setup_.width * setup_.height;
     uint8_t mask[48];
-    maru_b200::LeanRules rules(n.pos.board);
-    rules.move_mask(-n.color, mask);
+    MARU_PROF(T_mask, maru_b200::LeanRules rules(n.pos.board); rules.move_mask(-n.color, mask));
     n.moves.clear();
     n.picked_list.clear();
     n.best_free_valid = false;

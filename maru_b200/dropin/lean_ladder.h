@@ -146,8 +146,10 @@ struct LeanBoard {
     Group g;
     group(index, g);
     if (g.n_libs > 1) return false;
-    std::vector<LeanBoard> stack;
-    stack.reserve(16);
+    // (one scratch stack per thread: the read-out runs for every group in atari of every evaluated leaf, and a heap
+    // allocation per call was a visible share of the host time per leaf)
+    static thread_local std::vector<LeanBoard> stack;
+    stack.clear();
     stack.push_back(*this);
     const int d[4] = {-1, -W, 1, W};
     while (!stack.empty()) {

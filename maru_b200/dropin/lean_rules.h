@@ -110,9 +110,12 @@ struct LeanRules {
     // One pass over the board: cells are scanned in ascending order, so the first unlabelled stone of a group
     // is its smallest cell = its id.  lib_mark[q] == id says "q is already counted as a liberty of this group".
     int16_t lib_mark[LeanBoard::MAXN];
-    for (int i = 0; i < b.N; i++) {
-      gid[i] = (b.c[i] == LeanBoard::kEdge) ? -2 : -1;
-      lib_mark[i] = -1;
+    std::memset(lib_mark, 0xFF, (size_t)b.N * sizeof(int16_t));                    // -1
+    std::memset(gid, 0xFF, (size_t)b.N * sizeof(int16_t));                         // -1: empty (stones are labelled below)
+    {                                                                              // -2: the border ring
+      const int W = b.W, H = b.h + 2;
+      for (int x = 0; x < W; x++) gid[x] = gid[(H - 1) * W + x] = -2;
+      for (int y = 1; y < H - 1; y++) gid[y * W] = gid[y * W + W - 1] = -2;
     }
     int lp = 0, sp = 0;
     int16_t stack[361];
@@ -395,45 +398,50 @@ struct LeanRules {
       bool checks[LeanBoard::MAXN];
       std::memset(checks, 0, sizeof checks);
       std::memset(area_flag[c], 0, sizeof area_flag[c]);
-      for (int index = 0; index < b.N; index++) {
+      // (local copies: through `this` / `b` every store to the scratch arrays forces the compiler to reload them)
+      const int8_t* const cc = b.c;
+      const int16_t* const gg = gid;
+      const int N = b.N, d0 = d[0], d1 = d[1], d2 = d[2], d3 = d[3];
+      int16_t* const aid = area_id[c];
+      bool* const afl = area_flag[c];
+      for (int index = 0; index < N; index++) {
         if (checks[index]) continue;
-        const int ic = b.c[index];
+        const int ic = cc[index];
         if (ic != LeanBoard::kEmpty && ic != op) {
-          area_id[c][index] = -1;
+          aid[index] = -1;
           continue;
         }
         Ids4 connected;
-        for (int a : d) {
-          const int t = index + a;
-          if (t >= 0 && t < b.N && b.c[t] == col) connected.insert(gid[t]);
+        {
+          const int ts[4] = {index + d0, index + d1, index + d2, index + d3};
+          for (int t : ts)
+            if (t >= 0 && t < N && cc[t] == col) connected.insert(gg[t]);
         }
         int16_t stack[4 * LeanBoard::MAXN];
         int sp = 0;
         stack[sp++] = (int16_t)index;
-        area_flag[c][index] = true;
+        afl[index] = true;
+        bool live = true;                                   // == afl[index] (the only flag of the area ever read)
         while (sp > 0) {
           const int pos = stack[--sp];
           if (checks[pos]) continue;
           checks[pos] = true;
-          area_id[c][pos] = (int16_t)index;
-          // once the area is known to be undecided only the labelling is left (flags of other cells of the
-          // area are never read: area_flag is looked up through area_id, i.e. at `index` only)
-          if (area_flag[c][index]) {
+          aid[pos] = (int16_t)index;
+          const int ts[4] = {pos + d0, pos + d1, pos + d2, pos + d3};
+          if (live) {
             Ids4 around;
-            for (int a : d) {
-              const int t = pos + a;
-              if (gid[t] >= 0 && b.c[t] == col) around.insert(gid[t]);
-            }
-            if (around.n == 0) area_flag[c][pos] = false;
-            if (around != connected) area_flag[c][index] = false;
+            for (int t : ts)
+              if (gg[t] >= 0 && cc[t] == col) around.insert(gg[t]);
+            if (around.n == 0) afl[pos] = false;
+            if (around != connected) afl[index] = false;
+            live = afl[index];
           }
-          for (int a : d) {
-            const int t = pos + a;
-            const int tc = b.c[t];
+          for (int t : ts) {
+            const int tc = cc[t];
             if ((tc == LeanBoard::kEmpty || tc == op) && !checks[t]) stack[sp++] = (int16_t)t;
           }
         }
-        if (area_flag[c][index]) {
+        if (afl[index]) {
           for (int k = 0; k < connected.n; k++) {
             pair_group[n_pairs] = connected.v[k];
             pair_area[n_pairs++] = (int16_t)index;
