@@ -16,6 +16,9 @@
 // blocks except the wait for its oldest ticket.
 #include <pthread.h>
 #include <sched.h>
+#include <sys/resource.h>
+#include <sys/syscall.h>
+#include <unistd.h>
 
 #include <atomic>
 #include <chrono>
@@ -248,6 +251,11 @@ static void fail(maru_selfplay* sp, const std::string& what) {
 
 static void worker_run(maru_selfplay* sp, int widx, int n_workers) {
   const maru_selfplay_config& cfg = sp->cfg;
+  // Search workers are throughput threads; the leaf queue's worker thread (gather, launch, scatter: a few per cent of a
+  // core) is latency-critical — the GPU idles until it has run.  When the workers occupy every core of the rank, a lower
+  // priority lets the scheduler put the queue thread on a core the moment it wakes.  (Raising a priority needs
+  // privileges, lowering one does not.)
+  setpriority(PRIO_PROCESS, (id_t)syscall(SYS_gettid), 5);
   if (cfg.cpu_count > 0) {
     cpu_set_t set;
     CPU_ZERO(&set);

@@ -97,6 +97,33 @@ struct LeanBoard {
     group(start, g);
     return g.n_libs;
   }
+  // min(#liberties, limit) of the group containing `start`: the flood stops at the limit-th liberty (every caller
+  // below only asks "exactly one?" or "more than one?", and the groups next to a ladder are often large)
+  int liberties_upto(int start, int limit) const {
+    uint8_t seen[MAXN];
+    std::memset(seen, 0, (size_t)N);
+    const int8_t col = c[start];
+    const int d[4] = {-1, -W, 1, W};
+    int16_t stack[361];
+    int sp = 0, libs = 0;
+    stack[sp++] = (int16_t)start;
+    seen[start] = 1;
+    while (sp > 0) {
+      const int p = stack[--sp];
+      for (int k = 0; k < 4; k++) {
+        const int q = p + d[k];
+        if (seen[q]) continue;
+        if (c[q] == kEmpty) {
+          seen[q] = 1;
+          if (++libs >= limit) return libs;
+        } else if (c[q] == col) {
+          seen[q] = 1;
+          stack[sp++] = (int16_t)q;
+        }
+      }
+    }
+    return libs;
+  }
 
   // Board::_isEnabled(index, color, false)
   bool enabled(int idx, int color) const {
@@ -107,7 +134,7 @@ struct LeanBoard {
       const int q = idx + d[k];
       if (c[q] == kEmpty) return true;
       if (c[q] == kEdge) continue;
-      const int nl = liberties(q);
+      const int nl = liberties_upto(q, 2);
       if (c[q] == color && nl > 1) return true;
       if (c[q] == -color && nl == 1) return true;
     }
@@ -163,7 +190,7 @@ struct LeanBoard {
       for (int i = 0; i < g.n_stones && !escaped; i++) {
         for (int k = 0; k < 4; k++) {
           const int q = g.stones[i] + d[k];
-          if (board.c[q] == op && board.liberties(q) == 1) {
+          if (board.c[q] == op && board.liberties_upto(q, 2) == 1) {
             escaped = true;
             break;
           }
