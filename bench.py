@@ -454,7 +454,10 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
                 mean_batch=positions / max(batches, 1.0), max_batch=int(mx[1].item()),
                 host_us_per_visit=host_s / max(visits, 1.0) * 1e6,
                 gpu_busy_frac=gpu_busy, host_busy_frac=host_busy, stall_frac=stall_s / (wall * world * threads),
-                limiter='host cores (search threads busy, GPU mostly idle)' if gpu_busy < 0.6 else 'GPU',
+                limiter=('host cores: the search threads are saturated (per GPU: (cores - 1) / host_us_per_visit)'
+                         if host_busy > max(gpu_busy, 0.85) else
+                         'GPU: the evaluator is saturated' if gpu_busy >= 0.85 else
+                         'neither saturated (tail of the timed region / batch latency)'),
                 clocks=clocks.summary(), config=cfg,
                 impl='maru_selfplay_* (native search, one descent in flight per game, asynchronous leaf batches)')
 
