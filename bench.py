@@ -62,10 +62,15 @@ def parse():
     ap.add_argument('--sp-board', type=int, default=19)
     ap.add_argument('--sp-visits', type=int, default=50, help='descents per move (reference default --visits 50)')
     ap.add_argument('--sp-moves', type=int, default=8, help='timed moves per game (after 1 untimed move)')
-    ap.add_argument('--sp-games', type=int, default=1920, help='concurrent games per GPU (split over the search threads)')
+    ap.add_argument('--sp-games', type=int, default=0,
+                    help='concurrent games per GPU (0: 1920 over the queue; 480 per lane with evaluator lanes, whose batches '
+                         'are not merged across threads)')
     ap.add_argument('--sp-opening', type=int, default=-1, help='random opening moves (-1: board*board/6)')
     ap.add_argument('--sp-root', default='pucb', choices=['pucb', 'gumbel'])
     ap.add_argument('--sp-max-batch', type=int, default=1024)
+    ap.add_argument('--sp-backend', default='auto', choices=['auto', 'lanes', 'queue'],
+                    help='lanes: the search threads submit their batches themselves (maru_lane_*); queue: through maru_queue; '
+                         'auto: lanes when this rank has <= 8 cores (no core to spare for a queue thread), else the queue')
     ap.add_argument('--sp-no-pin', action='store_true', help='do not pin the search threads to this rank\'s cores')
     ap.add_argument('--sp-lanes', type=int, default=2)
     ap.add_argument('--sp-threads', type=int, default=0,
@@ -405,11 +410,17 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
     cpus = rank_cpus(local)
     # one core stays free for the queue's worker thread (gather, launch, scatter): it is a few % of a core, but the GPU idles
     # until it runs — measured on 4 cores: 3 search threads 429 k visits/s, 4 threads 370-410 k (pinned or not, 2-4 lanes)
-    threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus) - 1)
-    games = max(threads, args.sp_games // threads * threads)      # per GPU, independent of the thread count
+    backend = args.sp_backend if args.sp_backend != 'auto' else ('lanes' if len(cpus) <= 8 else 'queue')
+    if backend == 'lanes':              # no queue thread: every core of the rank searches
+        threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus))
+        n_games = args.sp_games if args.sp_games > 0 else min(480, args.sp_max_batch) * args.sp_lanes * threads
+    else:
+        threads = args.sp_threads if args.sp_threads > 0 else max(1, len(cpus) - 1)
+        n_games = args.sp_games if args.sp_games > 0 else 1920
+    games = max(threads, n_games // threads * threads)
     ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=args.sp_max_batch)
-    q = maru_b200.LeafQueue([ev], batch_size=args.sp_max_batch)
-    sp = selfplay.NativeSelfPlay(q, games=games, size=args.sp_board, visits=args.sp_visits, threads=threads,
+    q = maru_b200.LeafQueue([ev], batch_size=args.sp_max_batch) if backend == 'queue' else None
+    sp = selfplay.NativeSelfPlay(q, evaluator=None if q is not None else ev, games=games, size=args.sp_board, visits=args.sp_visits, threads=threads,
                                  max_moves=10 ** 6, root=args.sp_root, width=16,
                                  noise=1.0 if args.sp_root == 'gumbel' else 0.0, criterion='lcb',
                                  opening_moves=cfg['opening_moves'], restart=True, seed=1000 + rank,
@@ -421,9 +432,15 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
             dist.barrier()
         torch.cuda.synchronize(dev)
     sp.run(1)                                                     # untimed: first move of every game
-    s0, q0 = sp.stats(), q.stats()
+    def qstats():
+        if q is not None:
+            x = q.stats()
+            return x.batches, x.positions, x.device_ms_total, x.max_batch_seen
+        x = sp.stats()                        # lanes: one submit = one evaluator batch
+        return x.submits, x.evals, x.device_s * 1e3, x.max_submit
+    s0 = sp.stats()
     v0, e0, h0, st0, sub0 = s0.visits, s0.evals, s0.host_s, s0.stall_s, s0.submits
-    b0, p0, d0 = q0.batches, q0.positions, q0.device_ms_total
+    b0, p0, d0, _ = qstats()
     sync_all()
     with ClockSampler(local) as clocks:
         t0 = time.perf_counter()
@@ -431,12 +448,14 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         sync_all()
-    s1, q1 = sp.stats(), q.stats()
+    s1 = sp.stats()
+    b1, p1, d1, mb1 = qstats()
     mine = dict(visits=s1.visits - v0, evals=s1.evals - e0, wall_s=dt, host_s=s1.host_s - h0,
-                stall_s=s1.stall_s - st0, submits=s1.submits - sub0, batches=q1.batches - b0,
-                positions=q1.positions - p0, device_ms=q1.device_ms_total - d0, max_batch=q1.max_batch_seen)
+                stall_s=s1.stall_s - st0, submits=s1.submits - sub0, batches=b1 - b0,
+                positions=p1 - p0, device_ms=d1 - d0, max_batch=mb1)
     sp.close()
-    q.close()
+    if q is not None:
+        q.close()
     ev.close()
     sums = torch.tensor([mine['visits'], mine['evals'], mine['batches'], mine['positions'], mine['host_s'],
                          mine['stall_s'], mine['device_ms']], dtype=torch.float64, device=dev)
@@ -459,6 +478,8 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
                          'GPU: the evaluator is saturated' if gpu_busy >= 0.85 else
                          'neither saturated (tail of the timed region / batch latency)'),
                 clocks=clocks.summary(), config=cfg,
+                backend=('evaluator lanes: every search thread stages its leaves in pinned memory and submits the batch '
+                         'itself (maru_lane_*)' if q is None else 'leaf-batch queue (maru_queue_submit_leaves)'),
                 impl='maru_selfplay_* (native search, one descent in flight per game, asynchronous leaf batches)')
 
 

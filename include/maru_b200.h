@@ -271,6 +271,23 @@ int  maru_game_play(maru_game* g, int x, int y, int color);      /* captured sto
 int  maru_game_state(const maru_game* g, int color, float komi, int rule, int superko, int with_move_mask,
                      maru_state* out);
 
+/* ---- evaluator lanes: leaves staged by the caller, no queue thread ------------------------------ */
+/* A lane is the pinned staging of ONE in-flight batch of an evaluator: the caller writes up to max_rows records
+ * straight into maru_lane_states(), submits (H2D + forward + D2H are enqueued on the evaluator's stream, the call
+ * returns), keeps working, and reads maru_lane_leaves() after maru_lane_wait().  Any number of lanes may be in flight
+ * on one evaluator (they run in submission order); the call is thread-safe across lanes, a lane itself belongs to one
+ * thread at a time.  Compared with the queue (whose worker thread gathers jobs into its own staging and scatters the
+ * results back: two copies and two thread hand-offs per batch, Executor.cpp:144-189 in the reference) nothing is copied
+ * on the host and no other thread has to run — what a search thread wants when the search threads own every core. */
+typedef struct maru_lane maru_lane;
+int  maru_eval_lane_create(maru_eval* e, int max_rows, maru_lane** out);
+void maru_lane_destroy(maru_lane* l);
+maru_state* maru_lane_states(maru_lane* l);         /* pinned host memory, [max_rows]                         */
+const maru_leaf* maru_lane_leaves(maru_lane* l);    /* pinned host memory, [max_rows]; valid after wait        */
+int  maru_lane_submit(maru_lane* l, int n);          /* asynchronous; one batch in flight per lane              */
+int  maru_lane_poll(maru_lane* l, int* done);
+int  maru_lane_wait(maru_lane* l);                   /* blocks (the thread sleeps) until the lane's batch is done */
+
 /* ---- native search + self-play game scheduler (rows a10 / f1) -------------------------------- */
 /* Many concurrent games per host thread over the flat board: the reference's tree policy
  * (Node::evaluate, Node.cpp:71-225; Player::_evaluate / play / getCandidates, Player.cpp:93-115,
@@ -318,6 +335,7 @@ typedef struct maru_selfplay_stats {
   double   run_s;                       /* wall time inside maru_selfplay_run                          */
   double   host_s;                      /* summed over workers: tree + record building                 */
   double   stall_s;                     /* summed over workers: blocked on a ticket                    */
+  double   device_s;                    /* evaluator lanes only: CUDA-event time of the batches (GPU busy time) */
 } maru_selfplay_stats;
 typedef struct maru_candidate {         /* deepgo::Candidate (player.py:65-93)                         */
   int32_t x, y, color, visits, playouts;
@@ -330,6 +348,9 @@ typedef struct maru_selfplay maru_selfplay;
 typedef int (*maru_leaf_fn)(const maru_state* s, maru_leaf* out, int n, void* user);
 int  maru_selfplay_create(maru_queue* q, const maru_selfplay_config* cfg, maru_selfplay** out);
 int  maru_selfplay_create_fn(maru_leaf_fn fn, void* user, const maru_selfplay_config* cfg, maru_selfplay** out);
+/* The same scheduler straight on ONE evaluator through lanes (above): every search thread stages its leaves in pinned
+ * memory and submits them itself; there is no queue thread to schedule, so all of a rank's cores can search. */
+int  maru_selfplay_create_eval(maru_eval* e, const maru_selfplay_config* cfg, maru_selfplay** out);
 void maru_selfplay_destroy(maru_selfplay* sp);
 /* Force a move in one game (Player::play): openings, replays.  Not while maru_selfplay_run is active. */
 int  maru_selfplay_play(maru_selfplay* sp, int game, int x, int y);

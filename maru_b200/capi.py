@@ -59,7 +59,7 @@ class SelfPlayConfig(C.Structure):
 class SelfPlayStats(C.Structure):
     _fields_ = [('visits', C.c_uint64), ('evals', C.c_uint64), ('expansions', C.c_uint64), ('moves', C.c_uint64),
                 ('games_finished', C.c_uint64), ('submits', C.c_uint64), ('max_submit', C.c_uint64),
-                ('run_s', C.c_double), ('host_s', C.c_double), ('stall_s', C.c_double)]
+                ('run_s', C.c_double), ('host_s', C.c_double), ('stall_s', C.c_double), ('device_s', C.c_double)]
 
 
 class CandidateRec(C.Structure):
@@ -82,7 +82,9 @@ ABI_SYMBOLS = [
     'maru_queue_get_stats', 'maru_ladder_flags', 'maru_rules_eval', 'maru_game_create', 'maru_game_clone',
     'maru_game_destroy', 'maru_game_play', 'maru_game_state', 'maru_last_error', 'maru_abi_version',
     'maru_queue_submit_leaves', 'maru_queue_poll', 'maru_queue_wait', 'maru_queue_set_coalesce',
-    'maru_eval_set_device_board', 'maru_selfplay_create', 'maru_selfplay_create_fn', 'maru_selfplay_destroy', 'maru_selfplay_play',
+    'maru_eval_set_device_board', 'maru_eval_lane_create', 'maru_lane_destroy', 'maru_lane_states', 'maru_lane_leaves',
+    'maru_lane_submit', 'maru_lane_poll', 'maru_lane_wait', 'maru_selfplay_create_eval',
+    'maru_selfplay_create', 'maru_selfplay_create_fn', 'maru_selfplay_destroy', 'maru_selfplay_play',
     'maru_selfplay_run', 'maru_selfplay_get_stats', 'maru_selfplay_get_moves', 'maru_selfplay_get_candidates',
 ]
 
@@ -153,6 +155,17 @@ def load_library():
     lib.maru_queue_set_coalesce.argtypes = [vp, ci, ci]
     lib.maru_selfplay_create.argtypes = [vp, C.POINTER(SelfPlayConfig), C.POINTER(vp)]
     lib.maru_selfplay_create_fn.argtypes = [vp, vp, C.POINTER(SelfPlayConfig), C.POINTER(vp)]
+    lib.maru_selfplay_create_eval.argtypes = [vp, C.POINTER(SelfPlayConfig), C.POINTER(vp)]
+    lib.maru_eval_lane_create.argtypes = [vp, ci, C.POINTER(vp)]
+    lib.maru_lane_destroy.argtypes = [vp]
+    lib.maru_lane_destroy.restype = None
+    lib.maru_lane_states.argtypes = [vp]
+    lib.maru_lane_states.restype = vp
+    lib.maru_lane_leaves.argtypes = [vp]
+    lib.maru_lane_leaves.restype = vp
+    lib.maru_lane_submit.argtypes = [vp, ci]
+    lib.maru_lane_poll.argtypes = [vp, C.POINTER(ci)]
+    lib.maru_lane_wait.argtypes = [vp]
     lib.maru_selfplay_destroy.argtypes = [vp]
     lib.maru_selfplay_destroy.restype = None
     lib.maru_selfplay_play.argtypes = [vp, ci, ci, ci]
@@ -382,11 +395,46 @@ class Evaluator:
         _check(self.lib, self.lib.maru_eval_set_device_board(self.handle, width, height),
                'maru_eval_set_device_board')
 
+    def lane(self, max_rows: int) -> 'EvalLane':
+        """Pinned staging of one in-flight batch (maru_lane_*): fill .states[:n], submit(n), wait() -> .leaves[:n]."""
+        return EvalLane(self, max_rows)
+
     def sync(self) -> None:
         _check(self.lib, self.lib.maru_eval_sync(self.handle), 'maru_eval_sync')
 
     def stream(self) -> int:
         return int(self.lib.maru_eval_stream(self.handle) or 0)
+
+
+class EvalLane:
+    """maru_lane: the caller stages records in pinned memory and submits the batch itself (no queue thread)."""
+
+    def __init__(self, ev: Evaluator, max_rows: int):
+        self.lib, self.ev = ev.lib, ev
+        h = C.c_void_p()
+        _check(self.lib, self.lib.maru_eval_lane_create(ev.handle, max_rows, C.byref(h)), 'maru_eval_lane_create')
+        self.handle = h
+        self.states = np.ctypeslib.as_array(C.cast(self.lib.maru_lane_states(h), C.POINTER(C.c_uint8)),
+                                            shape=(max_rows, STATE_SIZE))
+        self.leaves = np.ctypeslib.as_array(C.cast(self.lib.maru_lane_leaves(h), C.POINTER(C.c_float)),
+                                            shape=(max_rows, LEAF_SIZE))
+
+    def submit(self, n: int) -> None:
+        _check(self.lib, self.lib.maru_lane_submit(self.handle, n), 'maru_lane_submit')
+
+    def poll(self) -> bool:
+        d = C.c_int(0)
+        _check(self.lib, self.lib.maru_lane_poll(self.handle, C.byref(d)), 'maru_lane_poll')
+        return bool(d.value)
+
+    def wait(self) -> None:
+        _check(self.lib, self.lib.maru_lane_wait(self.handle), 'maru_lane_wait')
+
+    def close(self) -> None:
+        if getattr(self, 'handle', None):
+            self.states = self.leaves = None
+            self.lib.maru_lane_destroy(self.handle)
+            self.handle = None
 
 
 class LeafQueue:

@@ -319,6 +319,47 @@ int maru_ladder_flags(const int8_t* colors, int width, int height, int ko_x, int
   return 0;
 }
 
+// ---- evaluator lanes (engine.cu: Engine::lane_*) ------------------------------------------------------------------
+struct maru_lane {
+  maru::Lane l;
+};
+static maru::Lane* LN(maru_lane* l) { return reinterpret_cast<maru::Lane*>(l); }
+
+int maru_eval_lane_create(maru_eval* ev, int max_rows, maru_lane** out) {
+  if (ev == nullptr || out == nullptr) {
+    maru::set_error("maru_eval_lane_create: null argument");
+    return 1;
+  }
+  *out = reinterpret_cast<maru_lane*>(E(ev)->lane_create(max_rows));
+  return *out == nullptr ? 1 : 0;
+}
+void maru_lane_destroy(maru_lane* l) {
+  if (l != nullptr) LN(l)->e->lane_destroy(LN(l));
+}
+maru_state* maru_lane_states(maru_lane* l) { return l ? LN(l)->h_states : nullptr; }
+const maru_leaf* maru_lane_leaves(maru_lane* l) { return l ? LN(l)->h_leaves : nullptr; }
+int maru_lane_submit(maru_lane* l, int n) {
+  if (l == nullptr) {
+    maru::set_error("maru_lane_submit: null lane");
+    return 1;
+  }
+  return LN(l)->e->lane_submit(LN(l), n);
+}
+int maru_lane_poll(maru_lane* l, int* done) {
+  if (l == nullptr || done == nullptr) {
+    maru::set_error("maru_lane_poll: null argument");
+    return 1;
+  }
+  return LN(l)->e->lane_poll(LN(l), done);
+}
+int maru_lane_wait(maru_lane* l) {
+  if (l == nullptr) {
+    maru::set_error("maru_lane_wait: null lane");
+    return 1;
+  }
+  return LN(l)->e->lane_wait(LN(l), nullptr);
+}
+
 int maru_eval_set_device_board(maru_eval* ev, int width, int height) {
   if (ev == nullptr || width < 0 || height < 0 || width > 19 || height > 19 || ((width == 0) != (height == 0))) {
     maru::set_error("maru_eval_set_device_board: bad argument");

@@ -1096,6 +1096,98 @@ int Engine::wait_slot(int slot_idx, float* device_ms) {
   return 0;
 }
 
+// ---- evaluator lanes -------------------------------------------------------------------------------------------
+// The device side of a lane is the evaluator's own staging (slot 2): every batch is one H2D -> forward -> D2H sequence
+// enqueued atomically under the evaluator's mutex on its one stream, so the D2H of batch i has drained the device
+// buffers before the H2D of batch i+1 overwrites them, whichever lane or blocking call i+1 comes from.
+Lane* Engine::lane_create(int rows) {
+  if (rows < 1 || rows > max_batch) {
+    set_error("maru_eval_lane_create: rows outside 1..max_batch");
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lock(mu);
+  if (cudaSetDevice(gpu_id) != cudaSuccess) return nullptr;
+  Lane* l = new (std::nothrow) Lane();
+  if (l == nullptr) return nullptr;
+  l->e = this;
+  l->rows = rows;
+  cudaError_t er = cudaMallocHost(&l->h_states, (size_t)rows * sizeof(maru_state));
+  if (er == cudaSuccess) er = cudaMallocHost(&l->h_leaves, (size_t)rows * sizeof(maru_leaf));
+  if (er == cudaSuccess) er = cudaEventCreateWithFlags(&l->done, cudaEventBlockingSync | cudaEventDisableTiming);
+  if (er == cudaSuccess) er = cudaEventCreate(&l->t0);
+  if (er == cudaSuccess) er = cudaEventCreate(&l->t1);
+  if (er != cudaSuccess) {
+    set_error(std::string("maru_eval_lane_create: ") + cudaGetErrorString(er));
+    if (l->h_states) cudaFreeHost(l->h_states);
+    if (l->h_leaves) cudaFreeHost(l->h_leaves);
+    if (l->done) cudaEventDestroy(l->done);
+    if (l->t0) cudaEventDestroy(l->t0);
+    if (l->t1) cudaEventDestroy(l->t1);
+    delete l;
+    return nullptr;
+  }
+  return l;
+}
+
+void Engine::lane_destroy(Lane* l) {
+  if (l == nullptr) return;
+  std::lock_guard<std::mutex> lock(mu);
+  cudaSetDevice(gpu_id);
+  if (l->inflight) cudaEventSynchronize(l->done);
+  cudaFreeHost(l->h_states);
+  cudaFreeHost(l->h_leaves);
+  cudaEventDestroy(l->done);
+  cudaEventDestroy(l->t0);
+  cudaEventDestroy(l->t1);
+  delete l;
+}
+
+int Engine::lane_submit(Lane* l, int n) {
+  if (n < 1 || n > l->rows || l->inflight) {
+    set_error("maru_lane_submit: n outside 1..max_rows, or the lane's previous batch has not been waited for");
+    return 1;
+  }
+  NvtxRange range("maru.lane.submit");
+  std::lock_guard<std::mutex> lock(mu);
+  CK(cudaSetDevice(gpu_id));
+  Slot& sl = slot[2];
+  CK(cudaMemcpyAsync(sl.d_states, l->h_states, (size_t)n * sizeof(maru_state), cudaMemcpyHostToDevice, stream));
+  CK(cudaEventRecord(l->t0, stream));
+  int bw = 0, bh = 0;
+  uniform_board(l->h_states, n, &bw, &bh);
+  if (forward_device(KIND_LEAVES, sl.d_states, sl.d_out, n, bw, bh)) return 1;
+  CK(cudaEventRecord(l->t1, stream));
+  CK(cudaMemcpyAsync(l->h_leaves, sl.d_out, (size_t)n * sizeof(maru_leaf), cudaMemcpyDeviceToHost, stream));
+  CK(cudaEventRecord(l->done, stream));
+  l->n = n;
+  l->inflight = true;
+  return 0;
+}
+
+int Engine::lane_wait(Lane* l, float* device_ms) {
+  if (!l->inflight) return 0;
+  CK(cudaEventSynchronize(l->done));
+  l->inflight = false;
+  if (device_ms) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, l->t0, l->t1);
+    *device_ms = ms;
+  }
+  return 0;
+}
+
+int Engine::lane_poll(Lane* l, int* done) {
+  *done = 1;
+  if (!l->inflight) return 0;
+  const cudaError_t er = cudaEventQuery(l->done);
+  if (er == cudaErrorNotReady) {
+    *done = 0;
+    return 0;
+  }
+  CK(er);
+  return 0;
+}
+
 // K1 alone on host buffers: records -> reference rows (bit-exact Board::getInputs)
 int Engine::encode_rows_host(const maru_state* st, float* out_rows, int n) {
   std::lock_guard<std::mutex> lock(mu);

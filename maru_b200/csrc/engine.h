@@ -82,6 +82,17 @@ struct Geom {
   }
 };
 
+struct Engine;
+// pinned staging of one in-flight batch (include/maru_b200.h: maru_lane)
+struct Lane {
+  Engine* e = nullptr;
+  maru_state* h_states = nullptr;
+  maru_leaf* h_leaves = nullptr;
+  int rows = 0, n = 0;
+  bool inflight = false;
+  cudaEvent_t done = nullptr, t0 = nullptr, t1 = nullptr;
+};
+
 struct GraphKey {
   int kind, bucket;
   const void* in;
@@ -200,6 +211,12 @@ struct Engine {
   int enqueue_slot(int kind, int slot_idx, int n);
   int wait_slot(int slot_idx, float* device_ms);
   int encode_rows_host(const maru_state* s, float* out_rows, int n);
+  // evaluator lanes (maru_lane_*): leaves staged by the caller in pinned memory, enqueued by the caller's thread
+  Lane* lane_create(int rows);
+  void lane_destroy(Lane* l);
+  int lane_submit(Lane* l, int n);
+  int lane_wait(Lane* l, float* device_ms);
+  int lane_poll(Lane* l, int* done);
 };
 
 }  // namespace maru

@@ -36,6 +36,17 @@ struct Slot {
   int kind = 0, n = 0;
 };
 
+struct Engine;
+struct Lane {
+  Engine* e = nullptr;
+  std::vector<maru_state> vs;
+  std::vector<maru_leaf> vl;
+  maru_state* h_states = nullptr;
+  maru_leaf* h_leaves = nullptr;
+  int rows = 0, n = 0;
+  bool inflight = false;
+};
+
 struct Engine {
   int gpu_id = 0, max_batch = 0;
   double device_ms_last = 0;
@@ -73,6 +84,30 @@ struct Engine {
     std::this_thread::sleep_for(std::chrono::microseconds(50));     // "GPU time": lets batches accumulate
     if (s.kind == KIND_LEAVES)
       for (int i = 0; i < s.n; i++) eval(s.h_states[i], reinterpret_cast<maru_leaf*>(s.h_out) + i);
+    if (ms) *ms = 0.05f;
+    return 0;
+  }
+  Lane* lane_create(int rows) {
+    Lane* l = new Lane();
+    l->e = this;
+    l->rows = rows;
+    l->vs.resize((size_t)rows);
+    l->vl.resize((size_t)rows);
+    l->h_states = l->vs.data();
+    l->h_leaves = l->vl.data();
+    return l;
+  }
+  void lane_destroy(Lane* l) { delete l; }
+  int lane_submit(Lane* l, int n) {
+    std::lock_guard<std::mutex> g(mu);
+    l->n = n;
+    l->inflight = true;
+    return 0;
+  }
+  int lane_wait(Lane* l, float* ms) {
+    if (l->inflight)
+      for (int i = 0; i < l->n; i++) eval(l->h_states[i], &l->h_leaves[i]);
+    l->inflight = false;
     if (ms) *ms = 0.05f;
     return 0;
   }

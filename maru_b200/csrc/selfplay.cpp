@@ -207,19 +207,22 @@ struct GameRunner {
   int moves_done_in_run = 0;
 };
 
-struct Lane {
+struct GameLane {
   std::vector<int> games;               // indices into maru_selfplay::games
-  std::vector<maru_state> states;
+  std::vector<maru_state> states;       // (queue / function back ends; an evaluator lane stages in pinned memory)
   std::vector<maru_leaf> leaves;
   std::vector<int> owner;               // game of row i of the batch in flight
   int n = 0;
   maru_ticket* ticket = nullptr;
+  Lane* direct = nullptr;               // evaluator lane (maru_selfplay_create_eval)
   bool inflight = false;
+  maru_state* in() { return direct != nullptr ? direct->h_states : states.data(); }
+  const maru_leaf* out() const { return direct != nullptr ? direct->h_leaves : leaves.data(); }
 };
 
 struct WorkerStats {
   uint64_t submits = 0, max_submit = 0;
-  double host_s = 0, stall_s = 0;
+  double host_s = 0, stall_s = 0, device_s = 0;
 };
 
 }  // namespace maru
@@ -227,6 +230,7 @@ struct WorkerStats {
 struct maru_selfplay {
   maru_selfplay_config cfg{};
   maru_queue* queue = nullptr;
+  maru::Engine* engine = nullptr;        // evaluator lanes: the search threads submit their batches themselves
   maru_leaf_fn fn = nullptr;
   void* fn_user = nullptr;
   std::mutex fn_mu;                      // a caller-supplied evaluator is called by one worker at a time
@@ -263,45 +267,71 @@ static void worker_run(maru_selfplay* sp, int widx, int n_workers) {
     pthread_setaffinity_np(pthread_self(), sizeof(set), &set);   // best effort
   }
   const int n_lanes = cfg.lanes > 0 ? cfg.lanes : 2;
-  std::vector<Lane> lanes((size_t)n_lanes);
+  std::vector<GameLane> lanes((size_t)n_lanes);
   int k = 0;
   for (int g = widx; g < (int)sp->games.size(); g += n_workers) lanes[(size_t)(k++ % n_lanes)].games.push_back(g);
-  for (Lane& L : lanes) {
-    L.states.resize(L.games.size());
-    L.leaves.resize(L.games.size());
+  bool broken = false;
+  for (GameLane& L : lanes) {
     L.owner.resize(L.games.size());
+    if (L.games.empty()) continue;
+    if (sp->engine != nullptr) {
+      L.direct = sp->engine->lane_create((int)L.games.size());
+      if (L.direct == nullptr) {
+        fail(sp, std::string("evaluator lane: ") + g_last_error);
+        broken = true;
+      }
+    } else {
+      L.states.resize(L.games.size());
+      L.leaves.resize(L.games.size());
+    }
   }
   WorkerStats& ws = sp->wstats[(size_t)widx];
-  bool any = true, broken = false;
+  bool any = true;
   while (any && !broken && !sp->failed.load(std::memory_order_relaxed)) {
     any = false;
-    for (Lane& L : lanes) {
+    for (GameLane& L : lanes) {
       if (L.games.empty()) continue;
       auto t0 = Clock::now();
       if (L.inflight) {
         L.inflight = false;
-        if (sp->queue != nullptr && maru_queue_wait(sp->queue, L.ticket) != 0) {
-          fail(sp, std::string("leaf batch failed: ") + maru_last_error());
+        int rc = 0;
+        if (L.direct != nullptr) {
+          float ms = 0;
+          rc = sp->engine->lane_wait(L.direct, &ms);
+          ws.device_s += ms * 1e-3;
+        } else if (sp->queue != nullptr) {
+          rc = maru_queue_wait(sp->queue, L.ticket);
+        }
+        if (rc != 0) {
+          fail(sp, std::string("leaf batch failed: ") + g_last_error);
           broken = true;
           break;
         }
         const auto t1 = Clock::now();
         ws.stall_s += secs(t0, t1);
         t0 = t1;
-        for (int i = 0; i < L.n; i++)
-          sp->games[(size_t)L.owner[(size_t)i]]->search.deliver(L.states[(size_t)i], L.leaves[(size_t)i]);
+        const maru_state* in = L.in();
+        const maru_leaf* out = L.out();
+        for (int i = 0; i < L.n; i++) sp->games[(size_t)L.owner[(size_t)i]]->search.deliver(in[i], out[i]);
       }
       L.n = 0;
+      maru_state* in = L.in();
       for (int g : L.games)
-        if (sp->games[(size_t)g]->advance(&L.states[(size_t)L.n])) L.owner[(size_t)L.n++] = g;
+        if (sp->games[(size_t)g]->advance(&in[L.n])) L.owner[(size_t)L.n++] = g;
       ws.host_s += secs(t0, Clock::now());
       if (L.n == 0) continue;
       any = true;
       ws.submits++;
       if ((uint64_t)L.n > ws.max_submit) ws.max_submit = (uint64_t)L.n;
-      if (sp->queue != nullptr) {
+      if (L.direct != nullptr) {
+        if (sp->engine->lane_submit(L.direct, L.n) != 0) {
+          fail(sp, std::string("leaf submit failed: ") + g_last_error);
+          broken = true;
+          break;
+        }
+      } else if (sp->queue != nullptr) {
         if (maru_queue_submit_leaves(sp->queue, L.states.data(), L.leaves.data(), L.n, &L.ticket) != 0) {
-          fail(sp, std::string("leaf submit failed: ") + maru_last_error());
+          fail(sp, std::string("leaf submit failed: ") + g_last_error);
           broken = true;
           break;
         }
@@ -316,10 +346,13 @@ static void worker_run(maru_selfplay* sp, int widx, int n_workers) {
       L.inflight = true;
     }
   }
-  // stopping early (a failure here or in another worker): still retire this worker's tickets, the
-  // queue writes into the lanes' buffers until then
-  for (Lane& L : lanes)
-    if (L.inflight && sp->queue != nullptr) maru_queue_wait(sp->queue, L.ticket);
+  // stopping early (a failure here or in another worker): still retire this worker's batches, the evaluator writes
+  // into the lanes' buffers until then
+  for (GameLane& L : lanes) {
+    if (L.inflight && L.direct != nullptr) sp->engine->lane_wait(L.direct, nullptr);
+    else if (L.inflight && sp->queue != nullptr) maru_queue_wait(sp->queue, L.ticket);
+    if (L.direct != nullptr) sp->engine->lane_destroy(L.direct);
+  }
 }
 
 static int check_cfg(const maru_selfplay_config* c) {
@@ -332,8 +365,8 @@ static int check_cfg(const maru_selfplay_config* c) {
   return 0;
 }
 
-static int create(maru_queue* q, maru_leaf_fn fn, void* user, const maru_selfplay_config* cfg, maru_selfplay** out) {
-  if (out == nullptr || (q == nullptr && fn == nullptr) || check_cfg(cfg)) {
+static int create(maru_queue* q, Engine* e, maru_leaf_fn fn, void* user, const maru_selfplay_config* cfg, maru_selfplay** out) {
+  if (out == nullptr || (q == nullptr && fn == nullptr && e == nullptr) || check_cfg(cfg)) {
     set_error("maru_selfplay_create: bad argument");
     return 1;
   }
@@ -343,6 +376,7 @@ static int create(maru_queue* q, maru_leaf_fn fn, void* user, const maru_selfpla
     sp->cfg = *cfg;
     if (sp->cfg.threads > sp->cfg.games) sp->cfg.threads = sp->cfg.games;
     sp->queue = q;
+    sp->engine = e;
     sp->fn = fn;
     sp->fn_user = user;
     for (int g = 0; g < cfg->games; g++) {
@@ -370,7 +404,7 @@ int maru_selfplay_create(maru_queue* q, const maru_selfplay_config* cfg, maru_se
     maru::set_error("maru_selfplay_create: no leaf-batch queue (there is no CPU evaluator)");
     return 1;
   }
-  return maru::create(q, nullptr, nullptr, cfg, out);
+  return maru::create(q, nullptr, nullptr, nullptr, cfg, out);
 }
 
 int maru_selfplay_create_fn(maru_leaf_fn fn, void* user, const maru_selfplay_config* cfg, maru_selfplay** out) {
@@ -378,7 +412,15 @@ int maru_selfplay_create_fn(maru_leaf_fn fn, void* user, const maru_selfplay_con
     maru::set_error("maru_selfplay_create_fn: no leaf function");
     return 1;
   }
-  return maru::create(nullptr, fn, user, cfg, out);
+  return maru::create(nullptr, nullptr, fn, user, cfg, out);
+}
+
+int maru_selfplay_create_eval(maru_eval* e, const maru_selfplay_config* cfg, maru_selfplay** out) {
+  if (e == nullptr) {
+    maru::set_error("maru_selfplay_create_eval: no evaluator (there is no CPU evaluator)");
+    return 1;
+  }
+  return maru::create(nullptr, reinterpret_cast<maru::Engine*>(e), nullptr, nullptr, cfg, out);
 }
 
 void maru_selfplay_destroy(maru_selfplay* sp) { delete sp; }
@@ -446,6 +488,7 @@ int maru_selfplay_get_stats(maru_selfplay* sp, maru_selfplay_stats* st) {
     if (w.max_submit > st->max_submit) st->max_submit = w.max_submit;
     st->host_s += w.host_s;
     st->stall_s += w.stall_s;
+    st->device_s += w.device_s;
   }
   st->run_s = sp->run_s;
   return 0;

@@ -229,13 +229,15 @@ class SelfPlayScheduler:
 class NativeSelfPlay:
     """The product scheduler: `maru_selfplay_*` (maru_b200/csrc/selfplay.cpp, search.h).
 
-    queue: a `LeafQueue` on this rank's GPU, or `leaf_fn` = a C function pointer of type maru_leaf_fn
-    (another evaluator: the CPU tests pass the oracle's synthetic one).  Games are this rank's shard."""
+    queue: a `LeafQueue` on this rank's GPU; or evaluator=: an `Evaluator` used directly through lanes (the search threads
+    stage their leaves in pinned memory and submit them themselves: no queue thread, every core of the rank can search);
+    or leaf_fn=: a C function pointer of type maru_leaf_fn (another evaluator: the CPU tests pass the oracle's synthetic
+    one).  Games are this rank's shard."""
 
     ROOTS = {'pucb': 0, 'gumbel': 1}
     CRITERIA = {'lcb': 0, 'visits': 1}
 
-    def __init__(self, queue=None, *, leaf_fn=None, games: int, size: int | Tuple[int, int] = 19, visits: int = 50,
+    def __init__(self, queue=None, *, evaluator=None, leaf_fn=None, games: int, size: int | Tuple[int, int] = 19, visits: int = 50,
                  threads: int = 1, max_moves: int = 400, root: str = 'pucb', width: int = 16, noise: float = 0.0,
                  temperature: float = 1.0, criterion: str = 'lcb', komi: float = 7.5, rule: int = 0,
                  superko: bool = False, eval_leaf_only: bool = False, opening_moves: int = 0,
@@ -253,9 +255,11 @@ class NativeSelfPlay:
             cpu_first=(min(cpus) if cpus else 0), cpu_count=(len(cpus) if cpus else 0), lanes=lanes,
             record=int(record))
         self.games = games
-        self._keep = (queue, leaf_fn)
+        self._keep = (queue, evaluator, leaf_fn)
         h_ = C.c_void_p()
-        if queue is not None:
+        if evaluator is not None:       # evaluator lanes: the search threads submit their own batches (no queue thread)
+            rc = self.lib.maru_selfplay_create_eval(evaluator.handle, C.byref(cfg), C.byref(h_))
+        elif queue is not None:
             rc = self.lib.maru_selfplay_create(queue.handle, C.byref(cfg), C.byref(h_))
         else:
             rc = self.lib.maru_selfplay_create_fn(C.cast(leaf_fn, C.c_void_p), None, C.byref(cfg), C.byref(h_))

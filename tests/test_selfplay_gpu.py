@@ -150,3 +150,43 @@ def test_native_selfplay_throughput_shape(built_lib, model_dir):
         sp.close()
         q.close()
         ev.close()
+
+
+def test_evaluator_lanes_equal_the_queue_and_drive_the_scheduler(built_lib, model_dir):
+    """maru_lane_*: records staged by the caller in pinned memory, submitted by the caller's thread (no queue thread).
+    Same results as the queue bit for bit, several lanes in flight, and the same self-play games as over the queue."""
+    import maru_b200
+    from maru_b200 import selfplay
+    path = model_dir('b2c64')
+    _, states = load_positions('19')
+    _, s9 = load_positions('9')
+    ev = maru_b200.Evaluator(path, gpu=0, max_batch=64)
+    q = maru_b200.LeafQueue([ev], batch_size=64)
+    try:
+        want, want9 = q.execute_leaves(states[:40]), q.execute_leaves(s9[:30])
+        a, b = ev.lane(40), ev.lane(64)
+        a.states[:40] = states[:40]
+        b.states[:30] = s9[:30]
+        a.submit(40)
+        b.submit(30)                                   # two lanes in flight, retired out of order
+        b.wait()
+        assert np.array_equal(b.leaves[:30], want9)
+        a.wait()
+        assert a.poll() and np.array_equal(a.leaves[:40], want)
+        with pytest.raises(maru_b200.MaruB200Error):
+            a.submit(41)                               # more rows than the lane holds
+        a.close()
+        b.close()
+        games = []
+        for kw in (dict(queue=q), dict(evaluator=ev)):
+            sp = selfplay.NativeSelfPlay(kw.get('queue'), evaluator=kw.get('evaluator'), games=12, size=9, visits=20,
+                                         threads=3, max_moves=6, root='pucb', criterion='lcb', opening_moves=4, seed=2)
+            sp.run(6)
+            st = sp.stats()
+            assert st.moves == 72 and st.visits == 20 * 72
+            games.append([sp.moves(g) for g in range(12)])
+            sp.close()
+        assert games[0] == games[1]
+    finally:
+        q.close()
+        ev.close()

@@ -5,7 +5,8 @@
 //   * 12 threads of blocking maru_queue_execute_leaves with n = 1 (how Evaluator.cpp:52 submits),
 //   * 4 threads of asynchronous tickets (submit / poll / wait, several in flight, retired out of order),
 //   * coalescing on and off while jobs are in flight, two evaluators behind one queue (least-loaded routing),
-//   * a self-play scheduler (4 workers x 3 lanes, 48 games, restarts) on the same queue at the same time.
+//   * a self-play scheduler (4 workers x 3 lanes, 48 games, restarts) on the same queue at the same time,
+//   * a second scheduler on evaluator lanes (maru_selfplay_create_eval: the workers submit their own batches).
 // Exit code 0 and no "WARNING: ThreadSanitizer" on stderr = pass (tests/test_tsan.py runs it when built).
 #include "../maru_b200/csrc/queue.cpp"
 #include "../maru_b200/csrc/selfplay.cpp"
@@ -90,7 +91,21 @@ int main() {
   th.emplace_back([&] {
     if (maru_selfplay_run(sp, 10)) bad++;
   });
+  // a second scheduler straight on an evaluator through lanes (no queue thread), at the same time
+  maru_selfplay* sp2 = nullptr;
+  maru_selfplay_config cfg2 = cfg;
+  cfg2.games = 24;
+  cfg2.threads = 3;
+  cfg2.seed = 9;
+  if (maru_selfplay_create_eval(evs[1], &cfg2, &sp2)) return 4;
+  th.emplace_back([&] {
+    if (maru_selfplay_run(sp2, 10)) bad++;
+  });
   for (auto& t : th) t.join();
+  maru_selfplay_stats st2;
+  maru_selfplay_get_stats(sp2, &st2);
+  if (st2.moves != 240 || st2.visits != 12ull * 240ull) bad++;
+  maru_selfplay_destroy(sp2);
   maru_selfplay_stats st;
   maru_selfplay_get_stats(sp, &st);
   maru_queue_stats qs;
