@@ -648,9 +648,14 @@ def run_b200(args):
         small = small_boards_leg(args, model_path, local, dev)
 
     # ---------------- selfplay: every rank plays its shard of the games ---------------------------------
-    sp_block = None
+    sp_block = sp_13 = None
     if not args.no_selfplay:
         sp_block = selfplay_leg(args, model_path, rank, local, world, dist, dev)
+        if world == 1 and (args.sp_board, args.sp_root) == (19, 'pucb'):
+            # BASELINE.json configs[3]: 13x13 Gumbel sequential-halving self-play, many concurrent games, 1 GPU
+            a13 = argparse.Namespace(**vars(args))
+            a13.sp_board, a13.sp_root, a13.sp_opening = 13, 'gumbel', -1
+            sp_13 = selfplay_leg(a13, model_path, rank, local, world, dist, dev)
 
     # ---------------- reduce over ranks ----------------------------------------------------------
     from maru_b200 import shard
@@ -743,7 +748,7 @@ def run_b200(args):
             gpu_launches=info.launches_per_forward * args.steps,
             clocks=clock, roofline=roofline, cpu_baseline=cpu, kernels=table,
             wall_ms_per_step=t_wall / args.steps * 1e3, sustained=sustained,
-            gpu_reference=gpu_ref, small_boards=small, selfplay=sp_block)
+            gpu_reference=gpu_ref, small_boards=small, selfplay=sp_block, selfplay_13x13_gumbel=sp_13)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
