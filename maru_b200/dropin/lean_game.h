@@ -7,7 +7,13 @@
 // LeanGame::to_state produces byte for byte the record maru_b200::state_from_board() builds from a
 // reference Board through its public getters (tests/test_lean_game.py replays random games move by move
 // on both and compares all 448 bytes at every ply, move mask included).
-// One copy is ~0.6 KB of plain data (the reference copies ~440 Ren objects with three std::set each).
+// One copy is ~0.9 KB of plain data (the reference copies ~440 Ren objects with three std::set each).
+//
+// Liberties are kept INCREMENTALLY: `info[y*w+x]` = colour | min(liberties, 8) << 3 of the stone's group (the record's
+// cell byte without the ladder bit) is updated by play() for the groups the move can have changed — the played stone's
+// group, the neighbouring opponent groups, the groups around captured stones — instead of re-labelling the whole board
+// for every evaluated leaf (which was the largest part of the host time per visit once the move filter had become lazy).
+// The ladder flags cannot be kept: a ladder depends on stones far away, so every group in atari is read out again.
 #pragma once
 
 #include "lean_rules.h"
@@ -19,9 +25,13 @@ struct LeanGame {
   LeanBoard board;
   int16_t hist[2][3];          // [0] black, [1] white: ring of board indices, -1 = empty slot
   uint8_t hist_pos[2];         // next slot to overwrite (History::_index)
+  uint8_t info_valid;          // info[] describes the board (0 after `board` was edited behind play()'s back)
+  uint8_t info[361];           // per board cell: MARU_CELL_* colour | min(#liberties, 8) << MARU_CELL_LIB_SHIFT
 
   void init(int width, int height) {
     board.init(width, height);
+    std::memset(info, 0, sizeof info);
+    info_valid = 1;
     for (int s = 0; s < 2; s++) {
       hist_pos[s] = 0;
       for (int i = 0; i < 3; i++) hist[s][i] = -1;
@@ -36,12 +46,42 @@ struct LeanGame {
       return 0;
     }
     const int idx = board.index(x, y);
-    const int r = board.play(idx, color);
+    int16_t captured[361];
+    const int r = board.play(idx, color, captured);
     if (r < 0) return -1;
+    if (info_valid) refresh_info(idx, captured, r);
     const int s = (color == LeanBoard::kBlack) ? 0 : 1;
     hist[s][hist_pos[s]] = (int16_t)idx;
     hist_pos[s] = (uint8_t)((hist_pos[s] + 1) % 3);
     return r;
+  }
+
+  // After a legal move at `idx` that emptied `captured[0..n_cap)`: liberties can only have changed for the group of the
+  // played stone (which absorbed its friendly neighbours), for the opponent groups next to it (one liberty less) and for
+  // every group next to a captured stone (liberties gained).  Each such group is flooded once.
+  void refresh_info(int idx, const int16_t* captured, int n_cap) {
+    const int w = board.w, W = board.W;
+    const int d[4] = {-1, -W, 1, W};
+    uint8_t seen[LeanBoard::MAXN];
+    std::memset(seen, 0, (size_t)board.N);
+    LeanBoard::Group g;
+    auto relabel = [&](int start) {
+      const int8_t c = board.c[start];
+      if ((c != LeanBoard::kBlack && c != LeanBoard::kWhite) || seen[start]) return;
+      board.group(start, g);
+      const int libs = g.n_libs > 8 ? 8 : g.n_libs;
+      const uint8_t cell = (uint8_t)(((c == LeanBoard::kBlack) ? MARU_CELL_BLACK : MARU_CELL_WHITE) | (libs << MARU_CELL_LIB_SHIFT));
+      for (int k = 0; k < g.n_stones; k++) {
+        const int p = g.stones[k];
+        seen[p] = 1;
+        info[(p / W - 1) * w + (p % W - 1)] = cell;
+      }
+    };
+    for (int i = 0; i < n_cap; i++) info[(captured[i] / W - 1) * w + (captured[i] % W - 1)] = MARU_CELL_EMPTY;
+    relabel(idx);
+    for (int k = 0; k < 4; k++) relabel(idx + d[k]);
+    for (int i = 0; i < n_cap; i++)
+      for (int k = 0; k < 4; k++) relabel(captured[i] + d[k]);
   }
 
   // the record of Board::getInputs' inputs for `color` to move (include/maru_b200.h: maru_state)
@@ -55,33 +95,45 @@ struct LeanGame {
     st->superko = superko ? 1 : 0;
     st->komi = komi;
 
-    LeanRules rules(board);                       // group labelling: liberties per stone
-    // Board::_updateShicho: only groups in atari are read out (Board.cpp:1045-1067); the labelling above
-    // already knows them, so the board is not flood-filled a second time (LeanBoard::ladder_flags does)
-    uint8_t ladder[361];
-    std::memset(ladder, 0, (size_t)(w * h));
-    for (int idx = 0; idx < board.N; idx++) {
-      if (rules.gid[idx] != idx || rules.n_libs[idx] != 1) continue;
-      if (!board.ladder(idx)) continue;
-      for (int i = 0; i < rules.n_stones[idx]; i++) {
-        const int p = rules.stone_pool[rules.stone_off[idx] + i];
-        ladder[(p / board.W - 1) * w + (p % board.W - 1)] = 1;
-      }
-    }
-    for (int y = 0; y < h; y++) {
-      for (int x = 0; x < w; x++) {
-        const int idx = board.index(x, y);
-        const int c = board.c[idx];
-        uint8_t cell = MARU_CELL_EMPTY;
-        if (c == LeanBoard::kBlack || c == LeanBoard::kWhite) {
-          int libs = rules.n_libs[rules.gid[idx]];
-          if (libs > 8) libs = 8;
-          cell = (c == LeanBoard::kBlack) ? MARU_CELL_BLACK : MARU_CELL_WHITE;
-          cell |= (uint8_t)(libs << MARU_CELL_LIB_SHIFT);
-          if (ladder[y * w + x]) cell |= MARU_CELL_LADDER;
+    if (!info_valid) {                                  // (only after direct edits of `board`): label everything once
+      LeanRules rules(board);
+      LeanGame* self = const_cast<LeanGame*>(this);
+      for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+          const int idx = board.index(x, y);
+          const int c = board.c[idx];
+          uint8_t cell = MARU_CELL_EMPTY;
+          if (c == LeanBoard::kBlack || c == LeanBoard::kWhite) {
+            int libs = rules.n_libs[rules.gid[idx]];
+            if (libs > 8) libs = 8;
+            cell = (uint8_t)(((c == LeanBoard::kBlack) ? MARU_CELL_BLACK : MARU_CELL_WHITE) | (libs << MARU_CELL_LIB_SHIFT));
+          }
+          self->info[y * w + x] = cell;
         }
-        st->cells[y * w + x] = cell;
-      }
+      self->info_valid = 1;
+    }
+    std::memcpy(st->cells, info, (size_t)(w * h));
+    // Board::_updateShicho: only groups in atari are read out (Board.cpp:1045-1067)
+    {
+      uint8_t done[361];
+      bool any = false;
+      for (int i = 0; i < w * h; i++)
+        if ((info[i] >> MARU_CELL_LIB_SHIFT) == 1) {
+          if (!any) {
+            std::memset(done, 0, (size_t)(w * h));
+            any = true;
+          }
+          if (done[i]) continue;
+          const int idx = board.index(i % w, i / w);
+          LeanBoard::Group g;
+          board.group(idx, g);
+          const bool caught = board.ladder(idx);
+          for (int k = 0; k < g.n_stones; k++) {
+            const int p = g.stones[k], cell = (p / board.W - 1) * w + (p % board.W - 1);
+            done[cell] = 1;
+            if (caught) st->cells[cell] |= MARU_CELL_LADDER;
+          }
+        }
     }
 
     // Board::getHistories: ring read oldest -> newest, empty slots dropped; the record wants newest first
@@ -107,6 +159,7 @@ struct LeanGame {
     }
 
     if (with_move_mask) {
+      LeanRules rules(board);
       rules.move_mask(color, st->move_mask);
       st->flags |= MARU_STATE_HAS_MASK;
     }

@@ -141,8 +141,9 @@ struct LeanBoard {
     return false;
   }
 
-  // Board::play for an on-board point: number of captured stones, -1 if not allowed (board unchanged)
-  int play(int idx, int color) {
+  // Board::play for an on-board point: number of captured stones, -1 if not allowed (board unchanged).
+  // `captured` (optional, room for 361 cells) receives the cells that were emptied.
+  int play(int idx, int color, int16_t* captured = nullptr) {
     if (!enabled(idx, color)) return -1;
     c[idx] = (int8_t)color;
     const int d[4] = {-1, -W, 1, W};
@@ -151,12 +152,14 @@ struct LeanBoard {
     for (int k = 0; k < 4; k++) {
       const int q = idx + d[k];
       if (c[q] != -color) continue;
+      if (liberties_upto(q, 1) != 0) continue;        // (most neighbours are alive: no need to collect their stones)
       group(q, g);
-      if (g.n_libs == 0) {
-        removed += g.n_stones;
-        for (int i = 0; i < g.n_stones; i++) c[g.stones[i]] = kEmpty;
-        ko_index = q;
+      for (int i = 0; i < g.n_stones; i++) {
+        c[g.stones[i]] = kEmpty;
+        if (captured != nullptr) captured[removed + i] = g.stones[i];
       }
+      removed += g.n_stones;
+      ko_index = q;
     }
     group(idx, g);
     if (removed != 1 || g.n_stones > 1 || g.n_libs > 1) {

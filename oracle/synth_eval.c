@@ -27,9 +27,10 @@ static void synth_one(const maru_state* s, maru_leaf* out) {
   memset(out, 0, sizeof(*out));
   uint64_t h = 0x9e3779b97f4a7c15ull;
   const int cells = s->width * s->height;
-  for (int i = 0; i < cells; i++) h = mix(h ^ ((uint64_t)(s->cells[i] & MARU_CELL_COLOR_MASK) + 3u * (uint64_t)i));
+  for (int i = 0; i < cells; i++) h = mix(h ^ ((uint64_t)s->cells[i] + 131u * (uint64_t)i));   /* colour, liberties AND ladder flag */
   h = mix(h ^ (uint64_t)(uint8_t)s->color);
   h = mix(h ^ ((uint64_t)s->ko_x << 8 | s->ko_y));
+  for (int i = 0; i < 12; i++) h = mix(h ^ ((uint64_t)((const uint8_t*)s->hist)[i] << (i & 7)));   /* move history */
   double w[361], sum = 0.0;
   for (int i = 0; i < cells; i++) {
     const double u = (double)(mix(h ^ (0x1234567ull * (uint64_t)(i + 1))) >> 11) / 9007199254740992.0;
