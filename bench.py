@@ -73,7 +73,7 @@ def parse():
                          'threads submit their own batches (maru_lane_*; measured: 510 k vs 440 k visits/s on one B200 restricted to '
                          '4 cores, but 2.74 M vs 3.08 M on the 8-GPU box whose 32 logical cores are then all taken)')
     ap.add_argument('--sp-no-pin', action='store_true', help='do not pin the search threads to this rank\'s cores')
-    ap.add_argument('--sp-lanes', type=int, default=2)
+    ap.add_argument('--sp-lanes', type=int, default=3)
     ap.add_argument('--sp-threads', type=int, default=0,
                     help='search threads per rank (0: this rank\'s cores minus one for the queue thread)')
     return ap.parse_args()
