@@ -74,6 +74,8 @@ def parse():
                          '4 cores, but 2.74 M vs 3.08 M on the 8-GPU box whose 32 logical cores are then all taken)')
     ap.add_argument('--sp-no-pin', action='store_true', help='do not pin the search threads to this rank\'s cores')
     ap.add_argument('--sp-lanes', type=int, default=3)
+    ap.add_argument('--sp-evaluators', type=int, default=1,
+                    help='evaluators (streams + buffer sets) behind the queue on this GPU: batches of two overlap on the device')
     ap.add_argument('--sp-threads', type=int, default=0,
                     help='search threads per rank (0: this rank\'s cores minus one for the queue thread)')
     return ap.parse_args()
@@ -420,7 +422,9 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
         n_games = args.sp_games if args.sp_games > 0 else 1920
     games = max(threads, n_games // threads * threads)
     ev = maru_b200.Evaluator(model_path, gpu=local, max_batch=args.sp_max_batch)
-    q = maru_b200.LeafQueue([ev], batch_size=args.sp_max_batch) if backend == 'queue' else None
+    more = [maru_b200.Evaluator(model_path, gpu=local, max_batch=args.sp_max_batch)
+            for _ in range(args.sp_evaluators - 1)] if backend == 'queue' else []
+    q = maru_b200.LeafQueue([ev] + more, batch_size=args.sp_max_batch) if backend == 'queue' else None
     sp = selfplay.NativeSelfPlay(q, evaluator=None if q is not None else ev, games=games, size=args.sp_board, visits=args.sp_visits, threads=threads,
                                  max_moves=10 ** 6, root=args.sp_root, width=16,
                                  noise=1.0 if args.sp_root == 'gumbel' else 0.0, criterion='lcb',
@@ -457,6 +461,8 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
     sp.close()
     if q is not None:
         q.close()
+    for e in more:
+        e.close()
     ev.close()
     sums = torch.tensor([mine['visits'], mine['evals'], mine['batches'], mine['positions'], mine['host_s'],
                          mine['stall_s'], mine['device_ms']], dtype=torch.float64, device=dev)
