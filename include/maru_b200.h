@@ -178,6 +178,9 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
 #define MARU_DBG_TIMELINE 3           /* 1: every conv launch stamps %globaltimer (see debug_timeline)  */
 #define MARU_DBG_FLOW_TRACE_CTA 4     /* >= 0: that CTA of a flow kernel stamps every item (debug_trace, [256][8]) */
 #define MARU_DBG_FLOW_TRACE_LAUNCH 5  /* which flow launch of the forward is traced (default 0)          */
+#define MARU_DBG_ATT_TRACE_CTA 6      /* EXPERIMENTS builds: >= 0: that CTA of the first attention launch stamps clock64 per step
+                                         (debug_trace, [64 steps][8]: softmax group {S seen, S read, P written}, control warp
+                                         {P seen, PV issued, QK issued}) */
 int  maru_eval_debug_set(maru_eval* e, int key, int value);
 /* [64 launches][first CTA, last CTA][8] ns stamps: entry, prologue done, dependency resolved, first
  * operands landed, first accumulator ready, exit. */

@@ -226,6 +226,14 @@ __global__ void __launch_bounds__(ATT_THREADS) attention_kernel(const AttnParams
 // rows 20..399 fit 3 tiles of 128 (rows 400..403 of the last tile belong to the next position's halo
 // or to the tail rows: they are computed and dropped).
 // =============================================================================================
+// per-step clock64 stamps of one CTA (debug key 6, tools/att_trace.py), experiment builds only: the product kernel
+// carries none of it
+#ifdef MARU_EXPERIMENTS
+#define ATT_STAMP(cond, step, slot) do { if (tr != nullptr && (cond) && (step) < 64) tr[(step) * 16 + (slot)] = clock64(); } while (0)
+#else
+#define ATT_STAMP(cond, step, slot) do { } while (0)
+#endif
+
 constexpr int A2_SM_WARPS = 8;              // warps 0..7 softmax/epilogue: lane group = w & 3, group = w >> 2
 constexpr int A2_WARPS = A2_SM_WARPS + 1;   // warp 8: control (bulk loads + MMA issue)
 constexpr int A2_THREADS = A2_WARPS * 32;
@@ -325,6 +333,9 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
   const int head = blockIdx.x - pos * heads;
   if (pos >= ((p.n_dev != nullptr) ? *p.n_dev : p.n)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#ifdef MARU_EXPERIMENTS
+  long long* const tr = (p.trace != nullptr && (int)blockIdx.x == p.trace_cta) ? p.trace : nullptr;
+#endif
   // frame geometry (common.cuh): 20 / 400 for the 19x19 frame; a compact frame of a small board has fewer rows, hence
   // fewer key parts and query tiles (9x9: 100 rows = 2 parts x 1 tile instead of 5 x 3)
   const int pos_rows = p.pos_rows, q0 = p.pitch;
@@ -449,6 +460,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       const int part = (int)((plist >> (3 * pi)) & 7u);
       const int sb = step & 1, ob = tile & 1;
       mbar_wait(&p_full[sb], (step >> 1) & 1);     // P[sb] written (and fenced), S[sb] consumed
+      ATT_STAMP(lane == 0, step, 4);
       if (pi == 0 && tile >= 2) mbar_wait(&o_empty[ob], 0);     // epilogue of tile-2 has read O[ob]
       tc_fence_after();
       if (elect_one()) {
@@ -463,6 +475,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         if (pi == np - 1) umma_commit(&o_full[ob]);
       }
       __syncwarp();
+      ATT_STAMP(lane == 0, step, 5);
       // the last QK of this tile completed before p_full(step): its Q buffer can take tile+2
       if (pi == np - 1 && tile + 2 < nt && elect_one()) load_q(tile + 2);
       __syncwarp();
@@ -470,6 +483,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       // what allows the softmax group to overwrite P[sb] at step+2. (Issuing it earlier, as soon as S[sb]
       // had been read out, was tried: no gain, and it needs an extra P-free barrier.)
       if (step + 2 < n_steps) issue_qk(step + 2);
+      ATT_STAMP(lane == 0, step, 6);
     }
   } else {
     // =========================== softmax + epilogue warps ===========================
@@ -593,8 +607,10 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
           c = fminf(sqrtf(ss * maxk2) * 1.0001f + 1e-3f, 96.0f);
         }
       }
+      ATT_STAMP(lg == 0 && lane == 0, step, 0);
       mbar_wait(&s_full[grp], (step >> 1) & 1);
       tc_fence_after();
+      ATT_STAMP(lg == 0 && lane == 0, step, 1);
       // s_full(step) was committed after PV(step-2) and, for step >= 5*tile+1, after the last PV of
       // the previous tile: its O is complete, the epilogue does not stall
       {
@@ -613,12 +629,14 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         exp_store16<(A2_POLY_MASK >> 2) & 1>(vb, c, pb, 4, trow);
         exp_store16<(A2_POLY_MASK >> 3) & 1>(vb + 16, c, pb, 6, trow);
         tmem_ld_wait();
+        ATT_STAMP(lg == 0 && lane == 0, step, 2);
         exp_store16<(A2_POLY_MASK >> 4) & 1>(va, c, pb, 8, trow);
       }
       fence_async_smem();     // P visible to the async proxy
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[grp]);
+      ATT_STAMP(lg == 0 && lane == 0, step, 3);
       // (with fewer than three parts per tile a group may not see a later step of the tile: it takes the epilogue at once)
       if (epi_done < tile && (step >= tile_first_step + 1 || np < 3)) {
         epilogue(epi_done);

@@ -384,6 +384,7 @@ int maru_eval_debug_set(maru_eval* ev, int key, int value) {
   else if (key == MARU_DBG_TIMELINE) e->dbg_timeline = value;
   else if (key == MARU_DBG_FLOW_TRACE_CTA) e->dbg_flow_trace_cta = value;
   else if (key == MARU_DBG_FLOW_TRACE_LAUNCH) e->dbg_flow_trace_chain = value;
+  else if (key == MARU_DBG_ATT_TRACE_CTA) e->dbg_att_trace_cta = value;
   else {
     maru::set_error("maru_eval_debug_set: unknown key");
     return 1;

@@ -852,6 +852,8 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
       ap.n_dev = n_dev;
       ap.pdl = (dbg_desc & 1) ? 0 : 1;
       ap.dbg = (dbg_desc >> 1) & 3;
+      ap.trace = (dbg_att_trace_cta >= 0 && ai == 1) ? d_trace : nullptr;
+      ap.trace_cta = dbg_att_trace_cta;
       if (flush_chain(st)) return 1;
       if (!(dbg_stop_after >= 0 && launches_done >= dbg_stop_after)) {
         launches_done++;

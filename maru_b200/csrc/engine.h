@@ -145,6 +145,7 @@ struct Engine {
   int dbg_timeline = 0;
   int dbg_flow_trace_cta = -1;     // debug key 4: CTA of the flow kernel to trace per item; key 5: which flow launch
   int dbg_flow_trace_chain = 0;
+  int dbg_att_trace_cta = -1;      // debug key 6 (EXPERIMENTS builds)
   void clear_graphs();
 
   // per-launch profiling (maru_eval_profile_states): when prof != nullptr every launch is bracketed

@@ -159,6 +159,8 @@ struct AttnParams {
   const int* n_dev;
   int pdl;
   int dbg;                   // bit0: swap LBO/SBO of the MN-major V descriptor, bit1: legacy mma.sync kernel
+  long long* trace;          // EXPERIMENTS builds: [64 steps][8] clock64 stamps of CTA trace_cta (tools/att_trace.py)
+  int trace_cta;
 };
 cudaError_t configure_attention();
 cudaError_t launch_attention(const AttnParams& p, cudaStream_t stream);
