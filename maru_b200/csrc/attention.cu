@@ -547,8 +547,10 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     auto epilogue = [&](int tile) {
       const int ob = tile & 1;
       const int row = q0 + tile * TILE_M + trow;
+      ATT_STAMP(warp == 0 && lane == 0, 32 + tile, 0);
       mbar_wait(&o_full[ob], (tile >> 1) & 1);
       tc_fence_after();
+      ATT_STAMP(warp == 0 && lane == 0, 32 + tile, 1);
       uint32_t o[16];
       tmem_ld16(t_lane + A2_O_COL + ob * A2_NV + grp * 16, o);
       const uint32_t lbits = tmem_ld1(t_lane + A2_O_COL + ob * A2_NV + 32);
@@ -556,6 +558,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_empty[ob]);
+      ATT_STAMP(warp == 0 && lane == 0, 32 + tile, 2);
       if (row < pos_rows) {
         const bool on = s_mask[row] != 0;
         const float inv = on ? 1.0f / __uint_as_float(lbits) : 0.0f;
@@ -572,6 +575,7 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
           *reinterpret_cast<uint4*>(p.out + off) = w;
         }
       }
+      ATT_STAMP(warp == 0 && lane == 0, 32 + tile, 3);
     };
 
     float c = 0.0f;

@@ -33,6 +33,9 @@ for s in range(16):
     if t[s].max() == 0:
         continue
     print(f'{s:4d} ' + ' '.join(f'{(int(v - t0) if v > 0 else -1):11d}' for v in t[s, :7]))
+print('epilogue of tile 0..2 (group 0, warp 0): start, O ready, O read, stored:')
+for k in range(3):
+    print('   ', [int(v - t0) if v > 0 else -1 for v in t[32 + k, :4]])
 d = np.diff(np.sort(t[:15, 3][t[:15, 3] > 0]))
 print('P-done to P-done (cycles):', d.tolist(), 'mean', float(d.mean()) if len(d) else None)
 ev.close()
