@@ -52,6 +52,49 @@ def test_two_ranks_shard_and_reduce():
     assert shard.evals_per_sec(a0) == pytest.approx(256 * 11 / 0.020)
 
 
+def _selfplay_worker(rank: int, world: int, port: int, out):
+    """One rank of the self-play job: its shard of the games on the native scheduler (synthetic evaluator: no GPU here),
+    then the reduction bench.py does — visits summed, wall time = slowest rank."""
+    import ctypes as C
+    import time
+    import torch.distributed as dist
+    from maru_b200 import selfplay, shard
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    lib = C.CDLL(str(ROOT / 'oracle' / '_build' / 'liboracle_synth.so'))
+    fn = C.cast(lib.oracle_synth_leaves, C.c_void_p)
+    games = shard.shard_items(10, rank, world)
+    sp = selfplay.NativeSelfPlay(leaf_fn=fn, games=len(games), size=9, visits=16, threads=2, max_moves=5, root='gumbel',
+                                 width=4, noise=1.0, criterion='visits', seed=100 + rank, opening_moves=2)
+    dist.barrier()
+    t0 = time.perf_counter()
+    sp.run(5)
+    st = sp.stats()
+    agg = shard.reduce_stats(shard.RankStats(visits=st.visits, positions=st.evals, batches=st.moves,
+                                             wall_s=time.perf_counter() - t0), dist)
+    out[rank] = (len(games), st.visits, st.moves, agg)
+    sp.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_play_their_shards_of_the_games():
+    if not (ROOT / 'oracle' / '_build' / 'liboracle_synth.so').exists() or \
+            not (ROOT / 'maru_b200' / 'lib' / 'libmaru_b200.so').exists():
+        pytest.skip('native libraries not built')
+    world = 2
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_selfplay_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    (n0, v0, m0, a0), (n1, v1, m1, a1) = out[0], out[1]
+    assert n0 + n1 == 10 and m0 == 5 * n0 and m1 == 5 * n1 and v0 == 16 * m0 and v1 == 16 * m1
+    assert a0['visits'] == a1['visits'] == v0 + v1 == 16 * 50
+    assert a0['wall_s'] == a1['wall_s'] > 0
+    from maru_b200 import selfplay
+    assert selfplay.visits_per_sec(a0) > 0
+
+
 def test_single_process_passthrough():
     from maru_b200 import shard
     agg = shard.reduce_stats(shard.RankStats(positions=5, device_ms=1.0))
