@@ -326,6 +326,7 @@ typedef struct maru_selfplay_config {
   int32_t cpu_first, cpu_count;         /* cpu_count > 0: pin worker i to core cpu_first + i % cpu_count */
   int32_t lanes;                        /* batches in flight per worker (0 -> 2)                      */
   int32_t record;                       /* 1: keep every move's candidate list (maru_selfplay_get_candidates) */
+  int32_t use_ucb1;                     /* PUCB root only: UCB1 instead of PUCB at the root (run.py --search ucb1, Node.cpp:211-212) */
 } maru_selfplay_config;
 typedef struct maru_selfplay_stats {
   uint64_t visits;                      /* root descents (Player.cpp:300)                              */

@@ -53,7 +53,8 @@ class SelfPlayConfig(C.Structure):
                 ('max_moves', C.c_int32), ('root', C.c_int32), ('root_width', C.c_int32), ('noise', C.c_float),
                 ('temperature', C.c_float), ('criterion', C.c_int32), ('eval_leaf_only', C.c_int32),
                 ('opening_moves', C.c_int32), ('restart', C.c_int32), ('seed', C.c_uint64),
-                ('cpu_first', C.c_int32), ('cpu_count', C.c_int32), ('lanes', C.c_int32), ('record', C.c_int32)]
+                ('cpu_first', C.c_int32), ('cpu_count', C.c_int32), ('lanes', C.c_int32), ('record', C.c_int32),
+                ('use_ucb1', C.c_int32)]
 
 
 class SelfPlayStats(C.Structure):

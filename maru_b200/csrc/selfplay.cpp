@@ -149,6 +149,7 @@ struct GameRunner {
           }
           RootMode m;
           m.temperature = cfg->temperature;
+          m.use_ucb1 = cfg->use_ucb1 != 0;
           if (cfg->root == MARU_ROOT_GUMBEL) {
             m.equally = true;
             m.width = phases[phase].first;

@@ -80,13 +80,15 @@ class Move:
 class PlayerAdapter:
     """Uniform view of a reference-style player (see module docstring)."""
 
-    def __init__(self, player):
+    def __init__(self, player, **extra):
         self.player = player
+        self.extra = extra           # fixed keyword arguments of every evaluate() call (use_ucb1=...)
 
     def initialize(self) -> None:
         self.player.initialize()
 
     def evaluate(self, **kw) -> List[Move]:
+        kw = dict(kw, **self.extra)
         out = []
         for c in self.player.evaluate(**kw):
             if isinstance(c, dict):
@@ -165,11 +167,12 @@ class SelfPlayScheduler:
 
     def __init__(self, make_player: Callable[[int], object], n_games: int, visits: int,
                  max_moves: int = 400, root: str = 'gumbel', width: int = 16, noise: float = 1.0,
-                 temperature: float = 1.0, criterion: str = 'visits', rank: int = 0, world: int = 1):
+                 temperature: float = 1.0, criterion: str = 'visits', rank: int = 0, world: int = 1,
+                 use_ucb1: bool = False):
         if root not in ('gumbel', 'pucb'):
             raise ValueError(f'unknown root search {root!r}')
         self.games = shard.shard_items(n_games, rank, world)
-        self.players = [PlayerAdapter(make_player(g)) for g in self.games]
+        self.players = [PlayerAdapter(make_player(g), **({'use_ucb1': True} if use_ucb1 else {})) for g in self.games]
         self.visits, self.max_moves = visits, max_moves
         self.root, self.width, self.noise = root, width, noise
         self.temperature, self.criterion = temperature, criterion
@@ -242,7 +245,7 @@ class NativeSelfPlay:
                  temperature: float = 1.0, criterion: str = 'lcb', komi: float = 7.5, rule: int = 0,
                  superko: bool = False, eval_leaf_only: bool = False, opening_moves: int = 0,
                  restart: bool = False, seed: int = 0, cpus: Optional[Sequence[int]] = None, lanes: int = 2,
-                 record: bool = False):
+                 record: bool = False, use_ucb1: bool = False):
         import ctypes as C
         from . import capi
         self.lib = capi.load_library()
@@ -253,7 +256,7 @@ class NativeSelfPlay:
             temperature=temperature, criterion=self.CRITERIA[criterion], eval_leaf_only=int(eval_leaf_only),
             opening_moves=opening_moves, restart=int(restart), seed=seed,
             cpu_first=(min(cpus) if cpus else 0), cpu_count=(len(cpus) if cpus else 0), lanes=lanes,
-            record=int(record))
+            record=int(record), use_ucb1=int(use_ucb1))
         self.games = games
         self._keep = (queue, evaluator, leaf_fn)
         h_ = C.c_void_p()

@@ -46,14 +46,15 @@ def openings(n_games, size, n_moves, seed):
     return out
 
 
-def reference_games(size, n_games, visits, max_moves, root, width, criterion, opens, temperature=1.0):
+def reference_games(size, n_games, visits, max_moves, root, width, criterion, opens, temperature=1.0,
+                    use_ucb1=False, eval_leaf_only=False):
     from oracle import ref
     proc = ref.RefProcessor('synthetic', gpus=[0], batch_size=16, kind='search_synth')
     made = []
 
     class Opened:
         def __init__(self, g):
-            self.p = ref.RefPlayer(proc, 1, size, size)
+            self.p = ref.RefPlayer(proc, 1, size, size, eval_leaf_only=eval_leaf_only)
             self.g = g
 
         def initialize(self):
@@ -71,7 +72,7 @@ def reference_games(size, n_games, visits, max_moves, root, width, criterion, op
         made.append(Opened(g))
         return made[-1]
     sched = selfplay.SelfPlayScheduler(make, n_games, visits, max_moves=max_moves, root=root, width=width,
-                                       noise=0.0, temperature=temperature, criterion=criterion)
+                                       noise=0.0, temperature=temperature, criterion=criterion, use_ucb1=use_ucb1)
     sched.run()
     recs = sched.records
     for p in made:
@@ -80,10 +81,11 @@ def reference_games(size, n_games, visits, max_moves, root, width, criterion, op
     return recs
 
 
-def native_games(fn, size, n_games, visits, max_moves, root, width, criterion, opens, threads=2, temperature=1.0):
+def native_games(fn, size, n_games, visits, max_moves, root, width, criterion, opens, threads=2, temperature=1.0,
+                 use_ucb1=False, eval_leaf_only=False):
     sp = selfplay.NativeSelfPlay(leaf_fn=fn, games=n_games, size=size, visits=visits, threads=threads,
                                  max_moves=max_moves, root=root, width=width, noise=0.0, temperature=temperature,
-                                 criterion=criterion, record=True)
+                                 criterion=criterion, record=True, use_ucb1=use_ucb1, eval_leaf_only=eval_leaf_only)
     for g, mv in enumerate(opens):
         for (x, y) in mv:
             assert sp.play(g, x, y) >= 0
@@ -98,23 +100,27 @@ def key(c):
     return (c.x, c.y, c.color, c.visits, c.playouts, np.float32(c.value).tobytes())
 
 
-@pytest.mark.parametrize('size,root,visits,width,criterion,temperature', [
-    (9, 'pucb', 40, 0, 'lcb', 1.0),
-    (9, 'gumbel', 48, 8, 'lcb', 1.0),
-    (13, 'pucb', 30, 0, 'lcb', 1.0),
-    (9, 'pucb', 25, 0, 'lcb', 0.6),          # root temperature: pow() on the priors (Node.cpp:100-114)
-    (7, 'gumbel', 33, 5, 'lcb', 1.0),
+@pytest.mark.parametrize('size,root,visits,width,criterion,temperature,ucb1,leaf_only', [
+    (9, 'pucb', 40, 0, 'lcb', 1.0, False, False),
+    (9, 'gumbel', 48, 8, 'lcb', 1.0, False, False),
+    (13, 'pucb', 30, 0, 'lcb', 1.0, False, False),
+    (9, 'pucb', 25, 0, 'lcb', 0.6, False, False),    # root temperature: pow() on the priors (Node.cpp:100-114)
+    (7, 'gumbel', 33, 5, 'lcb', 1.0, False, False),
+    (19, 'pucb', 30, 0, 'lcb', 1.0, False, False),
+    (9, 'pucb', 40, 0, 'lcb', 1.0, True, False),      # run.py --search ucb1 (Node.cpp:211-212, 493-502)
+    (9, 'pucb', 40, 0, 'lcb', 1.0, False, True),      # run.py --eval-leaf-only (Player.cpp:337-341)
 ])
-def test_native_search_replays_the_reference_search(synth_fn, size, root, visits, width, criterion, temperature):
+def test_native_search_replays_the_reference_search(synth_fn, size, root, visits, width, criterion, temperature, ucb1,
+                                                    leaf_only):
     from oracle import ref
     if not ref.available('search_synth') or not ref.available('board'):
         pytest.skip('oracle/_ref search_synth not present')
     _, fn = synth_fn
     n_games, max_moves = 6, 12
     opens = openings(n_games, size, 4, seed=size * 100 + visits)
-    want = reference_games(size, n_games, visits, max_moves, root, width, criterion, opens, temperature)
+    want = reference_games(size, n_games, visits, max_moves, root, width, criterion, opens, temperature, ucb1, leaf_only)
     got, st = native_games(fn, size, n_games, visits, max_moves, root, width, criterion, opens,
-                           temperature=temperature)
+                           temperature=temperature, use_ucb1=ucb1, eval_leaf_only=leaf_only)
     assert st.moves == sum(len(m) for m, _ in got)
     assert st.visits == visits * st.moves                       # exactly `visits` descents per move
     compared = 0
