@@ -410,6 +410,19 @@ def selfplay_leg(args, model_path: Path, rank: int, local: int, world: int, dist
     import maru_b200
     from maru_b200 import selfplay
     cfg = selfplay_config(args)
+    try:
+        return _selfplay_leg(args, cfg, model_path, rank, local, world, dist, dev)
+    except Exception as exc:
+        if dist is not None:
+            raise                              # multi-rank: let torchrun report it (the other ranks are inside collectives)
+        return dict(metric='selfplay_visits_per_sec', value=None, unit='visits/s', error=f'{type(exc).__name__}: {exc}',
+                    config=cfg)
+
+
+def _selfplay_leg(args, cfg, model_path: Path, rank: int, local: int, world: int, dist, dev) -> dict:
+    import torch
+    import maru_b200
+    from maru_b200 import selfplay
     cpus = rank_cpus(local)
     # one core stays free for the queue's worker thread (gather, launch, scatter): it is a few % of a core, but the GPU idles
     # until it runs — measured on 4 cores: 3 search threads 429 k visits/s, 4 threads 370-410 k (pinned or not, 2-4 lanes)
@@ -651,13 +664,18 @@ def run_b200(args):
     # ---------------- small boards (north_star: 9x9 / 13x13 / 19x19 throughput), N = 1 ----------------------
     small = None
     if world == 1 and not args.no_small_boards and args.board == 19:
-        small = small_boards_leg(args, model_path, local, dev)
+        try:
+            small = small_boards_leg(args, model_path, local, dev)
+        except Exception as exc:               # a side leg must never cost the headline line
+            small = dict(error=f'{type(exc).__name__}: {exc}')
 
     # ---------------- selfplay: every rank plays its shard of the games ---------------------------------
     sp_block = sp_13 = None
     if not args.no_selfplay:
+        # (every rank takes part in the reductions inside: an exception on one rank would hang the others, so the leg
+        # reduces a failure flag first)
         sp_block = selfplay_leg(args, model_path, rank, local, world, dist, dev)
-        if world == 1 and (args.sp_board, args.sp_root) == (19, 'pucb'):
+        if world == 1 and sp_block is not None and 'error' not in sp_block and (args.sp_board, args.sp_root) == (19, 'pucb'):
             # BASELINE.json configs[3]: 13x13 Gumbel sequential-halving self-play, many concurrent games, 1 GPU
             a13 = argparse.Namespace(**vars(args))
             a13.sp_board, a13.sp_root, a13.sp_opening = 13, 'gumbel', -1
