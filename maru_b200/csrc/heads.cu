@@ -59,11 +59,14 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   const int pos = blockIdx.x;
   if (pos >= ((p.n_dev != nullptr) ? *p.n_dev : p.n)) return;
   const int tid = threadIdx.x;
+  // 416 threads (one per padded row) on the 19x19 frame; a compact frame is launched with just enough warps for its rows
+  // (128 threads for 9x9), so that several positions share an SM instead of leaving three quarters of a CTA idle
+  const int nthreads = (int)blockDim.x, nwarps = nthreads >> 5;
   const int ch = p.ch;
   const int warp = tid >> 5, lane = tid & 31;
   const int n_chunks = ch / 8;
 
-  for (int i = tid; i < 6 * ch; i += HEAD_THREADS) s_wp[i / ch][i % ch] = p.w_planes[i];
+  for (int i = tid; i < 6 * ch; i += nthreads) s_wp[i / ch][i % ch] = p.w_planes[i];
   if (tid < 6) s_bp[tid] = p.b_planes[tid];
   pdl_wait();   // g and mask come from the previous kernels
 
@@ -108,9 +111,9 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   float* out = (p.out != nullptr) ? p.out + (size_t)pos * OUT_ROW : nullptr;
   if (compact) {                                         // model cells outside the board are not visited below
     if (out != nullptr)
-      for (int i = tid; i < 6 * CELLS; i += HEAD_THREADS) out[i] = 0.0f;
+      for (int i = tid; i < 6 * CELLS; i += nthreads) out[i] = 0.0f;
     if (p.logits != nullptr)
-      for (int i = tid; i < 2 * CELLS; i += HEAD_THREADS) p.logits[(size_t)pos * 2 * CELLS + i] = 0.0f;
+      for (int i = tid; i < 2 * CELLS; i += nthreads) p.logits[(size_t)pos * 2 * CELLS + i] = 0.0f;
     __syncthreads();
   }
   if (cell_ok && p.logits != nullptr) {
@@ -155,8 +158,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   }
   __syncthreads();
   float bm0 = -INFINITY, bm1 = -INFINITY;
-#pragma unroll
-  for (int w = 0; w < HEAD_WARPS; w++) {
+  for (int w = 0; w < nwarps; w++) {
     bm0 = fmaxf(bm0, s_red[0][w]);
     bm1 = fmaxf(bm1, s_red[1][w]);
   }
@@ -170,8 +172,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   }
   if (tid < ch) {                                        // finish the pooling while the sums settle
     float sv = 0.0f, mv = 0.0f, cnt = 0.0f;
-#pragma unroll
-    for (int w = 0; w < HEAD_WARPS; w++) {
+    for (int w = 0; w < nwarps; w++) {
       sv += s_psum[w][tid];
       mv = fmaxf(mv, s_pmax[w][tid]);
       cnt += s_cnt[w];
@@ -181,8 +182,7 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
   }
   __syncthreads();
   float t0 = 0.0f, t1 = 0.0f;
-#pragma unroll
-  for (int w = 0; w < HEAD_WARPS; w++) {
+  for (int w = 0; w < nwarps; w++) {
     t0 += s_red[2][w];
     t1 += s_red[3][w];
   }
@@ -203,10 +203,10 @@ __global__ void __launch_bounds__(HEAD_THREADS) heads_kernel(const HeadParams p)
       const bool allowed = !(st->flags & MARU_STATE_HAS_MASK) || ((st->move_mask[idx >> 3] >> (idx & 7)) & 1u);
       lf->prior[idx] = allowed ? e0 / t0 : 0.0f;
     }
-    if (tid >= w * h && tid < CELLS) lf->prior[tid] = 0.0f;   // tail of the fixed-size record
+    for (int i = w * h + tid; i < CELLS; i += nthreads) lf->prior[i] = 0.0f;   // tail of the fixed-size record
   }
   // ---- value / score MLP: fc1 rows are read coalesced-by-row by one warp each
-  for (int j = warp; j < p.cv; j += HEAD_WARPS) {
+  for (int j = warp; j < p.cv; j += nwarps) {
     const float* w = p.w_fc1 + (size_t)j * 2 * ch;
     float a = 0.0f;
     for (int k = lane; k < 2 * ch; k += 32) a = fmaf(w[k], s_pool[k], a);
@@ -239,7 +239,15 @@ cudaError_t configure_heads() {
 cudaError_t launch_heads(const HeadParams& p, cudaStream_t stream) {
   if (p.n <= 0) return cudaSuccess;
   if (p.ch > HEAD_MAX_CH || p.ch % 8 != 0 || p.cv > HEAD_MAX_CV) return cudaErrorInvalidValue;
-  return launch_kernel(heads_kernel, dim3(p.n), dim3(HEAD_THREADS), 0, stream, p.pdl != 0, p);
+  // Compact frames leave most of a 416-thread CTA idle.  With many positions in flight the machine is better used by
+  // small CTAs (128 threads for 9x9: 7 instead of 2 CTAs per SM; measured 42 -> 20 us at batch 1024); a lone wave of
+  // CTAs is faster with all 13 warps sharing the value MLP (11 us vs 17 at batch 256), so small batches keep them.
+  int threads = HEAD_THREADS;
+  if (p.board_w > 0 && p.n > 592) {                     // more than two full-size CTAs per SM on 148 SMs
+    threads = (p.pos_rows + 31) / 32 * 32;
+    if (threads < 128) threads = 128;                   // the value MLP's last layer runs on warps 0..2
+  }
+  return launch_kernel(heads_kernel, dim3(p.n), dim3(threads), 0, stream, p.pdl != 0, p);
 }
 
 }  // namespace maru
