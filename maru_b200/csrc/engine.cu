@@ -1039,25 +1039,56 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n, int b
 
 // Blocking forward on host buffers: H2D, kernels, D2H (Model::forward, Model.cpp:88-100).
 // `in` / `out` may be pageable (the reference passes stack arrays, Evaluator.cpp:48-49).
+// The compact transports are small enough to cross PCIe INSIDE the kernels that use them: 448-byte records are read by
+// the encode kernel (and the heads kernel's mask lookup) straight from pinned host memory, 1456-byte results are written
+// by the heads kernel straight into it — no copy operation, no launch gap before the first and after the last kernel of a
+// forward (a batch of 256: 115 KB up, 373 KB down; the two copies and their gaps were ~20 us of a 496 us blocking call).
+// Only for page-locked memory (cudaMallocHost / cudaHostRegister: the caller's, or the queue's staging); pageable buffers
+// (the reference passes stack arrays, Evaluator.cpp:48-49) and the large fp32 transports keep the staged copies.
+static bool zero_copy_on() {
+  static const bool on = [] {
+    const char* v = getenv("MARU_B200_ZEROCOPY");
+    return v == nullptr || v[0] != '0';
+  }();
+  return on;
+}
+static void* mapped_host(const void* p) {
+  if (!zero_copy_on()) return nullptr;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
 int Engine::forward_host(int kind, const void* in, void* out, int n) {
   NvtxRange range("maru.forward_host");
   std::lock_guard<std::mutex> lock(mu);
   CK(cudaSetDevice(gpu_id));
   const size_t in_row = in_row_bytes(kind), out_row = out_row_bytes(kind);
+  uint8_t* const zin = kind != KIND_PLANES ? static_cast<uint8_t*>(mapped_host(in)) : nullptr;
+  uint8_t* const zout = kind == KIND_LEAVES ? static_cast<uint8_t*>(mapped_host(out)) : nullptr;
   for (int off = 0; off < n; off += max_batch) {
     const int m = (n - off < max_batch) ? n - off : max_batch;
     Slot& sl = slot[2];
     void* d_in = kind != KIND_PLANES ? (void*)sl.d_states : (void*)sl.d_rows;
-    CK(cudaMemcpyAsync(d_in, static_cast<const uint8_t*>(in) + (size_t)off * in_row, (size_t)m * in_row,
-                       cudaMemcpyHostToDevice, stream));
+    if (zin != nullptr) {
+      d_in = zin + (size_t)off * in_row;
+    } else {
+      CK(cudaMemcpyAsync(d_in, static_cast<const uint8_t*>(in) + (size_t)off * in_row, (size_t)m * in_row,
+                         cudaMemcpyHostToDevice, stream));
+    }
+    void* const d_res = zout != nullptr ? (void*)(zout + (size_t)off * out_row) : (void*)sl.d_out;
     CK(cudaEventRecord(sl.t0, stream));
     int bw = 0, bh = 0;
     if (kind != KIND_PLANES) uniform_board(static_cast<const maru_state*>(in) + off, m, &bw, &bh);
     else uniform_board_rows(static_cast<const float*>(in) + (size_t)off * IN_ROW, m, &bw, &bh);
-    if (forward_device(kind, d_in, sl.d_out, m, bw, bh)) return 1;
+    if (forward_device(kind, d_in, d_res, m, bw, bh)) return 1;
     CK(cudaEventRecord(sl.t1, stream));
-    CK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + (size_t)off * out_row, sl.d_out, (size_t)m * out_row,
-                       cudaMemcpyDeviceToHost, stream));
+    if (zout == nullptr)
+      CK(cudaMemcpyAsync(static_cast<uint8_t*>(out) + (size_t)off * out_row, sl.d_out, (size_t)m * out_row,
+                         cudaMemcpyDeviceToHost, stream));
     CK(cudaStreamSynchronize(stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, sl.t0, sl.t1);
@@ -1074,14 +1105,17 @@ int Engine::enqueue_slot(int kind, int slot_idx, int n) {
   const size_t in_row = in_row_bytes(kind);
   void* d_in = kind != KIND_PLANES ? (void*)sl.d_states : (void*)sl.d_rows;
   const void* h_in = kind != KIND_PLANES ? (const void*)sl.h_states : (const void*)sl.h_rows;
-  CK(cudaMemcpyAsync(d_in, h_in, (size_t)n * in_row, cudaMemcpyHostToDevice, stream));
+  // the staging is page-locked: records in and compact results out cross PCIe inside the kernels (see forward_host)
+  const bool zin = kind != KIND_PLANES && zero_copy_on(), zout = kind == KIND_LEAVES && zero_copy_on();
+  if (zin) d_in = sl.h_states;
+  else CK(cudaMemcpyAsync(d_in, h_in, (size_t)n * in_row, cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(sl.t0, stream));
   int bw = 0, bh = 0;
   if (kind != KIND_PLANES) uniform_board(sl.h_states, n, &bw, &bh);
   else uniform_board_rows(sl.h_rows, n, &bw, &bh);
-  if (forward_device(kind, d_in, sl.d_out, n, bw, bh)) return 1;
+  if (forward_device(kind, d_in, zout ? (void*)sl.h_out : (void*)sl.d_out, n, bw, bh)) return 1;
   CK(cudaEventRecord(sl.t1, stream));
-  CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)n * out_row_bytes(kind), cudaMemcpyDeviceToHost, stream));
+  if (!zout) CK(cudaMemcpyAsync(sl.h_out, sl.d_out, (size_t)n * out_row_bytes(kind), cudaMemcpyDeviceToHost, stream));
   CK(cudaEventRecord(sl.done, stream));
   return 0;
 }
@@ -1153,6 +1187,8 @@ int Engine::lane_submit(Lane* l, int n) {
   std::lock_guard<std::mutex> lock(mu);
   CK(cudaSetDevice(gpu_id));
   Slot& sl = slot[2];
+  // (staged copies, not the zero-copy transport of forward_host: a forward graph is cached per buffer pair, and dozens of
+  // lanes would each want their own)
   CK(cudaMemcpyAsync(sl.d_states, l->h_states, (size_t)n * sizeof(maru_state), cudaMemcpyHostToDevice, stream));
   CK(cudaEventRecord(l->t0, stream));
   int bw = 0, bh = 0;
