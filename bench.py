@@ -758,6 +758,8 @@ def run_b200(args):
             dtype='bf16', data='synthetic', impl='b200',
             config=base_config(args, world),
             details=dict(l2='flushed between steps (256 MiB write)', launches_per_step=info.launches_per_forward,
+                         conv_path=('persistent multi-layer kernels (conv_flow)' if info.launches_per_forward <= 12
+                                    else 'one launch per conv layer') + ', picked by the engine\'s own timing of both',
                          flops_per_eval=info.flops_per_eval, flops_per_eval_executed=info.flops_per_eval_executed),
             e2e=dict(value=total / e2e_leaf_s, unit=UNIT, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
                      d2h_bytes_per_step=B * maru_b200.LEAF_SIZE * 4,

@@ -44,6 +44,14 @@ namespace maru {
 constexpr int FLOW_THREADS = 448;     // warp 0 producer, 1 and 10 MMA issue, 2..9 epilogue, 11 weights, 12 and 13 publishers
 constexpr int FLOW_SMEM = 232448;     // 227 KB
 constexpr int FLOW_SLOTS = 4;         // input slabs in flight (barrier slots of the byte ring)
+// Epilogue organisation.  1: the eight epilogue warps share every tile (two warps per TMEM lane quarter, half of the
+// columns each) and tiles drain one after the other.  2: two groups of four warps (warps 2-5 even items, 6-9 odd items),
+// a thread owns all columns of its row: two tiles drain CONCURRENTLY, which hides the latency chain of a drain
+// (residual load -> accumulator wait -> tcgen05.ld -> stores -> count) behind the other group's.
+#ifndef FLOW_EPI_GROUPS
+#define FLOW_EPI_GROUPS 2
+#endif
+constexpr uint32_t FLOW_EPI_WARPS = 8 / FLOW_EPI_GROUPS;   // warps that drain one tile (= arrivals per accumulator / item)
 constexpr int FLOW_CTRL_BYTES = 1024;
 constexpr int FLOW_ONES_BYTES = 2 * TILE_M * 16;
 constexpr int FLOW_MASK_BYTES = FLOW_MAX_TILES * TILE_M;
@@ -66,7 +74,7 @@ constexpr uint32_t CB_MDONE = 144;     // [2] both MMA warps' last MMAs of layer
                                        //     so that the waiter can never fall two phases behind however short a layer is)
 constexpr uint32_t CB_SLOT_OFF = 160;  // [4] u32 byte offset of the slab of the item in slot s
 constexpr uint32_t CB_TMEM = 176;      // u32 TMEM base
-constexpr uint32_t CB_RAW = 256;       // [FLOW_MAX_TILES] u32 epilogue-warp completions per item index (8 per layer): stored
+constexpr uint32_t CB_RAW = 256;       // [FLOW_MAX_TILES] u32 epilogue-warp completions per item index (FLOW_EPI_WARPS per layer): stored
 constexpr uint32_t CB_DONE = 448;      // [FLOW_MAX_TILES] u32 the same count once a publisher warp has fenced: readable by bulk copies
 
 // shared-memory helpers on 32-bit shared addresses (no generic 64-bit pointers in the hot loops)
@@ -427,7 +435,7 @@ __device__ __noinline__ void flow_publisher(const FlowParams& fp, uint32_t c_sme
   const int n_layers = fp.n_layers;
   uint32_t g = 0;
   for (int l = 0; l < n_layers; l++) {
-    const uint32_t need = 8u * (uint32_t)(l + 1);
+    const uint32_t need = FLOW_EPI_WARPS * (uint32_t)(l + 1);
     for (int i = 0; i < k; i++, g++) {
       if ((g & 1u) != pw) continue;
       flow_wait_done(c.ctrl + CB_RAW + 4 * i, need, l, -1 - i);
@@ -447,25 +455,28 @@ __device__ __noinline__ void flow_publisher(const FlowParams& fp, uint32_t c_sme
 
 // ------------------------------------------------------------------------------------------ epilogue (warps 2..9)
 // one tile: CW accumulator columns of this thread's row -> (+ residual) -> bf16 -> ReLU -> board mask -> 16-byte stores
-template <int CW>
+// (a 128-column row is drained as two calls of 64: FIRST waits for the accumulator, LAST hands it back)
+template <int CW, bool FIRST = true, bool LAST = true>
 __device__ __forceinline__ void flow_epilogue_tile(const int relu, const uint32_t t_addr, __nv_bfloat16* out_row,
                                                    const size_t pstride, const __nv_bfloat16* res_row,
                                                    const size_t rstride, const bool valid, const bool on,
                                                    const uint32_t tfull, const uint32_t tempty, const uint32_t parity,
                                                    long long* trs) {
   const bool has_res = res_row != nullptr;
-  // residual (same channel range as the output): prefetched before the accumulator is ready
+  // residual (same channel range as the output): requested before the accumulator is ready
   uint4 rv[CW / 8];
   if (has_res) {
 #pragma unroll
     for (int q = 0; q < CW / 8; q++)
       rv[q] = on ? *reinterpret_cast<const uint4*>(res_row + (size_t)q * rstride) : make_uint4(0u, 0u, 0u, 0u);
   }
-  mbar_wait_a(tfull, parity);
-  if (trs != nullptr) trs[4] = globaltimer_ns();
-  tc_fence_after();
-  // all of this thread's accumulator columns in one go (one wait), then the accumulator is handed back to the
-  // MMA warps before the conversion and the stores
+  if constexpr (FIRST) {
+    mbar_wait_a(tfull, parity);
+    if (trs != nullptr) trs[4] = globaltimer_ns();
+    tc_fence_after();
+  }
+  // all of this call's accumulator columns in one go (one wait); after the last read the accumulator is handed back
+  // to the MMA warps, before the conversion and the stores
   uint32_t v[CW];
   if constexpr (CW == 16) {
     tmem_ld16(t_addr, v);
@@ -476,9 +487,11 @@ __device__ __forceinline__ void flow_epilogue_tile(const int relu, const uint32_
     tmem_ld32(t_addr + 32, v + 32);
   }
   tmem_ld_wait();
-  tc_fence_before();
-  __syncwarp();
-  if ((threadIdx.x & 31) == 0) mbar_arrive_a(tempty);
+  if constexpr (LAST) {
+    tc_fence_before();
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive_a(tempty);
+  }
 #pragma unroll
   for (int q = 0; q < CW / 8; q++) {
     uint32_t o[4];
@@ -513,7 +526,12 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
   const int lane = threadIdx.x & 31;
   const int k = c.k;
   const int lg = warp & 3;                 // TMEM lane group this warp may access
+#if FLOW_EPI_GROUPS == 2
+  const uint32_t eg = (uint32_t)(warp - 2) >> 2;   // epilogue group: the items of this parity
+  const int half = 0;
+#else
   const int half = (warp - 2) >> 2;        // which half of the NT columns
+#endif
   const int trow = lg * 32 + lane;
   const uint32_t mask = c.ctrl + FLOW_CTRL_BYTES + FLOW_ONES_BYTES;
   const int n_layers = fp.n_layers;
@@ -527,11 +545,14 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
     const int out_blocked = fp.layer[l].out_blocked, res_blocked = fp.layer[l].res_blocked;
     const size_t out_planes = (size_t)fp.layer[l].out_planes, res_planes = (size_t)fp.layer[l].res_planes;
     const int relu = fp.layer[l].relu;
-    const int cw = fp.layer[l].nt / 2;     // columns per warp
+    const int cw = fp.layer[l].nt * FLOW_EPI_GROUPS / 2;   // columns per thread
     const int chunk0 = fp.layer[l].out_chunk0 + half * (cw / 8);
     const size_t pstride = out_blocked ? (size_t)TILE_M * 8 : rows_alloc * 8;
     const size_t rstride = res_blocked ? (size_t)TILE_M * 8 : rows_alloc * 8;
     for (int i = 0; i < k; i++, g++) {
+#if FLOW_EPI_GROUPS == 2
+      if ((g & 1u) != eg) continue;
+#endif
       const uint32_t acc = g & 3u;
       const int j = flow_tile_of(i, k);
       const int tile = c.t0 + j;
@@ -549,13 +570,18 @@ __device__ __noinline__ void flow_epilogue(const FlowParams& fp, uint32_t c_smem
                               : res + ((size_t)chunk0 * rows_alloc + grow) * 8;
       const uint32_t t_addr = c.tmem_base + ((uint32_t)(lg * 32) << 16) + acc * 128u + half * cw;
       const uint32_t tfull = c.ctrl + CB_TFULL + 8 * acc, tempty = c.ctrl + CB_TEMPTY + 8 * acc;
-      long long* trs = (c.tr != nullptr && warp == 2 && lane == 0 && g < 256) ? c.tr + g * 8 : nullptr;
+      long long* trs = (c.tr != nullptr && (warp == 2 || (FLOW_EPI_GROUPS == 2 && warp == 6)) && lane == 0 && g < 256) ? c.tr + g * 8 : nullptr;
       if (dbg & 128) {            // timing experiment: the epilogue only hands the accumulator back
         mbar_wait_a(tfull, (g >> 2) & 1u);
         tc_fence_after();
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive_a(tempty);
+      } else if (cw == 128) {
+        flow_epilogue_tile<64, true, false>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
+        flow_epilogue_tile<64, false, true>(relu, t_addr + 64, out_row + 8 * pstride, pstride,
+                                            res_row != nullptr ? res_row + 8 * rstride : nullptr, rstride, valid, on, tfull,
+                                            tempty, (g >> 2) & 1u, trs);
       } else if (cw == 64)
         flow_epilogue_tile<64>(relu, t_addr, out_row, pstride, res_row, rstride, valid, on, tfull, tempty, (g >> 2) & 1u, trs);
       else if (cw == 32)
@@ -596,7 +622,7 @@ __global__ void __launch_bounds__(FLOW_THREADS, 1) conv_flow_kernel(const __grid
     }
     for (int i = 0; i < 4; i++) {
       mbar_init_a(c.ctrl + CB_TFULL + 8 * i, 1);
-      mbar_init_a(c.ctrl + CB_TEMPTY + 8 * i, 8);
+      mbar_init_a(c.ctrl + CB_TEMPTY + 8 * i, FLOW_EPI_WARPS);
     }
     for (int i = 0; i < 2; i++) {
       mbar_init_a(c.ctrl + CB_WBAR + 8 * i, 1);

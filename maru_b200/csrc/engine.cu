@@ -306,6 +306,7 @@ int Engine::init(const char* weights_path, int gpu, int max_batch_, unsigned fla
     if (ff[0] == '1') dbg_desc |= 128;
     if (ff[0] == '0') dbg_desc |= 32;
   }
+  if (const char* ft = getenv("MARU_B200_FLOW_TUNE")) flow_tune_on = ft[0] != '0';
   device_ref(+1);
   dev_counted = true;
   max_batch = max_batch_ > 0 ? max_batch_ : 256;
@@ -678,7 +679,7 @@ int Engine::profile_states(const maru_state* d_states, float* d_out, int n, maru
     return 1;
   }
   fwd = (compact_on && !(dbg_desc & (1 << 21))) ? Geom::board(dev_w, dev_h) : Geom();
-  flow_live = flow_pays(n);
+  flow_live = flow_choice(n);
   std::vector<maru_launch_time> rec;
   rec.reserve(256);
   while ((int)prof_ev.size() < 512) {
@@ -771,6 +772,11 @@ bool Engine::pair_pays(int cin, int n) const {
   if (cin == 128) return true;
   return pair64_on && n >= pair64_min_batch;
 }
+bool Engine::flow_choice(int n) const {
+  if (!flow_pays(n)) return false;
+  const auto it = flow_tuned.find(fwd.w * 32 + fwd.h);
+  return it == flow_tuned.end() || it->second != 0;
+}
 bool Engine::flow_enabled() {
   if (dbg_desc & 128) return flow_device_ok();      // debug: force the flow kernels at any batch size
   return flow_live && flow_device_ok();
@@ -786,6 +792,7 @@ void Engine::clear_graphs() {
   for (auto& kv : graphs)
     if (kv.second) cudaGraphExecDestroy(kv.second);
   graphs.clear();
+  graph_launches.clear();
 }
 
 int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const int* n_dev, cudaStream_t st) {
@@ -967,6 +974,97 @@ void Engine::uniform_board_rows(const float* rows, int n, int* bw, int* bh) {
   *bh = h0;
 }
 
+// One forward on the stream with the path flow_live says (graph replay, or plain launches with MARU_FLAG_NO_GRAPH).
+// *ok = false: the launch failed (error text set), the stream is intact; return 1: a CUDA call failed.
+int Engine::enqueue_forward(int kind, const void* d_in, void* d_out, int n, bool* ok) {
+  const bool with_flow = flow_enabled();
+  *ok = true;
+  if (flags & MARU_FLAG_NO_GRAPH) {
+    *ok = launch_all(kind, d_in, d_out, n, nullptr, stream) == 0;
+  } else {
+    // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
+    const int bucket = bucket_for(n, max_batch);
+    GraphKey key{kind, bucket, d_in, d_out, with_flow, fwd.w, fwd.h};
+    auto it = graphs.find(key);
+    if (it == graphs.end()) {
+      // The cache is keyed by the caller's buffers: a device-API caller that rotates buffers must not grow it
+      // without bound. Graphs still in flight keep running (a cudaGraphExec_t may be destroyed once launched work
+      // has been submitted only after it completes, hence the sync).
+      if (graphs.size() >= 64) {
+        CK(cudaStreamSynchronize(stream));
+        clear_graphs();
+      }
+      cudaGraph_t gr = nullptr;
+      cudaGraphExec_t ex = nullptr;
+      CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+      const int rc = launch_all(kind, d_in, d_out, bucket, d_n, stream);
+      cudaError_t ce = cudaStreamEndCapture(stream, &gr);
+      if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&ex, gr, 0);
+      if (gr != nullptr) cudaGraphDestroy(gr);
+      if (rc != 0 || ce != cudaSuccess) {
+        if (rc == 0) set_error(std::string("forward graph: ") + cudaGetErrorString(ce));
+        *ok = false;
+      } else {
+        it = graphs.emplace(key, ex).first;
+        graph_launches[key] = n_launched;
+      }
+    }
+    if (*ok) {
+      // The live batch size travels BY VALUE as a kernel parameter (fixed at enqueue time): any number of forwards
+      // with different n may be in flight on the stream. (A pinned staging int read by an async copy at execution
+      // time was overwritten by later calls once more than a handful of forwards were outstanding.)
+      set_live_n_kernel<<<1, 1, 0, stream>>>(d_n, n);
+      CK(cudaGetLastError());
+      const cudaError_t le = cudaGraphLaunch(it->second, stream);
+      if (le == cudaSuccess) launches_per_forward = graph_launches[key];
+      if (le != cudaSuccess) {
+        set_error(std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
+        cudaGraphExecDestroy(it->second);
+        graphs.erase(it);
+        *ok = false;
+      }
+    }
+  }
+  return 0;
+}
+
+// Times both paths on this forward's own inputs (a forward recomputes everything from its input, so repeating it is
+// harmless) and records the faster for the board geometry. ~8 forwards and one synchronisation, once.
+int Engine::tune_flow(int kind, const void* d_in, void* d_out, int n) {
+  const int key = fwd.w * 32 + fwd.h;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  CK(cudaEventCreate(&e0));
+  CK(cudaEventCreate(&e1));
+  float ms[2] = {0.f, 0.f};
+  int rc = 0;
+  for (int v = 1; v >= 0 && rc == 0; v--) {        // 1: flow kernels, 0: one launch per layer
+    flow_tuned[key] = v;
+    flow_live = flow_choice(n);
+    bool ok = true;
+    for (int r = 0; r < 2 && rc == 0 && ok; r++) rc = enqueue_forward(kind, d_in, d_out, n, &ok);     // capture + warm
+    if (rc == 0 && ok) rc = cudaEventRecord(e0, stream) != cudaSuccess;
+    for (int r = 0; r < 3 && rc == 0 && ok; r++) rc = enqueue_forward(kind, d_in, d_out, n, &ok);
+    if (rc == 0 && ok) rc = cudaEventRecord(e1, stream) != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess;
+    if (rc == 0 && ok) cudaEventElapsedTime(&ms[v], e0, e1);
+    if (rc == 0 && !ok) {
+      // the flow kernels cannot be launched here: forward_device's fallback handles (and reports) it
+      cudaGetLastError();
+      ms[v] = 1e30f;
+    }
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (rc) {
+    flow_tuned.erase(key);
+    return 1;
+  }
+  flow_tuned[key] = ms[1] <= ms[0] ? 1 : 0;
+  if (getenv("MARU_B200_VERBOSE"))
+    fprintf(stderr, "maru_b200: GPU %d, %dx%d frame, %d positions: flow kernels %.1f us, one launch per layer %.1f us\n", gpu_id,
+            fwd.w, fwd.h, n, ms[1] * 1e3f / 3, ms[0] * 1e3f / 3);
+  return 0;
+}
+
 int Engine::forward_device(int kind, const void* d_in, void* d_out, int n, int bw, int bh) {
   if (n <= 0) return 0;
   // a batch whose positions all hold the same small board runs on that board's compact frame after the stem
@@ -975,56 +1073,17 @@ int Engine::forward_device(int kind, const void* d_in, void* d_out, int n, int b
     set_error("batch larger than max_batch");
     return 1;
   }
+  if (flow_tune_on && !(flags & MARU_FLAG_NO_GRAPH) && !(dbg_desc & (128 | 32)) && flow_pays(n) && flow_device_ok() &&
+      flow_tuned.find(fwd.w * 32 + fwd.h) == flow_tuned.end()) {
+    if (tune_flow(kind, d_in, d_out, n)) return 1;
+  }
   // Two attempts: if the persistent flow kernels cannot be launched (the cooperative launch does not fit: the
   // device is shared), the engine gives them up for good and the forward is enqueued again with one launch per layer.
   for (int attempt = 0; attempt < 2; attempt++) {
-    flow_live = flow_pays(n);               // by the LIVE batch size: a bucket has a flow graph and a per-layer graph
+    flow_live = flow_choice(n);             // by the LIVE batch size: a bucket has a flow graph and a per-layer graph
     const bool with_flow = flow_enabled();
     bool ok = true;
-    if (flags & MARU_FLAG_NO_GRAPH) {
-      ok = launch_all(kind, d_in, d_out, n, nullptr, stream) == 0;
-    } else {
-      // one graph per (kind, bucket, input, output); the live n is read from d_n by every kernel
-      const int bucket = bucket_for(n, max_batch);
-      GraphKey key{kind, bucket, d_in, d_out, with_flow, fwd.w, fwd.h};
-      auto it = graphs.find(key);
-      if (it == graphs.end()) {
-        // The cache is keyed by the caller's buffers: a device-API caller that rotates buffers must not grow it
-        // without bound. Graphs still in flight keep running (a cudaGraphExec_t may be destroyed once launched work
-        // has been submitted only after it completes, hence the sync).
-        if (graphs.size() >= 64) {
-          CK(cudaStreamSynchronize(stream));
-          clear_graphs();
-        }
-        cudaGraph_t gr = nullptr;
-        cudaGraphExec_t ex = nullptr;
-        CK(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
-        const int rc = launch_all(kind, d_in, d_out, bucket, d_n, stream);
-        cudaError_t ce = cudaStreamEndCapture(stream, &gr);
-        if (rc == 0 && ce == cudaSuccess) ce = cudaGraphInstantiate(&ex, gr, 0);
-        if (gr != nullptr) cudaGraphDestroy(gr);
-        if (rc != 0 || ce != cudaSuccess) {
-          if (rc == 0) set_error(std::string("forward graph: ") + cudaGetErrorString(ce));
-          ok = false;
-        } else {
-          it = graphs.emplace(key, ex).first;
-        }
-      }
-      if (ok) {
-        // The live batch size travels BY VALUE as a kernel parameter (fixed at enqueue time): any number of forwards
-        // with different n may be in flight on the stream. (A pinned staging int read by an async copy at execution
-        // time was overwritten by later calls once more than a handful of forwards were outstanding.)
-        set_live_n_kernel<<<1, 1, 0, stream>>>(d_n, n);
-        CK(cudaGetLastError());
-        const cudaError_t le = cudaGraphLaunch(it->second, stream);
-        if (le != cudaSuccess) {
-          set_error(std::string("cudaGraphLaunch: ") + cudaGetErrorString(le));
-          cudaGraphExecDestroy(it->second);
-          graphs.erase(it);
-          ok = false;
-        }
-      }
-    }
+    if (enqueue_forward(kind, d_in, d_out, n, &ok)) return 1;
     if (ok) break;
     if (!with_flow || attempt == 1) return 1;
     cudaGetLastError();                     // launch-configuration errors are not sticky

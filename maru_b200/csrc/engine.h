@@ -135,6 +135,7 @@ struct Engine {
   Slot slot[3];  // 0,1: leaf-queue double buffer; 2: direct blocking calls
   std::vector<void*> allocs;
   std::map<GraphKey, cudaGraphExec_t> graphs;
+  std::map<GraphKey, int> graph_launches;   // kernels per replay of each graph (info().launches_per_forward follows the path in use)
 
   int dbg_stop_after = -1;  // debug: stop the launch sequence after this many trunk launches
   int dbg_desc = 0;         // debug: bit0 = disable programmatic dependent launch
@@ -192,7 +193,15 @@ struct Engine {
   bool pair64_on = false;           // measured slower than conv_gemm<64,64,9> at every batch size
   int pair64_min_batch = 1;
   bool flow_pays(int n) const;      // enough tiles per CTA for the persistent kernels to win
-  bool flow_live = true;            // flow_pays(live batch size) of the forward being enqueued
+  bool flow_live = true;            // flow_choice(live batch size) of the forward being enqueued
+  // Inside the window of flow_pays the two paths are within ~8 % of each other and WHICH one wins depends on the GPU
+  // (same driver, same clocks: flow 448 vs per-layer 466 us on one B200, 484 vs 449 us on another - the SM -> die map is
+  // per part). The first forward in the window on a board geometry times both graphs and the engine keeps the faster.
+  std::map<int, int> flow_tuned;    // key w * 32 + h -> 1 flow, 0 one launch per layer
+  bool flow_tune_on = true;         // MARU_B200_FLOW_TUNE=0: trust the window
+  bool flow_choice(int n) const;    // flow_pays(n) and not measured slower
+  int tune_flow(int kind, const void* d_in, void* d_out, int n);
+  int enqueue_forward(int kind, const void* d_in, void* d_out, int n, bool* ok);
   bool flow_broken = false;         // a flow launch failed (cooperative grid does not fit: shared device): never again
   void device_ref(int delta);
   long long* d_stamps = nullptr;    // per-layer %globaltimer stamps of the chains (profiling)
