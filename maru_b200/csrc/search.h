@@ -52,8 +52,10 @@ namespace maru {
 // bring-up only: cycle counters around the phases of a visit (tools/search_prof.cpp defines the T_* globals)
 #ifdef MARU_SEARCH_PROFILE
 #define MARU_PROF(var, stmt) do { const unsigned long long _t = __rdtsc(); stmt; var += __rdtsc() - _t; } while (0)
+#define MARU_PROF_SCOPE(var) struct _ProfScope { unsigned long long t0 = __rdtsc(); ~_ProfScope() { var += __rdtsc() - t0; } } _prof_scope
 #else
 #define MARU_PROF(var, stmt) do { stmt; } while (0)
+#define MARU_PROF_SCOPE(var) do { } while (0)
 #endif
 
 struct SearchSetup {
@@ -169,6 +171,7 @@ class GameSearch {
   // Run descents.  WANT_LEAF: `*st` holds the record of the node that needs the network; call
   // deliver() and then advance() again.  MOVE_READY: the root has reached the target.
   Status advance(maru_state* st) {
+    MARU_PROF_SCOPE(T_advance);
     for (;;) {
       if (path_.empty()) {
         if (pool_[root_].visits >= target_) return MOVE_READY;
@@ -182,7 +185,7 @@ class GameSearch {
         return WANT_LEAF;
       }
       int next = -1, playouts = 0;
-      step(n, cur_, &next, &playouts);
+      MARU_PROF(T_step, step(n, cur_, &next, &playouts));
       const float v = n.net_value;
       if (playouts == 1) {
         for (int p : path_) {
@@ -208,6 +211,7 @@ class GameSearch {
 
   // The network's answer for the record advance() / need_root() produced last.
   void deliver(const maru_state& st, const maru_leaf& leaf) {
+    MARU_PROF_SCOPE(T_deliver);
     TreeNode& n = pool_[pending_];
     const int cells = st.width * st.height;
     n.moves.clear();
@@ -252,6 +256,7 @@ class GameSearch {
   // Player::play: the child at (x, y) becomes the root with its subtree, or a fresh node does
   // (Node::getChild); everything else goes back to the pool.  Returns the stones captured.
   int play(int x, int y) {
+    MARU_PROF_SCOPE(T_play);
     const int old = root_;
     const int cell = y * setup_.width + x;
     int keep = pool_[old].kid_of(cell);
@@ -344,17 +349,19 @@ class GameSearch {
     const float half = 1.96 * 0.5 / std::sqrt(c.visits + 1);
     return q - (half * c.color);
   }
-  float pucb(const TreeNode& c, int total) const {                                // Node::getPriorityByPUCB
+  // The terms that depend on the parent alone are computed once per visited node, not once per child (same
+  // expressions in the same types, so the same bits): c_puct as float, sqrt / log of the visit count as double.
+  static float pucb_c(int total) { return std::log((1 + total + 19652.0) / 19652.0) + 1.25; }
+  float pucb(const TreeNode& c, float c_puct, double sqrt_total) const {         // Node::getPriorityByPUCB
     if (c.count == 0) return -99.0f;
-    const float c_puct = std::log((1 + total + 19652.0) / 19652.0) + 1.25;
     const float q = (c.value_sum / c.count) * c.color;
-    const float u = c_puct * c.prior * std::sqrt(total) / (1 + c.visits);
+    const float u = c_puct * c.prior * sqrt_total / (1 + c.visits);
     return q + 2 * u;
   }
-  float ucb1(const TreeNode& c, int total) const {                                // Node::getPriorityByUCB1
+  float ucb1(const TreeNode& c, double log_total) const {                         // Node::getPriorityByUCB1
     if (c.count == 0) return -99.0f;
     const float q = (c.value_sum / c.count) * c.color;
-    const float u = 0.5 * std::sqrt(std::log(total) / (c.visits + 1));
+    const float u = 0.5 * std::sqrt(log_total / (c.visits + 1));
     return q + u;
   }
 
@@ -449,18 +456,24 @@ class GameSearch {
     }
 
     // --- otherwise revisit the most promising child
+    // (the LCB ranking is only computed when the root width actually cuts the list; otherwise the children keep their
+    // order, as in the reference, and the ranking would not be looked at)
     scratch_.clear();
+    const bool cut = m.width > 0 && (int)n.kids.size() > m.width;
     for (const TreeNode::Edge& e : n.kids) {
       const TreeNode& c = pool_[e.node];
-      scratch_.emplace_back(e.node, lcb(c) * c.color);
+      scratch_.emplace_back(e.node, cut ? lcb(c) * c.color : 0.0f);
     }
-    if (m.width > 0 && (int)scratch_.size() > m.width) {
+    if (cut) {
       std::sort(scratch_.begin(), scratch_.end(),
                 [](const std::pair<int, float>& a, const std::pair<int, float>& b) { return a.second > b.second; });
       scratch_.resize(m.width);
     }
     int pick = scratch_[0].first;
     float top = -1.0;
+    const float c_puct = pucb_c(n.visits);
+    const double sqrt_total = std::sqrt(n.visits);
+    const double log_total = m.use_ucb1 ? std::log(n.visits) : 0.0;
     for (const auto& kv : scratch_) {
       const TreeNode& c = pool_[kv.first];
       float pri;
@@ -469,9 +482,9 @@ class GameSearch {
         const float q = c.mean() * c.color;
         pri = 1.0 / (cv + 1 - q * 0.5);
       } else if (m.use_ucb1) {
-        pri = ucb1(c, n.visits);
+        pri = ucb1(c, log_total);
       } else {
-        pri = pucb(c, n.visits);
+        pri = pucb(c, c_puct, sqrt_total);
       }
       if (top < pri) {
         pick = kv.first;
