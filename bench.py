@@ -612,6 +612,39 @@ def run_b200(args):
         assert rc == 0
     sync_all()
     e2e_leaf_s = time.perf_counter() - t0
+    # the same transport through the leaf-batch queue with FOUR batches in flight (asynchronous tickets: how a search
+    # keeps the evaluator fed; the reference gets the same overlap from many threads blocked in Processor::execute).
+    # Host buffers in and out every step, staging copies inside the timed region; reported next to the blocking number.
+    e2e_async_s = float('nan')
+    try:
+        import ctypes as C
+        q = maru_b200.LeafQueue([ev], batch_size=B)
+        try:
+            st_np = h_states.numpy()
+            DEPTH = 4                            # tickets in flight
+            lf_np = [np.zeros((B, maru_b200.LEAF_SIZE), np.float32) for _ in range(DEPTH)]
+            def submit(i):
+                t = C.c_void_p()
+                rc = lib.maru_queue_submit_leaves(q.handle, st_np.ctypes.data, lf_np[i % DEPTH].ctypes.data, B, C.byref(t))
+                assert rc == 0
+                return t
+            for i in range(DEPTH):
+                assert lib.maru_queue_wait(q.handle, submit(i)) == 0
+            sync_all()
+            t0 = time.perf_counter()
+            pending = []
+            for i in range(args.steps):
+                if len(pending) == DEPTH:
+                    assert lib.maru_queue_wait(q.handle, pending.pop(0)) == 0
+                pending.append(submit(i))
+            for t in pending:
+                assert lib.maru_queue_wait(q.handle, t) == 0
+            e2e_async_s = time.perf_counter() - t0
+            assert all(np.array_equal(x, h_leaf.numpy()) for x in lf_np)
+        finally:
+            q.close()
+    except Exception as exc:                     # a side leg: never lose the line over it
+        print(f'bench: queue e2e leg failed: {exc}', file=sys.stderr)
     # reference-shaped rows in (47 680 B/position), same call the substitute deepgo::Model makes
     d_rows = torch.empty((B, maru_b200.INPUT_SIZE), dtype=torch.float32, device=dev)
     ev.encode_planes_device(d_states.data_ptr(), d_rows.data_ptr(), B)
@@ -685,10 +718,10 @@ def run_b200(args):
     from maru_b200 import shard
     agg = shard.reduce_stats(shard.RankStats(positions=B * args.steps, batches=args.steps,
                                              device_ms=dev_ms, wall_s=t_wall), dist, dev)
-    t = torch.tensor([e2e_s, e2e_planes_s, e2e_leaf_s], dtype=torch.float64, device=dev)
+    t = torch.tensor([e2e_s, e2e_planes_s, e2e_leaf_s, e2e_async_s], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s, e2e_planes_s, e2e_leaf_s = [float(x) for x in t.tolist()]
+    e2e_s, e2e_planes_s, e2e_leaf_s, e2e_async_s = [float(x) for x in t.tolist()]
     dev_ms, t_wall = agg['device_ms'], agg['wall_s']
     total = agg['positions']                      # all ranks' positions / the slowest rank's time
     value = shard.evals_per_sec(agg)
@@ -765,6 +798,10 @@ def run_b200(args):
                      d2h_bytes_per_step=B * maru_b200.LEAF_SIZE * 4,
                      api='maru_eval_forward_leaves (blocking, pinned host buffers): compact records in, '
                          'move priors + value out — the transport of the substitute Evaluator.cpp',
+                     queue_four_in_flight=dict(value=(total / e2e_async_s) if e2e_async_s == e2e_async_s else None,
+                                              h2d_bytes_per_step=B * maru_b200.STATE_SIZE, d2h_bytes_per_step=B * maru_b200.LEAF_SIZE * 4,
+                                              api='maru_queue_submit_leaves / maru_queue_wait, four tickets in flight '
+                                                  '(pageable host buffers, the queue stages them)'),
                      full_rows=dict(value=total / e2e_s, h2d_bytes_per_step=B * maru_b200.STATE_SIZE,
                                     d2h_bytes_per_step=B * maru_b200.OUTPUT_SIZE * 4,
                                     api='maru_eval_forward_states (compact records in, 2169-float rows out)'),
