@@ -166,9 +166,10 @@ int  maru_eval_debug_policy_logits(maru_eval* e, float* out, int n);
  * bit4 = conv_gemm instead of the K-split (3x3, 128 input channels) and wide (1x1, 256 -> k*256) kernels (A/B),
  * bit5 = DISABLE the persistent multi-layer flow kernels (conv_flow.cu): one PDL launch per conv layer
  * (A/B timing and the layer-by-layer parity tests), bit6 = record per-layer stamps of the flow kernels
- * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: for 249..354 positions on
- * 148 SMs), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B), bit21 = always the 19x19 frame (no
- * compact frame for small boards, A/B and parity).
+ * (maru_eval_debug_stamps), bit7 = use the flow kernels at every batch size (default: inside 249..354 positions on
+ * 148 SMs when the engine's own timing says they win), bit20 = conv_ksplit instead of the CTA-pair kernel conv_pair (A/B), bit21 = always the 19x19 frame (no
+ * compact frame for small boards, A/B and parity), bit23 = attention always subtracts the row shift c_i before the
+ * exponential (default: a warp skips it when its rows' scores are bounded by 64; A/B and parity of the shifted path).
  * Only in -DMARU_EXPERIMENTS builds of the library (not the product build): bit2 = the v1 mma.sync attention
  * kernel, bit3 = per-tile cross-layer flags in conv_gemm (measured slower), bits 8-17 = timing experiments inside
  * the flow kernels (tools/flow_ab.py; results are WRONG with any of them set). */

@@ -254,8 +254,9 @@ constexpr int A2_NV = 48;                   // V columns (32) + ones + padding t
 // 2^f (max relative error 7.5e-5, far below the bf16 rounding of P), exponent added as an integer.
 // The MUFU pipe (16 ex2 per clock per SM) is the busiest pipe of this kernel (ncu: 60 %); moving a
 // share of the exponentials off it lets both pipes work in parallel.
+template <bool CLAMP = true>
 __device__ __forceinline__ float exp2_fma(float x) {
-  x = fmaxf(x, -120.0f);
+  if (CLAMP) x = fmaxf(x, -120.0f);
   const float t = x + 12582912.0f;            // 1.5 * 2^23: n lands in the low mantissa bits
   const float f = x - (t - 12582912.0f);
   float p = fmaf(f, 0.05517162f, 0.24261113f);
@@ -273,16 +274,35 @@ __device__ __forceinline__ float exp2_fma(float x) {
 #define MARU_ATT_POLY_MASK 0x15
 #endif
 constexpr int A2_POLY_MASK = MARU_ATT_POLY_MASK;
+#ifndef MARU_ATT_POLY_NS_MASK
+#define MARU_ATT_POLY_NS_MASK 0x09
+#endif
+// the unshifted path has fewer FMA-pipe instructions per exponential to begin with: its optimum is 20 % (forward at batch 256,
+// both layers: 0 % 460.0 us, 10 % 455.0, 20 % 452.9-454.2 whichever calls, 30 % 455.8, 40 % 455.5, 50 % 461.6; shifted 463.7)
+constexpr int A2_POLY_NS_MASK = MARU_ATT_POLY_NS_MASK;
+// |score| bound (in the log2 units of the folded weights) below which a warp skips the shift: 400 keys x 2^64 and the
+// products with V stay far inside fp32 / bf16 range on both sides (2^-64 is a normal number in both)
+#ifndef MARU_ATT_NOSHIFT
+#define MARU_ATT_NOSHIFT 64.0f
+#endif
+constexpr float A2_NOSHIFT = MARU_ATT_NOSHIFT;
 
-template <bool POLY>
+// SHIFT = false: the scores of this warp's rows are bounded by A2_NOSHIFT (|s_ij| <= |q_i| max_j |k_j|), exp2(s) can
+// neither overflow nor lose the row sum, and the subtraction of c_i — one FADD per exponential in an issue-bound loop —
+// is dropped (softmax is shift invariant: c_i = 0 is as good as any other shift).
+template <bool POLY, bool SHIFT>
 __device__ __forceinline__ void exp_store16(const uint32_t* v, float c, uint8_t* s_p, int chunk, int trow) {
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     uint32_t o[4];
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const float x0 = __uint_as_float(v[h * 8 + 2 * e]) - c, x1 = __uint_as_float(v[h * 8 + 2 * e + 1]) - c;
-      o[e] = (POLY && h == 1) ? pack_bf16x2(exp2_fma(x0), exp2_fma(x1)) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
+      float x0 = __uint_as_float(v[h * 8 + 2 * e]), x1 = __uint_as_float(v[h * 8 + 2 * e + 1]);
+      if (SHIFT) {
+        x0 -= c;
+        x1 -= c;
+      }
+      o[e] = (POLY && h == 1) ? pack_bf16x2(exp2_fma<SHIFT>(x0), exp2_fma<SHIFT>(x1)) : pack_bf16x2(ex2_approx(x0), ex2_approx(x1));
     }
     *reinterpret_cast<uint4*>(s_p + ((chunk + h) * TILE_M + trow) * 16) = make_uint4(o[0], o[1], o[2], o[3]);
   }
@@ -579,6 +599,8 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
     };
 
     float c = 0.0f;
+    bool shift = true;                                      // warp-uniform, per tile
+    const bool force_shift = (p.dbg & 4) != 0;              // debug bit 23: A/B and parity of the shifted path
     int c_tile = -1, epi_done = 0;
     int s_tile = 0, s_pi = grp;                             // (tile, part index) of `step`, advanced by two per iteration
     while (s_pi >= np) {
@@ -608,7 +630,9 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
 #pragma unroll
             for (int e = 0; e < 8; e++) ss = fmaf(f[e], f[e], ss);
           }
-          c = fminf(sqrtf(ss * maxk2) * 1.0001f + 1e-3f, 96.0f);
+          const float bound = sqrtf(ss * maxk2) * 1.0001f + 1e-3f;
+          c = fminf(bound, 96.0f);
+          shift = force_shift || __any_sync(0xffffffffu, !(bound < A2_NOSHIFT));     // (a NaN bound keeps the shifted path)
         }
       }
       ATT_STAMP(lg == 0 && lane == 0, step, 0);
@@ -626,15 +650,27 @@ __global__ void __launch_bounds__(A2_THREADS, 2) attention_tc_kernel(const AttnP
         tmem_ld32(t_s, va);
         tmem_ld_wait();
         tmem_ld32(t_s + 32, vb);
-        exp_store16<(A2_POLY_MASK >> 0) & 1>(va, c, pb, 0, trow);
-        exp_store16<(A2_POLY_MASK >> 1) & 1>(va + 16, c, pb, 2, trow);
-        tmem_ld_wait();
-        tmem_ld16(t_s + 64, va);
-        exp_store16<(A2_POLY_MASK >> 2) & 1>(vb, c, pb, 4, trow);
-        exp_store16<(A2_POLY_MASK >> 3) & 1>(vb + 16, c, pb, 6, trow);
-        tmem_ld_wait();
-        ATT_STAMP(lg == 0 && lane == 0, step, 2);
-        exp_store16<(A2_POLY_MASK >> 4) & 1>(va, c, pb, 8, trow);
+        if (shift) {
+          exp_store16<(A2_POLY_MASK >> 0) & 1, true>(va, c, pb, 0, trow);
+          exp_store16<(A2_POLY_MASK >> 1) & 1, true>(va + 16, c, pb, 2, trow);
+          tmem_ld_wait();
+          tmem_ld16(t_s + 64, va);
+          exp_store16<(A2_POLY_MASK >> 2) & 1, true>(vb, c, pb, 4, trow);
+          exp_store16<(A2_POLY_MASK >> 3) & 1, true>(vb + 16, c, pb, 6, trow);
+          tmem_ld_wait();
+          ATT_STAMP(lg == 0 && lane == 0, step, 2);
+          exp_store16<(A2_POLY_MASK >> 4) & 1, true>(va, c, pb, 8, trow);
+        } else {
+          exp_store16<(A2_POLY_NS_MASK >> 0) & 1, false>(va, c, pb, 0, trow);
+          exp_store16<(A2_POLY_NS_MASK >> 1) & 1, false>(va + 16, c, pb, 2, trow);
+          tmem_ld_wait();
+          tmem_ld16(t_s + 64, va);
+          exp_store16<(A2_POLY_NS_MASK >> 2) & 1, false>(vb, c, pb, 4, trow);
+          exp_store16<(A2_POLY_NS_MASK >> 3) & 1, false>(vb + 16, c, pb, 6, trow);
+          tmem_ld_wait();
+          ATT_STAMP(lg == 0 && lane == 0, step, 2);
+          exp_store16<(A2_POLY_NS_MASK >> 4) & 1, false>(va, c, pb, 8, trow);
+        }
       }
       fence_async_smem();     // P visible to the async proxy
       tc_fence_before();

@@ -858,7 +858,7 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
       ap.head_dim = head_dim;
       ap.n_dev = n_dev;
       ap.pdl = (dbg_desc & 1) ? 0 : 1;
-      ap.dbg = (dbg_desc >> 1) & 3;
+      ap.dbg = ((dbg_desc >> 1) & 3) | ((dbg_desc >> 21) & 4);     // bit23 -> force the shifted softmax
       ap.trace = (dbg_att_trace_cta >= 0 && ai == 1) ? d_trace : nullptr;
       ap.trace_cta = dbg_att_trace_cta;
       if (flush_chain(st)) return 1;

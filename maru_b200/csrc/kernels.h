@@ -158,7 +158,7 @@ struct AttnParams {
   int pitch, pos_rows;       // frame geometry (20 / 400, or the compact frame of a small board)
   const int* n_dev;
   int pdl;
-  int dbg;                   // bit0: swap LBO/SBO of the MN-major V descriptor, bit1: legacy mma.sync kernel
+  int dbg;                   // bit0: swap LBO/SBO of the MN-major V descriptor, bit1: legacy mma.sync kernel, bit2: always shift
   long long* trace;          // EXPERIMENTS builds: [64 steps][8] clock64 stamps of CTA trace_cta (tools/att_trace.py)
   int trace_cta;
 };

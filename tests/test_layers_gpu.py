@@ -110,6 +110,33 @@ def test_flow_kernel_matches_per_layer_launches(built_lib, model_dir):
             ev.close()
 
 
+def test_attention_with_and_without_the_row_shift(built_lib, model_dir):
+    """attention.cu: a warp whose rows' scores are bounded by 64 (|q_i| max_j |k_j|, log2 units) skips the subtraction
+    of the row shift c_i before the exponential; debug bit 23 forces the shifted path everywhere. Softmax is shift
+    invariant: the attention output (buffer 5) and the network outputs must agree to the rounding of P (bf16), on the
+    19x19 frame and on a compact frame."""
+    import maru_b200
+    from maru_b200 import synth
+    for name in ('b2c64', 'b4c128'):
+        ev = maru_b200.Evaluator(model_dir(name), gpu=0, max_batch=64, flags=maru_b200.capi.FLAG_NO_GRAPH)
+        try:
+            C = ev.info().channels
+            for size, n in ((19, 33), (9, 64)):
+                st = synth.random_states(n, size, seed=70 + size)
+                ev.debug_set(1, 32)
+                got = ev.forward_states(st)
+                gbuf = ev.debug_planes(5, n, C)
+                ev.debug_set(1, 32 | (1 << 23))
+                want = ev.forward_states(st)
+                wbuf = ev.debug_planes(5, n, C)
+                scale = np.abs(wbuf).max() + 1e-6
+                assert np.abs(gbuf - wbuf).max() <= 0.02 * scale + 1e-3, (name, size)
+                assert np.abs(got - want).max() < 2e-3, (name, size, float(np.abs(got - want).max()))
+                assert not np.array_equal(gbuf, wbuf), (name, size)      # the unshifted path really ran by default
+        finally:
+            ev.close()
+
+
 def test_ksplit_kernel_matches_conv_gemm(built_lib, model_dir):
     """C = 256 nets: the CTA-pair kernel conv_pair.cu (3x3 128 -> 128, cta_group::2), its fallback conv_ksplit.cu (half-slab
     pipeline) and the 256-channel-per-CTA projections of conv_wide.cu, all against conv_gemm (debug bit 4). Same MMAs, but channels 0-63 of all taps are accumulated before 64-127:
