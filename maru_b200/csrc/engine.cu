@@ -617,7 +617,7 @@ int Engine::conv(const ConvLayer& L, Act& in, Act* res, Act& out, int relu, int 
                     (res == nullptr || res->blocked == out.blocked);
   ConvParams pw = p;
   pw.blob = L.blob_wide;
-  for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) {
+  for (int rep = 0; rep < reps_now(); rep++) {
     if (pair) CK(launch_conv_pair(pp, L.cin, sm_count, st));
     else if (ksplit) CK(launch_conv_ksplit(p, sm_count, st));
     else if (wide) CK(launch_conv_wide(pw, sm_count, st));
@@ -653,6 +653,11 @@ void Engine::prof_begin(const char* name, int kind, int cin, int cout, int taps,
   }
   cudaEventRecord(prof_ev[2 * (prof->size() - 1)], st);
 }
+// how often the launch being enqueued is repeated: prof_reps for the launch a profiling pass is timing, else once
+int Engine::reps_now() const {
+  if (prof == nullptr) return 1;
+  return (prof_only < 0 || (int)prof->size() - 1 == prof_only) ? prof_reps : 1;
+}
 void Engine::prof_end(cudaStream_t st) {
   if (prof == nullptr) return;
   cudaEventRecord(prof_ev[2 * (prof->size() - 1) + 1], st);
@@ -687,23 +692,31 @@ int Engine::profile_states(const maru_state* d_states, float* d_out, int n, maru
     CK(cudaEventCreate(&e));
     prof_ev.push_back(e);
   }
-  // warm the caches / leave valid activations in every buffer, then time each launch of the
-  // sequence as the average of prof_reps back-to-back launches between one CUDA-event pair
+  // One CLEAN forward per launch of the sequence: in pass i only launch i is repeated prof_reps times back to back
+  // inside its CUDA-event pair, everything before it ran once, on the real activations. (Repeating EVERY launch in one
+  // pass, as round 1 did, piles the in-place residual layers up tenfold per layer: the later kernels were then timed on
+  // garbage — harmless for the convolutions, but attention takes a different path when the scores explode.)
   if (launch_all(KIND_STATES, d_states, d_out, n, nullptr, stream)) return 1;
-  spin_kernel<<<1, 1, 0, stream>>>(3000000);   // 3 ms head start for the CPU
   prof_reps = 10;
-  prof = &rec;
-  const int rc = launch_all(KIND_STATES, d_states, d_out, n, nullptr, stream);
-  prof = nullptr;
-  if (rc) return 1;
-  CK(cudaStreamSynchronize(stream));
-  // the repeated in-place residual layers left garbage behind: recompute a clean forward
-  if (launch_all(KIND_STATES, d_states, d_out, n, nullptr, stream)) return 1;
-  CK(cudaStreamSynchronize(stream));
-  for (size_t i = 0; i < rec.size(); i++) {
-    cudaEventElapsedTime(&rec[i].ms, prof_ev[2 * i], prof_ev[2 * i + 1]);
-    rec[i].ms /= (float)prof_reps;   // average duration of one launch
+  int n_launches = 1;
+  for (int i = 0; i < n_launches; i++) {
+    std::vector<maru_launch_time> pass;
+    pass.reserve(256);
+    spin_kernel<<<1, 1, 0, stream>>>(1000000);   // 1 ms head start for the CPU: the event deltas measure GPU time
+    prof = &pass;
+    prof_only = i;
+    const int rc = launch_all(KIND_STATES, d_states, d_out, n, nullptr, stream);
+    prof = nullptr;
+    prof_only = -1;
+    if (rc) return 1;
+    CK(cudaStreamSynchronize(stream));
+    if (i == 0) n_launches = (int)pass.size();
+    if (i >= (int)pass.size()) break;
+    cudaEventElapsedTime(&pass[i].ms, prof_ev[2 * i], prof_ev[2 * i + 1]);
+    pass[i].ms /= (float)prof_reps;              // average duration of one launch
+    rec.push_back(pass[i]);
   }
+  // the last pass repeated the last launch only: the buffers hold a clean forward
   *count = (int)rec.size();
   for (int i = 0; i < (int)rec.size() && i < max; i++) out[i] = rec[i];
   return 0;
@@ -719,7 +732,7 @@ int Engine::flush_chain(cudaStream_t st) {
     // a chain of one layer: the one-layer kernel (its launch boundary overlaps the neighbours' through PDL)
     prof_begin(pending_first->name.c_str(), pending_first->taps == 9 ? 1 : 2, pending_first->cin, pending_first->cout,
                pending_first->taps, pending_flops, pending_bytes, st);
-    for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
+    for (int rep = 0; rep < reps_now(); rep++)
       CK(launch_conv_gemm(pending_single, pending_first->cin, pending_first->nt, pending_first->taps, sm_count, st));
     prof_end(st);
     return 0;
@@ -737,7 +750,7 @@ int Engine::flush_chain(cudaStream_t st) {
   snprintf(name, sizeof name, "flow%d[%s..%d layers]", n_flow_launches++, pending_first->name.c_str(), pending_convs);
   prof_begin(name, 5, 0, 0, 0, pending_flops, pending_bytes, st);
   cudaError_t e = cudaSuccess;
-  for (int rep = 0; rep < (prof ? prof_reps : 1) && e == cudaSuccess; rep++) {
+  for (int rep = 0; rep < reps_now() && e == cudaSuccess; rep++) {
     pending.flag_base = flag_next;      // flags only grow: every launch of a forward gets its own value range
     flag_next += (unsigned)nl;
     e = launch_conv_flow(pending, sm_count, st);
@@ -823,7 +836,7 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
       launches_done++;
       n_launched++;
       prof_begin("crop", 0, C, C, 0, 0.0, (double)fwd.w * fwd.h * C * 2.0 * 2.0 * n, st);
-      for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
+      for (int rep = 0; rep < reps_now(); rep++)
         CK(launch_crop(o.p, h.p, mask, mask_c, C, o.blocked ? 1 : 0, h.blocked ? 1 : 0, rows_alloc, fwd.w, fwd.h, n, n_dev,
                        (dbg_desc & 1) ? 0 : 1, st));
       prof_end(st);
@@ -868,7 +881,7 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
         const double T = CELLS;
         prof_begin(("att" + std::to_string(ai - 1) + ".core").c_str(), 3, C, C, 0,
                    4.0 * T * T * C * n, T * 4.0 * C * 2.0 * n, st);
-        for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) CK(launch_attention(ap, st));
+        for (int rep = 0; rep < reps_now(); rep++) CK(launch_attention(ap, st));
         prof_end(st);
         o.flagged = false;   // written by a kernel without tile flags: consumers use the grid dependency
       }
@@ -904,7 +917,7 @@ int Engine::launch_trunk(int kind, const void* d_in, void* d_out, int n, const i
   n_launched++;
   prof_begin("heads", 4, Ch, 6, 0, (2.0 * CELLS * Ch * 6 + 2.0 * 2 * Ch * Cv + 2.0 * Cv * 3) * n,
              ((double)CELLS * Ch * 2 + (double)out_row_bytes(kind)) * n, st);
-  for (int rep = 0; rep < (prof ? prof_reps : 1); rep++) CK(launch_heads(hp, st));
+  for (int rep = 0; rep < reps_now(); rep++) CK(launch_heads(hp, st));
   prof_end(st);
   return 0;
 }
@@ -918,7 +931,7 @@ int Engine::launch_all(int kind, const void* d_in, void* d_out, int n, const int
   if (kind != KIND_PLANES) {
     prof_begin("encode", 0, 0, IN_PLANES, 0, 0.0,
                ((double)sizeof(maru_state) + (double)CELLS * IN_PLANES * 2.0) * n, st);
-    for (int rep = 0; rep < (prof ? prof_reps : 1); rep++)
+    for (int rep = 0; rep < reps_now(); rep++)
       CK(launch_encode_trunk(static_cast<const maru_state*>(d_in), x0.p, mask, rows_alloc, n, n_dev, st));
     prof_end(st);
   } else {

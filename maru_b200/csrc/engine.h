@@ -154,6 +154,8 @@ struct Engine {
   std::vector<cudaEvent_t> prof_ev;
   int prof_n = 0;
   int prof_reps = 1;        // each launch is repeated back to back this many times inside its event pair
+  int prof_only = -1;       // >= 0: only that launch of the sequence is repeated (profile_states: one clean pass per launch)
+  int reps_now() const;
   void prof_begin(const char* name, int kind, int cin, int cout, int taps, double flops, double bytes,
                   cudaStream_t st);
   void prof_end(cudaStream_t st);
