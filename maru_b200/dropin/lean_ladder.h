@@ -144,15 +144,30 @@ struct LeanBoard {
   // Board::play for an on-board point: number of captured stones, -1 if not allowed (board unchanged).
   // `captured` (optional, room for 361 cells) receives the cells that were emptied.
   int play(int idx, int color, int16_t* captured = nullptr) {
-    if (!enabled(idx, color)) return -1;
-    c[idx] = (int8_t)color;
+    // Legality (== enabled(idx, color): an empty neighbour, an own neighbour group with more than one liberty, or an
+    // opponent neighbour group with exactly one) and the capture test share their floods: an opponent group is captured
+    // by this stone exactly when it has ONE liberty before the stone is placed (that liberty is idx).
+    if (c[idx] != kEmpty) return -1;
+    if (idx == ko_index && color == ko_color) return -1;
     const int d[4] = {-1, -W, 1, W};
+    bool ok = false;
+    bool atari[4] = {false, false, false, false};
+    for (int k = 0; k < 4; k++) {
+      const int q = idx + d[k];
+      if (c[q] == kEmpty) ok = true;
+      else if (c[q] == -color && liberties_upto(q, 2) == 1) ok = atari[k] = true;
+    }
+    for (int k = 0; k < 4 && !ok; k++) {
+      const int q = idx + d[k];
+      if (c[q] == color && liberties_upto(q, 2) > 1) ok = true;
+    }
+    if (!ok) return -1;
+    c[idx] = (int8_t)color;
     int removed = 0;
     Group g;
     for (int k = 0; k < 4; k++) {
       const int q = idx + d[k];
-      if (c[q] != -color) continue;
-      if (liberties_upto(q, 1) != 0) continue;        // (most neighbours are alive: no need to collect their stones)
+      if (!atari[k] || c[q] != -color) continue;      // (already taken through another neighbour: same group)
       group(q, g);
       for (int i = 0; i < g.n_stones; i++) {
         c[g.stones[i]] = kEmpty;
@@ -161,8 +176,14 @@ struct LeanBoard {
       removed += g.n_stones;
       ko_index = q;
     }
-    group(idx, g);
-    if (removed != 1 || g.n_stones > 1 || g.n_libs > 1) {
+    // a ko needs exactly one captured stone AND a lone capturing stone with one liberty: the flood of the played stone's
+    // group is only made when a single stone was taken (most moves, and most steps of a ladder read-out, capture nothing)
+    bool ko = false;
+    if (removed == 1) {
+      group(idx, g);
+      ko = g.n_stones == 1 && g.n_libs == 1;
+    }
+    if (!ko) {
       ko_index = -1;
       ko_color = 0;
     } else {
@@ -183,8 +204,10 @@ struct LeanBoard {
     stack.push_back(*this);
     const int d[4] = {-1, -W, 1, W};
     while (!stack.empty()) {
-      LeanBoard board = stack.back();
+      // (one copy per searched board: the board popped here is also the one the escaping side plays on)
+      LeanBoard curr = stack.back();
       stack.pop_back();
+      const LeanBoard& board = curr;
       const int color = board.c[index];
       const int op = -color;
       board.group(index, g);
@@ -201,7 +224,6 @@ struct LeanBoard {
       }
       if (escaped) continue;
       // the escaping side extends at its (lowest-index) liberty
-      LeanBoard curr = board;
       const int curr_pos = g.libs[0];
       if (curr.play(curr_pos, color) < 0) return true;
       Group e;
@@ -210,9 +232,8 @@ struct LeanBoard {
       if (e.n_libs > 2) continue;
       // the chasing side tries both liberties (an illegal try leaves the board unchanged and is still searched)
       for (int i = 0; i < e.n_libs; i++) {
-        LeanBoard next = curr;
-        next.play(e.libs[i], op);
-        stack.push_back(next);
+        stack.push_back(curr);
+        stack.back().play(e.libs[i], op);
       }
     }
     return false;
